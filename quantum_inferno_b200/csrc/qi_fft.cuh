@@ -1,0 +1,306 @@
+// qi_fft.cuh -- shared-memory radix-8/4/2 FFT tile core and the multi-pass ("four-step")
+// large-FFT pass kernel built on it.
+//
+// Conventions
+//   * Forward = decimation-in-frequency, natural order in -> bit-reversed order out.
+//     Inverse = decimation-in-time, bit-reversed order in -> natural order out.
+//     A spectrum therefore lives in HBM at position p = bitrev_m(k); products are taken in
+//     that order and no transpose / permutation kernel ever runs.  (Replaces the three
+//     scipy.fft c2c calls inside scipy.signal.fftconvolve that
+//     reference quantum_inferno/styx_cwt.py:195 bottoms out in.)
+//   * A length-2^m transform is split into passes of 2^m_i points (m = sum m_i).  Pass i is a
+//     set of independent 2^m_i-point FFTs over "rows" r at element stride sR = 2^(bits below),
+//     followed (forward) / preceded (inverse) by the Cooley-Tukey twiddle w_(R*sR)^(inner*k).
+//   * A CTA holds a tile of R rows x TC columns in shared memory as tile[r*TP + c]
+//     (TP = TC+1 -> conflict-free both for column-wise butterflies and row-wise staging).
+//     Butterfly lanes run along the columns, so twiddles are warp-uniform broadcasts.
+#pragma once
+#include "qi_platform.cuh"
+
+namespace qi {
+
+enum { FFT_FWD = 0, FFT_INV = 1 };
+
+// ---------------------------------------------------------------- small DFTs in registers
+// Outputs are left in BIT-REVERSED slot order (slot brev(f) holds frequency f), which makes a
+// radix-8 step identical to three in-place radix-2 DIF steps.
+template <typename T, int DIR> QI_DEV cplx<T> rot90(cplx<T> a) {   // * (-i) forward, * (+i) inverse
+    return DIR == FFT_FWD ? mul_mi(a) : mul_pi(a);
+}
+template <typename T, int DIR> QI_DEV cplx<T> rot45(cplx<T> a) {   // * w8^1
+    const T h = (T)0.70710678118654752440;
+    return DIR == FFT_FWD ? mk<T>((a.re + a.im) * h, (a.im - a.re) * h)
+                          : mk<T>((a.re - a.im) * h, (a.im + a.re) * h);
+}
+template <typename T, int DIR> QI_DEV cplx<T> rot135(cplx<T> a) {  // * w8^3
+    const T h = (T)0.70710678118654752440;
+    return DIR == FFT_FWD ? mk<T>((a.im - a.re) * h, -(a.re + a.im) * h)
+                          : mk<T>(-(a.re + a.im) * h, (a.re - a.im) * h);
+}
+
+// DIF butterflies: natural slots in, bit-reversed slots out (sign by DIR).
+template <typename T, int DIR> QI_DEV void dif2(cplx<T>* a) {
+    cplx<T> t = a[0] - a[1]; a[0] = a[0] + a[1]; a[1] = t;
+}
+template <typename T, int DIR> QI_DEV void dif4(cplx<T>* a) {
+    cplx<T> b0 = a[0] + a[2], b2 = a[0] - a[2];
+    cplx<T> b1 = a[1] + a[3], b3 = rot90<T, DIR>(a[1] - a[3]);
+    a[0] = b0 + b1; a[1] = b0 - b1; a[2] = b2 + b3; a[3] = b2 - b3;
+}
+template <typename T, int DIR> QI_DEV void dif8(cplx<T>* a) {
+    cplx<T> b0 = a[0] + a[4], b4 = a[0] - a[4];
+    cplx<T> b1 = a[1] + a[5], b5 = rot45<T, DIR>(a[1] - a[5]);
+    cplx<T> b2 = a[2] + a[6], b6 = rot90<T, DIR>(a[2] - a[6]);
+    cplx<T> b3 = a[3] + a[7], b7 = rot135<T, DIR>(a[3] - a[7]);
+    cplx<T> c0 = b0 + b2, c2 = b0 - b2, c1 = b1 + b3, c3 = rot90<T, DIR>(b1 - b3);
+    cplx<T> c4 = b4 + b6, c6 = b4 - b6, c5 = b5 + b7, c7 = rot90<T, DIR>(b5 - b7);
+    a[0] = c0 + c1; a[1] = c0 - c1; a[2] = c2 + c3; a[3] = c2 - c3;
+    a[4] = c4 + c5; a[5] = c4 - c5; a[6] = c6 + c7; a[7] = c6 - c7;
+}
+// DIT butterflies: bit-reversed slots in, natural slots out (exact mirror of the above).
+template <typename T, int DIR> QI_DEV void dit2(cplx<T>* a) {
+    cplx<T> t = a[0] - a[1]; a[0] = a[0] + a[1]; a[1] = t;
+}
+template <typename T, int DIR> QI_DEV void dit4(cplx<T>* a) {
+    cplx<T> b0 = a[0] + a[1], b1 = a[0] - a[1];
+    cplx<T> b2 = a[2] + a[3], b3 = rot90<T, DIR>(a[2] - a[3]);
+    a[0] = b0 + b2; a[2] = b0 - b2; a[1] = b1 + b3; a[3] = b1 - b3;
+}
+template <typename T, int DIR> QI_DEV void dit8(cplx<T>* a) {
+    // slots: a[brev3(f)] holds frequency-ordered input f
+    cplx<T> c0 = a[0] + a[1], c1 = a[0] - a[1];
+    cplx<T> c2 = a[2] + a[3], c3 = rot90<T, DIR>(a[2] - a[3]);
+    cplx<T> c4 = a[4] + a[5], c5 = a[4] - a[5];
+    cplx<T> c6 = a[6] + a[7], c7 = rot90<T, DIR>(a[6] - a[7]);
+    cplx<T> b0 = c0 + c2, b2 = c0 - c2, b1 = c1 + c3, b3 = c1 - c3;
+    cplx<T> b4 = c4 + c6, b6 = rot90<T, DIR>(c4 - c6);
+    cplx<T> b5 = rot45<T, DIR>(c5 + c7), b7 = rot135<T, DIR>(c5 - c7);
+    a[0] = b0 + b4; a[4] = b0 - b4; a[1] = b1 + b5; a[5] = b1 - b5;
+    a[2] = b2 + b6; a[6] = b2 - b6; a[3] = b3 + b7; a[7] = b3 - b7;
+}
+
+QI_HD int brev3(int f) { return ((f & 1) << 2) | (f & 2) | ((f >> 2) & 1); }
+QI_HD int brev2(int f) { return ((f & 1) << 1) | ((f >> 1) & 1); }
+
+// ---------------------------------------------------------------- one radix-2^STEP stage on a tile
+// tile[r*TP + c], R = 2^logR rows, TC columns; tw[m] = exp(-2*pi*i*m/R), m in [0,R).
+// Block size 2^logB, sub-stride h = 2^(logB-STEP).
+template <typename T, int DIR, int STEP>
+QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int TC, int TP) {
+    constexpr int Q = 1 << STEP;
+    const int logH = logB - STEP;
+    const int h = 1 << logH;
+    const int ntask = (1 << (logR - STEP)) * TC;
+    const int twshift = logR - logB;
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+        const int c = task % TC;
+        const int u = task / TC;
+        const int j = u & (h - 1);
+        const int g = u >> logH;
+        cplx<T>* p = tile + (size_t)(((g << logB) + j) * TP + c);
+        const int stride = h * TP;
+        cplx<T> a[Q];
+        if (DIR == FFT_FWD) {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) a[i] = p[i * stride];
+            if (STEP == 3) dif8<T, DIR>(a); else if (STEP == 2) dif4<T, DIR>(a); else dif2<T, DIR>(a);
+#pragma unroll
+            for (int s = 0; s < Q; ++s) {
+                const int f = STEP == 3 ? brev3(s) : (STEP == 2 ? brev2(s) : s);
+                cplx<T> v = a[s];
+                if (f != 0) v = v * tw[(j * f) << twshift];
+                p[s * stride] = v;
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < Q; ++s) {
+                const int f = STEP == 3 ? brev3(s) : (STEP == 2 ? brev2(s) : s);
+                cplx<T> v = p[s * stride];
+                if (f != 0) v = mul_conj(v, tw[(j * f) << twshift]);
+                a[s] = v;
+            }
+            if (STEP == 3) dit8<T, DIR>(a); else if (STEP == 2) dit4<T, DIR>(a); else dit2<T, DIR>(a);
+#pragma unroll
+            for (int i = 0; i < Q; ++i) p[i * stride] = a[i];
+        }
+    }
+}
+
+// Full tile FFT.  All threads of the CTA must call it; it ends with a __syncthreads().
+template <typename T, int DIR>
+QI_DEV void tile_fft(cplx<T>* tile, const cplx<T>* tw, int logR, int TC, int TP) {
+    if (logR == 0) { __syncthreads(); return; }
+    const int rem = logR % 3;            // the odd-sized stage sits at the small-block end
+    if (DIR == FFT_FWD) {
+        int logB = logR;
+        while (logB >= 3 && logB - 3 >= rem) {
+            tile_stage<T, DIR, 3>(tile, tw, logR, logB, TC, TP);
+            __syncthreads();
+            logB -= 3;
+        }
+        if (logB == 2) { tile_stage<T, DIR, 2>(tile, tw, logR, 2, TC, TP); __syncthreads(); }
+        else if (logB == 1) { tile_stage<T, DIR, 1>(tile, tw, logR, 1, TC, TP); __syncthreads(); }
+    } else {
+        int logB = rem;
+        if (rem == 2) { tile_stage<T, DIR, 2>(tile, tw, logR, 2, TC, TP); __syncthreads(); }
+        else if (rem == 1) { tile_stage<T, DIR, 1>(tile, tw, logR, 1, TC, TP); __syncthreads(); }
+        while (logB < logR) {
+            logB += 3;
+            tile_stage<T, DIR, 3>(tile, tw, logR, logB, TC, TP);
+            __syncthreads();
+        }
+    }
+}
+
+// fill tw[m] = exp(-2*pi*i*m/R)
+template <typename T> QI_DEV void fill_twiddles(cplx<T>* tw, int logR) {
+    const int R = 1 << logR;
+    for (int m = threadIdx.x; m < R; m += blockDim.x) tw[m] = conj(unit_root<T>((unsigned long long)m, logR));
+}
+
+// ---------------------------------------------------------------- pass geometry
+struct PassGeom {
+    int logR;        // rows per FFT = 2^logR
+    int logS;        // row stride in elements = 2^logS (bits below this pass)
+    int logL;        // total transform length 2^logL
+    int TC;          // tile columns
+    // column id c in [0, L/R): outer = c >> logS, inner = c & (S-1); element = outer*R*S + r*S + inner
+};
+
+QI_HD i64 pass_elem(const PassGeom& g, int r, i64 col) {
+    const i64 inner = col & ((1ll << g.logS) - 1);
+    const i64 outer = col >> g.logS;
+    return (outer << (g.logR + g.logS)) + ((i64)r << g.logS) + inner;
+}
+
+// Generic pass kernel.
+//   Src:  cplx<T> load(i64 batch, i64 elem) const
+//   Dst:  void store(i64 batch, i64 elem, cplx<T> v);  void finish(i64 batch, unsigned char* scratch)
+// grid = (tiles_per_batch, batches); block = 256; dyn smem = (R*TP + R) * sizeof(cplx<T>) (+ Dst scratch)
+template <typename T, int DIR, class Src, class Dst>
+__global__ void __launch_bounds__(256)
+fft_pass_kernel(PassGeom g, Src src, Dst dst) {
+    QI_DYN_SMEM(smem_raw);
+    const int R = 1 << g.logR;
+    const int TC = g.TC, TP = g.TC + 1;
+    cplx<T>* tile = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* tw = tile + (size_t)R * TP;
+    const i64 batch = blockIdx.y;
+    const i64 col0 = (i64)blockIdx.x * TC;
+    const int nelem = R * TC;
+    const int twlog = g.logR + g.logS;           // modulus of the inter-pass twiddle
+
+    fill_twiddles<T>(tw, g.logR);
+
+    const bool row_major = (g.logS == 0);        // rows contiguous in memory -> lanes along r
+    for (int idx = threadIdx.x; idx < nelem; idx += blockDim.x) {
+        int r, c;
+        if (row_major) { r = idx & (R - 1); c = idx >> g.logR; }
+        else { c = idx % TC; r = idx / TC; }
+        const i64 col = col0 + c;
+        const i64 e = pass_elem(g, r, col);
+        cplx<T> v = src.load(batch, e);
+        if (DIR == FFT_INV && g.logS > 0) {
+            const unsigned long long inner = (unsigned long long)(col & ((1ll << g.logS) - 1));
+            const unsigned k = brev_bits((unsigned)r, g.logR);
+            if (inner * k) v = mul_conj(v, conj(unit_root<T>(inner * k, twlog)));
+        }
+        tile[r * TP + c] = v;
+    }
+    __syncthreads();
+    tile_fft<T, DIR>(tile, tw, g.logR, TC, TP);
+    for (int idx = threadIdx.x; idx < nelem; idx += blockDim.x) {
+        int r, c;
+        if (row_major) { r = idx & (R - 1); c = idx >> g.logR; }
+        else { c = idx % TC; r = idx / TC; }
+        const i64 col = col0 + c;
+        const i64 e = pass_elem(g, r, col);
+        cplx<T> v = tile[r * TP + c];
+        if (DIR == FFT_FWD && g.logS > 0) {
+            const unsigned long long inner = (unsigned long long)(col & ((1ll << g.logS) - 1));
+            const unsigned k = brev_bits((unsigned)r, g.logR);
+            if (inner * k) v = mul_conj(v, unit_root<T>(inner * k, twlog));
+        }
+        dst.store(batch, e, v);
+    }
+    dst.finish(batch, reinterpret_cast<unsigned char*>(tw + R));
+}
+
+// ---------------------------------------------------------------- host-side plan
+struct FftPlan {
+    int logL;
+    int npass;
+    int logR[4];     // forward order: pass 0 handles the TOP bits of the index
+    int logS[4];
+    int TC[4];
+};
+
+// max rows per pass chosen so that R*(TC+1)*sizeof(cplx) stays <= ~100 KB with TC >= 8
+inline FftPlan make_plan(int logL, int elem_bytes /* sizeof(cplx<T>) */) {
+    FftPlan p;
+    p.logL = logL;
+    const int maxlog = 10;  // 1024 rows per pass
+    int np = (logL + maxlog - 1) / maxlog;
+    if (np < 1) np = 1;
+    p.npass = np;
+    int rem = logL;
+    int below = logL;
+    for (int i = 0; i < np; ++i) {
+        int lr = (rem + (np - i) - 1) / (np - i);   // balanced split, larger first
+        p.logR[i] = lr;
+        below -= lr;
+        p.logS[i] = below;
+        rem -= lr;
+        // tile columns: target ~96 KB tile, power of two, between 1 and 32
+        long budget = 96 * 1024 / elem_bytes;
+        int tc = 1;
+        while (tc < 32 && (long)(1 << lr) * (2 * tc + 1) <= budget) tc *= 2;
+        long ncols = 1l << (logL - lr);
+        while (tc > ncols) tc /= 2;
+        if (tc < 1) tc = 1;
+        p.TC[i] = tc;
+    }
+    return p;
+}
+
+template <typename T> inline size_t pass_smem_bytes(int logR, int TC, size_t dst_scratch) {
+    return ((size_t)(1 << logR) * (TC + 1) + (size_t)(1 << logR)) * sizeof(cplx<T>) + dst_scratch;
+}
+
+// Launch one pass.  `pass` indexes the FORWARD order; an inverse transform runs passes npass-1 .. 0.
+template <typename T, int DIR, class Src, class Dst>
+inline void launch_pass(const FftPlan& plan, int pass, i64 nbatch, Src src, Dst dst, size_t dst_scratch,
+                        cudaStream_t stream) {
+    PassGeom g;
+    g.logR = plan.logR[pass];
+    g.logS = plan.logS[pass];
+    g.logL = plan.logL;
+    g.TC = plan.TC[pass];
+    const i64 ncols = 1ll << (plan.logL - g.logR);
+    dim3 grid((unsigned)(ncols / g.TC), (unsigned)nbatch, 1);
+    const size_t smem = pass_smem_bytes<T>(g.logR, g.TC, dst_scratch);
+#ifndef QI_EMUL
+    cudaFuncSetAttribute(fft_pass_kernel<T, DIR, Src, Dst>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    QI_LAUNCH((fft_pass_kernel<T, DIR, Src, Dst>), grid, dim3(256), smem, stream, g, src, dst);
+}
+
+// ---------------------------------------------------------------- plain sources / sinks
+template <typename T> struct SrcComplex {
+    const cplx<T>* buf; i64 batch_stride;
+    QI_DEV cplx<T> load(i64 b, i64 e) const { return buf[b * batch_stride + e]; }
+};
+template <typename T> struct DstComplex {
+    cplx<T>* buf; i64 batch_stride; T scale;
+    QI_DEV void store(i64 b, i64 e, cplx<T> v) const { buf[b * batch_stride + e] = v * scale; }
+    QI_DEV void finish(i64, unsigned char*) const {}
+};
+// real input of n_points per batch row, zero-extended to 2^logL
+template <typename T> struct SrcRealPad {
+    const T* sig; i64 batch_stride; i64 n_points;
+    QI_DEV cplx<T> load(i64 b, i64 e) const {
+        return mk<T>(e < n_points ? sig[b * batch_stride + e] : (T)0, (T)0);
+    }
+};
+
+}  // namespace qi
