@@ -1,0 +1,488 @@
+"""
+qi_oracle -- TEST INFRASTRUCTURE, NOT A PRODUCT PATH.
+
+A plain numpy (float64) restatement of the time-frequency hot path of ISLA-UH/quantum-inferno
+v1.1.3, written band-by-band so it also runs at sizes where the reference's own B x 2N tiles do
+not fit in host memory.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import it, and only as the checker or as the timed CPU baseline.
+The quantum_inferno_b200 package never imports it.
+
+Parity pin: every function here is checked against outputs of the *reference itself*
+(imported from /root/reference in the build container by oracle/make_golden.py, which wrote
+tests/golden/*.npz) in tests/test_oracle_golden.py.  The reference's own test-suite holds no
+vectors for this path except the commented-out band-table KAT of
+quantum_inferno/tests/test_scales_dyadic.py:8-21, which is pinned too.
+
+Citations are file:line relative to the reference checkout.  The only third-party arithmetic
+the reference uses on this path is scipy (>=1.15, pyproject.toml:20): signal.fftconvolve,
+signal.stft / welch, fft.fft/ifft/rfft; their published algorithms are restated here with
+numpy.fft only.
+"""
+import numpy as np
+
+EPS64 = float(np.finfo(np.float64).eps)      # scales_dyadic.py:16
+EPS32 = float(np.finfo(np.float32).eps)      # scales_dyadic.py:17
+G2 = 2.0                                     # scales_dyadic.py:53
+G3 = 10.0 ** 0.3                             # scales_dyadic.py:54
+M_OVER_N = 0.75 * np.pi                      # scales_dyadic.py:21
+ORDER_MIN = 0.75                             # scales_dyadic.py:97
+T0S = 1e-42                                  # scales_dyadic.py:57
+VALID_ORDERS = [0.75, 1, 1.5, 3, 6, 12, 24, 48]   # scales_dyadic.py:102
+
+
+# ----------------------------------------------------------------------------- scales_dyadic
+def order_checked(order):
+    """scales_dyadic.py:105-122 (print side effect dropped)."""
+    order = np.abs(order)
+    return ORDER_MIN if order < ORDER_MIN else order
+
+
+def cycles_from_order(order):
+    """scales_dyadic.py:125-141: M = 0.75*pi*N."""
+    return M_OVER_N * order_checked(order)
+
+
+def scale_from_frequency_hz(order, f_hz, fs):
+    """scales_dyadic.py:167-180 -> (scale_atom, omega)."""
+    omega = 2.0 * np.pi * f_hz / fs
+    return cycles_from_order(order) / omega, omega
+
+
+def log_frequency_hz_from_fft_points(fs, n_points, order, ref_hz=1.0, base=G3):
+    """scales_dyadic.py:355-393: ascending band centres ref*base^(-j/N)."""
+    log2_len = int(np.ceil(np.log2(n_points)))
+    mult = cycles_from_order(order)
+    n_over_log2g = order_checked(order) / np.log2(base)
+    log2_mult = np.log2(mult)
+    log2_ref = np.log2(fs / ref_hz)
+    j_lo = int(np.ceil(n_over_log2g * (np.log2(2.5) - log2_ref)))
+    j_hi = int(np.floor(n_over_log2g * (log2_len - log2_mult - log2_ref)))
+    j = np.arange(j_lo, j_hi + 1)
+    return np.flip(ref_hz * base ** (-j / order))
+
+
+def band_intervals_periods(order_in, base_in, ref_in, low_in, high_in):
+    """scales_dyadic.py:241-352 (warnings dropped)."""
+    ref, low, high, base, order = np.absolute([ref_in, low_in, high_in, base_in, order_in])
+    if not (base == G3 or base == G2) and base < 1.0:
+        base = G2
+    if order not in VALID_ORDERS and order < 0.75:
+        order = 1
+    edge = base ** (1.0 / (2.0 * order))
+    if low < T0S:
+        low = T0S / edge
+    if high < low:
+        low = high / base
+    if high == low:
+        high *= edge
+        low /= edge
+    n_max = np.round(order * np.log(high / ref) / np.log(base))
+    n_min = np.floor(order * np.log(low / ref) / np.log(base))
+    c_min = ref * np.power(base, n_min / order)
+    if (c_min < low) or (c_min / edge < low - EPS64):
+        n_min += 1
+    if n_max < n_min:
+        n_max = np.floor(np.log10(high) / np.log10(base))
+        n_min = n_max - order
+    band = np.arange(n_min, n_max + 1)
+    centre = ref * np.power(base * np.ones(band.shape), band / order)
+    start = centre / edge
+    end = centre * edge
+    return order, base, band, ref, (start + end) / 2.0, centre, start, end
+
+
+def band_frequency_low_high(order_in, base_in, ref_in, f_low, f_high, fs):
+    """scales_dyadic.py:183-238."""
+    s_ref = 1 / ref_in
+    s_nyq = 2 / fs
+    s_low = 1 / f_high
+    if s_low < s_nyq:
+        s_low = s_nyq
+    s_high = 1 / f_low
+    order, base, band, ref, _, centre, start, end = band_intervals_periods(order_in, base_in, s_ref, s_low, s_high)
+    f_end = 1 / start
+    f_start = 1 / end
+    return order, base, -band, 1 / ref, (f_end + f_start) / 2.0, 1 / centre, f_start, f_end
+
+
+# ----------------------------------------------------------------------------- styx_cwt
+def wavelet_amplitude(scale):
+    """styx_cwt.py:29-40 (kept un-simplified as the source asks)."""
+    a_norm = (np.pi * scale ** 2) ** (-1 / 4)
+    a_spect = (4 * np.pi * scale ** 2) ** (-1 / 4) * a_norm
+    return a_norm, a_spect
+
+
+def gabor_atom_centered(order, n_points, f_hz, fs, dictionary_type="norm"):
+    """One band of styx_cwt.py:113-144 / :68-110: atom centred at (n_points-1)/2 samples.
+    Returns (atom[n_points] complex128, scale, omega, amp)."""
+    t = np.arange(n_points) / fs
+    x = fs * (t - t[-1] / 2.0)                       # styx_cwt.py:65,132,135
+    scale, omega = scale_from_frequency_hz(order, f_hz, fs)
+    gabor = np.exp(-0.5 * (x / scale) ** 2) * np.exp(1j * omega * x)    # styx_cwt.py:107
+    a_norm, a_spect = wavelet_amplitude(scale)
+    if dictionary_type == "spect":
+        amp = a_spect
+    elif dictionary_type == "unit":
+        amp = 1.0
+    else:
+        amp = a_norm
+    return amp * gabor, scale, omega, amp
+
+
+def cwt_band(sig_fft_2n, order, n_points, f_hz, fs, dictionary_type="norm"):
+    """One row of styx_cwt.py:195-196: fftconvolve(sig, conj(fliplr(atom)), 'same'), i.e.
+    ifft(fft(x,2N)*fft(h,2N))[(N-1)//2 : (N-1)//2+N] (scipy _freq_domain_conv + _centered)."""
+    atom, _, _, _ = gabor_atom_centered(order, n_points, f_hz, fs, dictionary_type)
+    h = np.conj(atom[::-1])
+    full = np.fft.ifft(sig_fft_2n * np.fft.fft(h, 2 * n_points))
+    s = (n_points - 1) // 2
+    return full[s:s + n_points]
+
+
+def cwt_complex_any_scale_pow2(order, sig, fs, cwt_type="fft", dictionary_type="norm"):
+    """styx_cwt.py:147-198 -> (frequency_hz[B], time_s[N], cwt[B,N] complex128)."""
+    sig = np.asarray(sig, dtype=np.float64)
+    n = len(sig)
+    freqs = log_frequency_hz_from_fft_points(fs, n, order)
+    xf = np.fft.fft(sig, 2 * n)
+    out = np.empty((len(freqs), n), dtype=np.complex128)
+    for b, f in enumerate(freqs):
+        out[b] = cwt_band(xf, order, n, f, fs, dictionary_type)
+    return freqs, np.arange(n) / fs, out
+
+
+# ----------------------------------------------------------------------------- styx_stx
+def stx_complex_any_scale_pow2(order, sig, fs):
+    """styx_stx.py:195-236."""
+    sig = np.asarray(sig, dtype=np.float64)
+    n = len(sig)
+    freqs = log_frequency_hz_from_fft_points(fs, n, order)
+    xf = np.fft.fft(sig)
+    xf2 = np.concatenate([xf, xf])
+    f_fft = np.fft.fftfreq(n, 1 / fs)
+    w_fft = 2 * np.pi * f_fft / fs
+    w_stx = 2 * np.pi * freqs / fs
+    sigma = cycles_from_order(order) / w_stx
+    out = np.empty((len(freqs), n), dtype=np.complex128)
+    for b, f in enumerate(freqs):
+        idx = int(np.abs(f_fft - f).argmin())                      # styx_stx.py:233 (first minimum)
+        win = np.exp(-0.5 * (sigma[b] ** 2.0) * (w_fft ** 2.0))    # styx_stx.py:223-225
+        out[b] = np.fft.ifft(xf2[idx:idx + n] * win)
+    return freqs, np.arange(n) / fs, out
+
+
+def stx_shift_indices(order, n, fs):
+    """Bit-exact integer part of styx_stx.py:231-233."""
+    freqs = log_frequency_hz_from_fft_points(fs, n, order)
+    f_fft = np.fft.fftfreq(n, 1 / fs)
+    return np.array([int(np.abs(f_fft - f).argmin()) for f in freqs], dtype=np.int64)
+
+
+def tfr_stx_fft(sig, dt, order=8.0, n_fft_in=None, frequency_min=None, frequency_max=None, frequency_step=None,
+                factor_q=0.0, power_p=0.0, power_r=1.0, is_geometric=False, is_inferno=False,
+                base=G3, ref=1.0):
+    """styx_stx.py:52-192, on its working domain n_fft_in == len(sig) == 2^m."""
+    sig = np.asarray(sig, dtype=np.float64)
+    n = sig.shape[-1]
+    if n_fft_in is None:
+        raise TypeError("'<' not supported between instances of 'NoneType' and 'int'")   # styx_stx.py:30
+    if n_fft_in < n:
+        raise ValueError(f"n_fft cannot be smaller than signal size. Got {n_fft_in} < {n}.")
+    if n_fft_in != n:
+        raise TypeError("unsupported padding path (styx_stx.py:44)")
+    fs = 1 / dt
+    cycles = 12.0 / 5.0 * order
+    xf = np.fft.fft(sig)
+    xf2 = np.concatenate([xf, xf], axis=-1)
+    f_fft = np.fft.fftfreq(n, dt)
+    w_fft = 2 * np.pi * f_fft / fs
+    f_min_nth = cycles / (n / fs)
+    if frequency_min is None:
+        frequency_min = f_min_nth
+    if frequency_max is None:
+        frequency_max = fs / 2.0
+    i0 = np.abs(f_fft - frequency_min).argmin()
+    i1 = np.abs(f_fft - frequency_max).argmin()
+    f_start, f_stop = f_fft[i0], f_fft[i1]
+    if frequency_step is None:
+        frequency_step = (frequency_max - frequency_min) * 2.0 / len(f_fft)
+    f_stx = np.arange(f_start, f_stop, frequency_step)
+    if is_geometric is True:
+        if is_inferno is True:
+            f_stx = band_frequency_low_high(order, base, ref, f_start, f_stop, fs)[5]
+        else:
+            n_bands = int(np.log2(f_stop / f_start) * order)
+            f_stx = np.logspace(np.log2(f_start), np.log2(f_stop), num=n_bands, base=base)
+    nb = len(f_stx)
+    f_snap = np.empty(nb)
+    windows = np.empty((nb, n), dtype=np.complex128)
+    tfr = np.empty((nb, n), dtype=np.complex128)
+    psd = np.empty((nb, n))
+    for b, f in enumerate(f_stx):
+        idx = np.abs(f_fft - f).argmin()
+        f_snap[b] = f_fft[idx]
+        w_sx = 2 * np.pi * f_snap[b] / fs
+        if w_sx == 0.0:
+            raise TypeError("object of type 'int' has no len()")     # styx_stx.py:173
+        sigma = cycles / w_sx * ((1 + factor_q * (w_sx ** power_p)) * (w_sx ** (1 - power_r)))
+        windows[b] = np.exp(-0.5 * (sigma ** 2.0) * (w_fft ** 2.0))
+        tfr[b] = np.fft.ifft(xf2[idx:idx + n] * windows[b])
+        psd[b] = np.abs(tfr[b]) ** 2 + EPS64
+    return tfr, psd, f_stx, f_snap, windows
+
+
+# ----------------------------------------------------------------------------- styx_fft (scipy.signal.stft / welch)
+def window_periodic(kind, param, n):
+    """scipy.signal.get_window((kind, param), n) with fftbins=True: the symmetric n+1 window minus
+    its last sample.  kind in {'tukey','gaussian'} (styx_fft.py:178,218,257)."""
+    m = n + 1
+    k = np.arange(m)
+    if kind == "tukey":
+        alpha = param
+        if alpha <= 0:
+            w = np.ones(m)
+        elif alpha >= 1.0:
+            w = 0.5 - 0.5 * np.cos(2.0 * np.pi * k / (m - 1))      # hann
+        else:
+            width = int(np.floor(alpha * (m - 1) / 2.0))
+            k1 = k[0:width + 1]
+            k3 = k[m - width - 1:]
+            w1 = 0.5 * (1 + np.cos(np.pi * (-1 + 2.0 * k1 / alpha / (m - 1))))
+            w2 = np.ones(m - 2 * width - 2)
+            w3 = 0.5 * (1 + np.cos(np.pi * (-2.0 / alpha + 1 + 2.0 * k3 / alpha / (m - 1))))
+            w = np.concatenate((w1, w2, w3))
+    elif kind == "gaussian":
+        x = k - (m - 1.0) / 2.0
+        w = np.exp(-0.5 * (x / param) ** 2)
+    else:
+        raise ValueError(kind)
+    return w[:-1]
+
+
+def _frames(x, nperseg, noverlap):
+    step = nperseg - noverlap
+    nfr = (x.shape[-1] - noverlap) // step
+    idx = np.arange(nperseg)[None, :] + step * np.arange(nfr)[:, None]
+    return x[..., idx]                                             # [..., frame, sample]
+
+
+def stft_scipy(x, fs, window, nperseg, noverlap, nfft):
+    """scipy.signal.stft(x, fs, window, nperseg, noverlap, nfft, detrend='constant',
+    return_onesided=True, boundary='zeros', padded=True, axis=-1, scaling='spectrum')
+    -- _spectral_helper(mode='stft'), as called at styx_fft.py:175-187 / :215-227."""
+    x = np.asarray(x, dtype=np.float64)
+    win = window_periodic(window[0], window[1], nperseg)
+    half = nperseg // 2
+    pad = [(0, 0)] * (x.ndim - 1)
+    x = np.pad(x, pad + [(half, half)])                            # boundary='zeros'
+    step = nperseg - noverlap
+    nadd = (-(x.shape[-1] - nperseg) % step) % nperseg             # padded=True
+    x = np.pad(x, pad + [(0, nadd)])
+    fr = _frames(x, nperseg, noverlap)
+    fr = fr - fr.mean(axis=-1, keepdims=True)                      # detrend='constant'
+    z = np.fft.rfft(fr * win, n=nfft, axis=-1) * (1.0 / win.sum())
+    t = np.arange(nperseg / 2, x.shape[-1] - nperseg / 2 + 1, step) / float(fs) - (nperseg / 2) / fs
+    f = np.fft.rfftfreq(nfft, 1 / fs)
+    return f, t, np.moveaxis(z, -1, -2)                            # [..., freq, time]
+
+
+def _pow2_defaults(segment, overlap, nfft):
+    if nfft is None:
+        nfft = int(2 ** np.ceil(np.log2(segment)))
+    if overlap is None:
+        overlap = int(segment / 2)
+    return overlap, nfft
+
+
+def stft_complex_pow2(sig, fs, segment_points, overlap_points=None, nfft_points=None, alpha=0.25):
+    """styx_fft.py:152-187."""
+    overlap_points, nfft_points = _pow2_defaults(segment_points, overlap_points, nfft_points)
+    return stft_scipy(sig, fs, ("tukey", alpha), segment_points, overlap_points, nfft_points)
+
+
+def gtx_complex_pow2(sig, fs, segment_points, gaussian_sigma=None, overlap_points=None, nfft_points=None):
+    """styx_fft.py:190-227."""
+    overlap_points, nfft_points = _pow2_defaults(segment_points, overlap_points, nfft_points)
+    if gaussian_sigma is None:
+        gaussian_sigma = int(segment_points / 4)
+    return stft_scipy(sig, fs, ("gaussian", gaussian_sigma), segment_points, overlap_points, nfft_points)
+
+
+def welch_power_pow2(sig, fs, segment_points, nfft_points=None, overlap_points=None, alpha=0.25):
+    """styx_fft.py:230-266: scipy.signal.welch(scaling='spectrum', average='mean', detrend='constant')
+    = _spectral_helper(mode='psd', boundary=None, padded=False) then mean over segments."""
+    overlap_points, nfft_points = _pow2_defaults(segment_points, overlap_points, nfft_points)
+    x = np.asarray(sig, dtype=np.float64)
+    win = window_periodic("tukey", alpha, segment_points)
+    fr = _frames(x, segment_points, overlap_points)
+    fr = fr - fr.mean(axis=-1, keepdims=True)
+    z = np.fft.rfft(fr * win, n=nfft_points, axis=-1)
+    p = (np.conjugate(z) * z).real * (1.0 / win.sum() ** 2)
+    if nfft_points % 2:
+        p[..., 1:] *= 2
+    else:
+        p[..., 1:-1] *= 2
+    return np.fft.rfftfreq(nfft_points, 1 / fs), p.mean(axis=-2)
+
+
+def get_num_points_ceil_log2(fs, duration_s):
+    """utilities/calculations.py:187-205 with rounding_type='ceil', output_unit='log2'."""
+    return int(np.ceil(np.log2(fs * duration_s)))
+
+
+def stft_from_sig(sig, fs, order, center_frequency_hz=None, octaves_below_center=4):
+    """styx_fft.py:14-57 -> (stft, stft_bits, time_s, frequency_hz)."""
+    if center_frequency_hz is None:
+        center_frequency_hz = fs * 0.075
+    f_ave = center_frequency_hz / octaves_below_center
+    nd = 2 ** get_num_points_ceil_log2(fs, cycles_from_order(order) / f_ave)
+    if len(sig) < nd:
+        raise ValueError(f"Signal length: {len(sig)} is less than time_fft_nd: {nd}")
+    f, t, z = stft_complex_pow2(sig, fs, nd, alpha=1.0)
+    z = z * (2 * np.sqrt(np.pi) / nd)
+    return z, np.log2(np.abs(z) + EPS64), t, f
+
+
+# ----------------------------------------------------------------------------- cwt_atoms
+def chirp_mqg_from_n(order, index_shift=0, base=G2):
+    """cwt_atoms.py:122-144 -> (cycles M, Q, gamma)."""
+    if order < 0.7:
+        order = 3.0
+    edge = base ** (1.0 / 2.0 / order)
+    q = 1.0 / (edge - 1.0 / edge)
+    gamma = np.sqrt(np.log(2)) * (1 - np.log(2) * (index_shift / np.pi) ** 2) ** (-0.5)
+    return 2 * q * gamma, q, gamma
+
+
+def chirp_atom_centered(order, n_points, f_hz, fs, index_shift=0, base=G2, dictionary_type="norm"):
+    """cwt_atoms.py:303-340 + :16-50 for one band."""
+    t = np.arange(n_points) / fs
+    x = fs * (t - t[-1] / 2.0)
+    m, _, gamma = chirp_mqg_from_n(order, index_shift, base)
+    scale = m * fs / f_hz / (2.0 * np.pi)                                      # cwt_atoms.py:158
+    p = (1 - 1j * index_shift * gamma / np.pi) / (2 * scale ** 2)               # cwt_atoms.py:211
+    a_norm = 1 / np.pi ** 0.25 * 1 / np.sqrt(scale)                             # cwt_atoms.py:224
+    a_spect = np.sqrt(np.abs(p) / np.pi)                                        # cwt_atoms.py:225
+    atom = np.exp(-p * x ** 2) * np.exp(1j * m * x / scale)
+    return (a_norm if dictionary_type == "norm" else a_spect) * atom
+
+
+def cwt_chirp_complex(order, sig, f_low, fs, f_high=1.0e42, cwt_type="fft", index_shift=0, ref=1.0, base=G2,
+                      dictionary_type="norm"):
+    """cwt_atoms.py:343-444 -> (cwt, cwt_bits, time_s, frequency_hz)."""
+    sig = np.asarray(sig, dtype=np.float64)
+    n = len(sig)
+    if f_high > fs / 2.0:
+        f_high = fs / 2.0
+    order_nth, base_out, _, _, _, f_desc, _, _ = band_frequency_low_high(order, base, ref, f_low, f_high, fs)
+    nb = len(f_desc)
+    out = np.empty((nb, n), dtype=np.complex128)
+    if cwt_type == "fft":
+        xf = np.fft.fft(sig)
+        for b in range(nb):
+            a = chirp_atom_centered(order_nth, n, f_desc[b], fs, index_shift, base_out, dictionary_type)
+            raw = np.fft.ifft(xf * np.conj(np.fft.fft(a)))
+            out[b] = np.append(raw[n // 2:], raw[0:n // 2])                   # cwt_atoms.py:421
+    elif cwt_type == "conv":
+        xf2 = np.fft.fft(sig, 2 * n)
+        for b in range(nb):
+            a = chirp_atom_centered(order_nth, n, f_desc[b], fs, index_shift, base_out, dictionary_type)
+            # scipy.signal.convolve(sig, conj(a)[::-1], 'same') == linear convolution, centred slice
+            full = np.fft.ifft(xf2 * np.fft.fft(np.conj(a)[::-1], 2 * n))
+            s = (n - 1) // 2
+            out[b] = full[s:s + n]
+    else:
+        raise ValueError(f"Incorrect cwt_type: {cwt_type} specified in cwt_chirp_complex")
+    out = np.flipud(out)
+    return out, np.log2(np.abs(out) + EPS64), np.arange(n) / fs, np.flip(f_desc)
+
+
+def cwt_chirp_from_sig(sig, fs, order=3, cwt_type="fft", index_shift=0, ref=1.0, base=G2, dictionary_type="norm"):
+    """cwt_atoms.py:447-486."""
+    m, _, _ = chirp_mqg_from_n(order, index_shift, base)
+    f_min = 1 / ((len(sig) / fs) / m)                                          # cwt_atoms.py:253-255
+    return cwt_chirp_complex(order, sig, f_min, fs, fs / 2.0, cwt_type, index_shift, ref, base, dictionary_type)
+
+
+# ----------------------------------------------------------------------------- tfr_info
+class ShannonStft:
+    """tfr_info.py:203-228."""
+
+    def __init__(self, pdf, deg_free):
+        self.info = -np.log2(pdf + EPS64)
+        self.shannon_bits = pdf * self.info
+        self.ref_bits = np.log2(deg_free) / deg_free
+        self.isnr = np.log2(deg_free) - self.info
+        self.esnr = self.shannon_bits / self.ref_bits
+
+
+def shannon_stft_from_tfr_power(p):
+    """tfr_info.py:231-236."""
+    return ShannonStft(p / np.sum(p), p.shape[0] * p.shape[1])
+
+
+def shannon_stft_per_time(p):
+    """tfr_info.py:239-248: eps is added to the reciprocal of the column sums."""
+    return ShannonStft((1 / np.sum(p, axis=0) + EPS64)[None, :] * p, p.shape[0])
+
+
+def shannon_stft_per_freq(p):
+    """tfr_info.py:251-260."""
+    return ShannonStft((1 / np.sum(p, axis=1) + EPS64)[:, None] * p, p.shape[1])
+
+
+def scale_power_bits(p):
+    """tfr_info.py:65-79."""
+    b = np.log2(p + EPS64)
+    return b - np.max(b)
+
+
+def power_dynamics_scaled_bits(p):
+    """tfr_info.py:82-94."""
+    return scale_power_bits(p), scale_power_bits(np.sum(p, axis=0)), scale_power_bits(np.sum(p, axis=1))
+
+
+class Shannon1D:
+    """tfr_info.py:97-135 (EPS32 inside the log)."""
+
+    def __init__(self, marginal):
+        self.marginal = marginal
+        self.info = -np.log2(marginal + EPS32)
+        self.entropy = marginal * self.info
+        self.ref_entropy = np.log2(len(marginal)) / len(marginal)
+        self.isnr = np.log2(len(self.info)) - self.info
+        self.esnr = self.entropy / self.ref_entropy
+
+
+def shannon_tdr(sig):
+    """tfr_info.py:138-151."""
+    s = sig / np.sqrt(np.sum(sig ** 2))
+    out = Shannon1D(s ** 2)
+    out.sig = s
+    return out
+
+
+def shannon_fft(sig):
+    """tfr_info.py:163-181."""
+    z = np.fft.rfft(sig)
+    p = np.abs(z) ** 2
+    out = Shannon1D(p / np.sum(p))
+    out.sig = z
+    out.angle_rads = np.unwrap(np.angle(z))
+    out.frequency = np.arange(len(z)) / len(z) / 2.0
+    return out
+
+
+# ----------------------------------------------------------------------------- fused north-star quantity
+def cwt_power_entropy(order, sig, fs, dictionary_type="norm"):
+    """The north-star composite: styx_cwt.py:147-198 -> |.|^2 -> tfr_info.py:231-236 and :251-260,
+    evaluated band-by-band with a two-pass total so it runs at any record length.
+    Returns dict(freq, power[B,N], info[B,N], band_sum[B], total, entropy_bits (sum of shannon_bits),
+    band_entropy_bits[B] (per-frequency ShannonStftPerFreq row sums))."""
+    freqs, _, c = cwt_complex_any_scale_pow2(order, sig, fs, dictionary_type=dictionary_type)
+    p = np.abs(c) ** 2
+    g = shannon_stft_from_tfr_power(p)
+    pf = shannon_stft_per_freq(p)
+    return dict(freq=freqs, power=p, info=g.info, band_sum=p.sum(axis=1), total=float(p.sum()),
+                entropy_bits=float(g.shannon_bits.sum()), band_entropy_bits=pf.shannon_bits.sum(axis=1))
