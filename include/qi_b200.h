@@ -43,6 +43,50 @@ const char* qi_last_cuda_error(void);
  * in == out is allowed. */
 int qi_fft_c2c(const void* in, void* out, int64_t batch, int log2n, int inverse, int dtype, void* stream);
 
+/* ---- Gabor-atom CWT by FFT convolution -------------------------------------------------------
+ * Replaces quantum_inferno/styx_cwt.py:147-198 (cwt_complex_any_scale_pow2: wavelet_centered_4cwt
+ * :113-144 + scipy.signal.fftconvolve :195) and quantum_inferno/cwt_atoms.py:343-444
+ * (cwt_chirp_complex, "fft" :406-421 and "conv" :423-435 branches).
+ *
+ * One band = one atom  a(x) = amp * exp(-(p_re + i p_im) x^2) * exp(i omega x),
+ * x = fs*(m/fs - ((n_points-1)/fs)/2), m = 0..n_points-1 (the reference's own rounding of the
+ * centred time axis, styx_cwt.py:65,132,135 / cwt_atoms.py:227-236).
+ *   analytic = 1 : the atom's frequency response is synthesised on the fly inside the inverse-FFT
+ *                  kernel (requires p_im == 0 and a Gaussian that has decayed at the record edge);
+ *   analytic = 0 : the truncated time-domain atom is transformed once (shared by all channels)
+ *                  and multiplied from HBM -- exact for any atom.
+ */
+typedef struct {
+    double omega;
+    double p_re;
+    double p_im;
+    double amp;
+    int32_t analytic;
+    int32_t reserved;
+} QiAtomBand;
+
+/* conv_mode */
+#define QI_CONV_LINEAR_SAME 0   /* out = fftconvolve(sig, conj(atom)[::-1], 'same')  (styx_cwt.py:195, cwt_atoms.py:435) */
+#define QI_CONV_CIRC_CORR 1     /* out = roll(ifft(fft(sig)*conj(fft(atom))), -n/2)  (cwt_atoms.py:406-421); n = 2^m */
+
+size_t qi_cwt_workspace_bytes(int64_t n_channels, int64_t n_points, int n_bands, int n_table_bands,
+                              int bands_per_group, int conv_mode, int dtype);
+
+/* sig        : real [n_channels, n_points] rows `sig_stride` elements apart
+ * bands      : HOST array of n_bands descriptors
+ * out_cwt    : complex [n_channels, n_bands, n_points] or NULL
+ * out_power  : real    [n_channels, n_bands, n_points] (|cwt|^2) or NULL
+ * band_sum   : double  [n_channels, n_bands] (sum over time of |cwt|^2, fp64 accumulation) or NULL
+ * workspace  : >= qi_cwt_workspace_bytes(...) bytes, 256-byte aligned */
+int qi_cwt_fft(const void* sig, int64_t n_channels, int64_t n_points, int64_t sig_stride,
+               const QiAtomBand* bands, int n_bands, double fs, int conv_mode, int dtype,
+               void* out_cwt, void* out_power, double* band_sum,
+               void* workspace, size_t workspace_bytes, int bands_per_group, void* stream);
+
+/* Time-domain atoms themselves (styx_cwt.py:113-144 wavelet_centered_4cwt): out complex [n_bands, n_points] */
+int qi_atoms_time(const QiAtomBand* bands, int n_bands, int64_t n_points, double fs, int dtype,
+                  void* out_atoms, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,344 @@
+// qi_cwt.cu -- Gabor / chirp atom CWT by FFT convolution (exact path).
+//
+//   forward : one batched FFT per record (real signal zero-extended to L >= 2N-1), spectrum kept in
+//             bit-reversed order in HBM.
+//   per band: first inverse pass reads the record spectrum, multiplies by the band response --
+//             synthesised ON THE FLY from (omega, scale) for Gaussian atoms that have decayed at the
+//             record edge, or read from a table made by transforming the truncated time-domain atom
+//             once for all channels -- and the last inverse pass fuses the 'same' slice, |.|^2 and the
+//             fp64 per-band power sum into its store.
+//
+// Reference arithmetic replaced: quantum_inferno/styx_cwt.py:101-107 (atoms), :195-196 (fftconvolve),
+// quantum_inferno/cwt_atoms.py:406-435.
+#include "qi_fft.cuh"
+#include "qi_host.h"
+#include "qi_reduce.cuh"
+
+#include <vector>
+#include <math.h>
+
+namespace qi {
+
+struct DevBand {
+    double gain;        // analytic: amp*sqrt(pi/p_re)/L ; table: 1/L
+    double g;           // analytic: u = g*(k - kappa + j*L), g = (2*pi/L)/sqrt(2*p_re)
+    double kappa_frac;
+    long long kappa_int;
+    long long table_off;   // element offset into the table buffer, -1 = analytic
+    // time-domain atom (table bands)
+    double omega, p_re, p_im, amp;
+};
+
+struct CwtGeom {
+    i64 n_points;      // N
+    i64 n_channels;    // C
+    int n_bands;       // B
+    int logL;
+    int half_shift;    // 1 if the 'same' slice leaves a half-sample offset (N even)
+    int conv_mode;
+    i64 d_min, d_max;  // kernel lag range placed circularly (linear mode)
+    i64 centre_idx;    // (N-1)//2
+    double fs;
+};
+
+// ---------------------------------------------------------------- on-the-fly Gabor response
+template <typename T>
+QI_DEV cplx<T> gabor_response(const DevBand& b, i64 k, int logL, int half_shift) {
+    const T g = (T)b.g;
+    const T dk = (T)(k - b.kappa_int) - (T)b.kappa_frac;
+    const T Lf = (T)(1ll << logL);
+    T acc = (T)0;
+#pragma unroll
+    for (int j = -2; j <= 2; ++j) {
+        const T u = g * (dk + (T)j * Lf);
+        const T e = exp((T)-0.5 * u * u);
+        acc += (half_shift && (j & 1)) ? -e : e;
+    }
+    acc *= (T)b.gain;
+    if (!half_shift) return mk<T>(acc, (T)0);
+    // exp(-i*theta_k/2) = exp(-i*pi*k/L)
+    const cplx<T> ph = conj(unit_root<T>((unsigned long long)k, logL + 1));
+    return ph * acc;
+}
+
+// ---------------------------------------------------------------- time-domain atom sample (double)
+// x replicates the reference's rounding: fs*(m/fs - ((N-1)/fs)/2)
+QI_DEV void atom_sample(const DevBand& b, i64 m, i64 n_points, double fs, double* re, double* im) {
+    const double t = (double)m / fs;
+    const double off = ((double)(n_points - 1) / fs) / 2.0;
+    const double x = fs * (t - off);
+    const double env = b.amp * exp(-b.p_re * x * x);
+    const double ph = b.omega * x - b.p_im * x * x;
+    double s, c;
+    sincos(ph, &s, &c);
+    *re = env * c;
+    *im = env * s;
+}
+
+// Source for the atom-table forward FFT.  batch = table band index.
+template <typename T> struct SrcAtomKernel {
+    const DevBand* bands; const int* table_band; CwtGeom geo;
+    QI_DEV cplx<T> load(i64 batch, i64 e) const {
+        const DevBand& b = bands[table_band[batch]];
+        double re, im;
+        if (geo.conv_mode == QI_CONV_LINEAR_SAME) {
+            const i64 L = 1ll << geo.logL;
+            i64 d;
+            if (e <= geo.d_max) d = e;
+            else if (e - L >= geo.d_min) d = e - L;
+            else return mk<T>((T)0, (T)0);
+            const i64 m = d + geo.centre_idx;          // index into h = conj(flip(atom))
+            atom_sample(b, geo.n_points - 1 - m, geo.n_points, geo.fs, &re, &im);
+            return mk<T>((T)re, (T)-im);
+        }
+        if (e >= geo.n_points) return mk<T>((T)0, (T)0);
+        atom_sample(b, e, geo.n_points, geo.fs, &re, &im);
+        return mk<T>((T)re, (T)im);
+    }
+};
+
+// Source for the first inverse pass: record spectrum x band response.  batch = band_in_group*C + chan
+template <typename T> struct SrcCwtSpec {
+    const cplx<T>* spec; const cplx<T>* tables; const DevBand* bands; int band0; CwtGeom geo;
+    QI_DEV cplx<T> load(i64 batch, i64 e) const {
+        const i64 chan = batch % geo.n_channels;
+        const DevBand& b = bands[band0 + (int)(batch / geo.n_channels)];
+        const cplx<T> X = spec[(chan << geo.logL) + e];
+        if (b.table_off >= 0) {
+            cplx<T> H = tables[b.table_off + e];
+            const T gn = (T)b.gain;
+            if (geo.conv_mode == QI_CONV_CIRC_CORR) return mul_conj(X, H) * gn;
+            return (X * H) * gn;
+        }
+        const i64 k = (i64)brev_bits((unsigned)e, geo.logL);
+        return X * gabor_response<T>(b, k, geo.logL, geo.half_shift);
+    }
+};
+
+// Sink of the last inverse pass: slice, optional rotation, complex / power planes, fp64 band sums.
+template <typename T> struct DstCwtOut {
+    cplx<T>* out_c; T* out_p; double* band_sum; int band0; CwtGeom geo; double acc;
+    QI_DEV void store(i64 batch, i64 n, cplx<T> v) {
+        if (n >= geo.n_points) return;
+        const i64 chan = batch % geo.n_channels;
+        const i64 band = band0 + batch / geo.n_channels;
+        i64 no = n;
+        if (geo.conv_mode == QI_CONV_CIRC_CORR) no = (n + (geo.n_points >> 1)) & (geo.n_points - 1);
+        const i64 o = (chan * geo.n_bands + band) * geo.n_points + no;
+        if (out_c) out_c[o] = v;
+        const T p = norm2(v);
+        if (out_p) out_p[o] = p;
+        acc += (double)p;
+    }
+    QI_DEV void finish(i64 batch, unsigned char* scratch) {
+        if (!band_sum) return;
+        const double s = block_sum(acc, reinterpret_cast<double*>(scratch));
+        if (threadIdx.x == 0) {
+            const i64 chan = batch % geo.n_channels;
+            const i64 band = band0 + batch / geo.n_channels;
+            atomicAdd(&band_sum[chan * geo.n_bands + band], s);
+        }
+    }
+};
+
+// plain kernel writing time-domain atoms (public API wavelet_centered_4cwt)
+template <typename T>
+__global__ void atoms_time_kernel(const DevBand* bands, int n_bands, i64 n_points, double fs, cplx<T>* out) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i >= n_points) return;
+    double re, im;
+    atom_sample(bands[b], i, n_points, fs, &re, &im);
+    out[(i64)b * n_points + i] = mk<T>((T)re, (T)im);
+}
+
+static int ceil_log2_i64(i64 v) { int l = 0; while ((1ll << l) < v) ++l; return l; }
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct CwtLayout {
+    int logL; i64 L;
+    size_t off_bands, off_tabidx, off_spec, off_tables, off_work, total;
+    int group;
+};
+
+template <typename T>
+static CwtLayout cwt_layout(i64 C, i64 N, int B, int n_tab, int group, int conv_mode) {
+    CwtLayout lo;
+    lo.logL = conv_mode == QI_CONV_CIRC_CORR ? ceil_log2_i64(N) : ceil_log2_i64(N > 1 ? 2 * N - 1 : 1);
+    lo.L = 1ll << lo.logL;
+    if (group < 1) group = 1;
+    if (group > B) group = B;
+    while ((i64)group * C > 65535 && group > 1) --group;
+    lo.group = group;
+    size_t o = 0;
+    lo.off_bands = o; o = align_up(o + sizeof(DevBand) * (size_t)B, 256);
+    lo.off_tabidx = o; o = align_up(o + sizeof(int) * (size_t)(n_tab > 0 ? n_tab : 1), 256);
+    lo.off_spec = o; o = align_up(o + sizeof(cplx<T>) * (size_t)C * lo.L, 256);
+    lo.off_tables = o; o = align_up(o + sizeof(cplx<T>) * (size_t)n_tab * lo.L, 256);
+    lo.off_work = o; o = align_up(o + sizeof(cplx<T>) * (size_t)group * C * lo.L, 256);
+    lo.total = o;
+    return lo;
+}
+
+static void fill_dev_bands(const QiAtomBand* hb, int B, int logL, std::vector<DevBand>& db, std::vector<int>& tab) {
+    const double L = (double)(1ll << logL);
+    db.resize(B);
+    tab.clear();
+    for (int b = 0; b < B; ++b) {
+        DevBand d;
+        d.omega = hb[b].omega; d.p_re = hb[b].p_re; d.p_im = hb[b].p_im; d.amp = hb[b].amp;
+        if (hb[b].analytic) {
+            d.gain = hb[b].amp * sqrt(M_PI / hb[b].p_re) / L;
+            d.g = (2.0 * M_PI / L) / sqrt(2.0 * hb[b].p_re);
+            const double kappa = hb[b].omega * L / (2.0 * M_PI);
+            const double ki = floor(kappa);
+            d.kappa_int = (long long)ki;
+            d.kappa_frac = kappa - ki;
+            d.table_off = -1;
+        } else {
+            d.gain = 1.0 / L; d.g = 0; d.kappa_frac = 0; d.kappa_int = 0;
+            d.table_off = (long long)tab.size() << logL;
+            tab.push_back(b);
+        }
+        db[b] = d;
+    }
+}
+
+template <typename T>
+static int cwt_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiAtomBand* hb, int B, double fs,
+                        int conv_mode, void* out_c, void* out_p, double* band_sum, void* ws, size_t ws_bytes,
+                        int group, cudaStream_t st) {
+    int n_tab = 0;
+    for (int b = 0; b < B; ++b) {
+        if (!hb[b].analytic) ++n_tab;
+        else if (hb[b].p_im != 0.0 || !(hb[b].p_re > 0.0) || conv_mode != QI_CONV_LINEAR_SAME) return QI_ERR_ARG;
+    }
+    const CwtLayout lo = cwt_layout<T>(C, N, B, n_tab, group, conv_mode);
+    if (ws_bytes < lo.total) return QI_ERR_WORKSPACE;
+    if (conv_mode == QI_CONV_CIRC_CORR && (N & (N - 1))) return QI_ERR_ARG;
+    if (C > 65535) return QI_ERR_UNSUPPORTED;
+    unsigned char* base = static_cast<unsigned char*>(ws);
+    DevBand* d_bands = reinterpret_cast<DevBand*>(base + lo.off_bands);
+    int* d_tab = reinterpret_cast<int*>(base + lo.off_tabidx);
+    cplx<T>* spec = reinterpret_cast<cplx<T>*>(base + lo.off_spec);
+    cplx<T>* tables = reinterpret_cast<cplx<T>*>(base + lo.off_tables);
+    cplx<T>* work = reinterpret_cast<cplx<T>*>(base + lo.off_work);
+
+    std::vector<DevBand> db; std::vector<int> tab;
+    fill_dev_bands(hb, B, lo.logL, db, tab);
+    cudaMemcpyAsync(d_bands, db.data(), sizeof(DevBand) * (size_t)B, cudaMemcpyHostToDevice, st);
+    if (n_tab) cudaMemcpyAsync(d_tab, tab.data(), sizeof(int) * (size_t)n_tab, cudaMemcpyHostToDevice, st);
+#ifndef QI_EMUL
+    cudaStreamSynchronize(st);   // host vectors go out of scope; pageable copies are staged but be explicit
+#endif
+
+    CwtGeom geo;
+    geo.n_points = N; geo.n_channels = C; geo.n_bands = B; geo.logL = lo.logL;
+    geo.conv_mode = conv_mode; geo.fs = fs;
+    geo.centre_idx = (N - 1) / 2;
+    geo.half_shift = (conv_mode == QI_CONV_LINEAR_SAME && (N % 2 == 0)) ? 1 : 0;
+    geo.d_min = -geo.centre_idx;
+    geo.d_max = N - 1 - geo.centre_idx;
+
+    const FftPlan plan = make_plan(lo.logL, (int)sizeof(cplx<T>));
+    const int np = plan.npass;
+    const T one = (T)1;
+
+    // record spectra
+    for (int p = 0; p < np; ++p) {
+        DstComplex<T> d{spec, lo.L, one};
+        if (p == 0) {
+            SrcRealPad<T> s{static_cast<const T*>(sig), stride, N};
+            launch_pass<T, FFT_FWD>(plan, p, C, s, d, 0, st);
+        } else {
+            SrcComplex<T> s{spec, lo.L};
+            launch_pass<T, FFT_FWD>(plan, p, C, s, d, 0, st);
+        }
+    }
+    // atom tables (one forward FFT per table band, shared by all channels)
+    if (n_tab) {
+        for (int p = 0; p < np; ++p) {
+            DstComplex<T> d{tables, lo.L, one};
+            if (p == 0) {
+                SrcAtomKernel<T> s{d_bands, d_tab, geo};
+                launch_pass<T, FFT_FWD>(plan, p, n_tab, s, d, 0, st);
+            } else {
+                SrcComplex<T> s{tables, lo.L};
+                launch_pass<T, FFT_FWD>(plan, p, n_tab, s, d, 0, st);
+            }
+        }
+    }
+    if (band_sum) cudaMemsetAsync(band_sum, 0, sizeof(double) * (size_t)C * B, st);
+
+    for (int band0 = 0; band0 < B; band0 += lo.group) {
+        const int g = (B - band0 < lo.group) ? (B - band0) : lo.group;
+        const i64 nb = (i64)g * C;
+        for (int p = np - 1; p >= 0; --p) {
+            const bool first = (p == np - 1), last = (p == 0);
+            SrcCwtSpec<T> s1{spec, tables, d_bands, band0, geo};
+            SrcComplex<T> s2{work, lo.L};
+            DstComplex<T> d1{work, lo.L, one};
+            DstCwtOut<T> d2{static_cast<cplx<T>*>(out_c), static_cast<T*>(out_p), band_sum, band0, geo, 0.0};
+            if (first && last) launch_pass<T, FFT_INV>(plan, p, nb, s1, d2, 256, st);
+            else if (first) launch_pass<T, FFT_INV>(plan, p, nb, s1, d1, 0, st);
+            else if (last) launch_pass<T, FFT_INV>(plan, p, nb, s2, d2, 256, st);
+            else launch_pass<T, FFT_INV>(plan, p, nb, s2, d1, 0, st);
+        }
+    }
+    return check_cuda("qi_cwt_fft");
+}
+
+template <typename T>
+static int atoms_time_impl(const QiAtomBand* hb, int B, i64 N, double fs, void* out, void* ws, size_t ws_bytes,
+                           cudaStream_t st) {
+    if (ws_bytes < sizeof(DevBand) * (size_t)B) return QI_ERR_WORKSPACE;
+    std::vector<DevBand> db; std::vector<int> tab;
+    std::vector<QiAtomBand> tmp(hb, hb + B);
+    for (auto& t : tmp) t.analytic = 0;
+    fill_dev_bands(tmp.data(), B, 0, db, tab);
+    DevBand* d_bands = static_cast<DevBand*>(ws);
+    cudaMemcpyAsync(d_bands, db.data(), sizeof(DevBand) * (size_t)B, cudaMemcpyHostToDevice, st);
+#ifndef QI_EMUL
+    cudaStreamSynchronize(st);
+#endif
+    dim3 grid((unsigned)((N + 255) / 256), (unsigned)B);
+    QI_LAUNCH((atoms_time_kernel<T>), grid, dim3(256), 0, st, d_bands, B, N, fs, static_cast<cplx<T>*>(out));
+    return check_cuda("qi_atoms_time");
+}
+
+}  // namespace qi
+
+extern "C" {
+
+size_t qi_cwt_workspace_bytes(int64_t C, int64_t N, int B, int n_tab, int group, int conv_mode, int dtype) {
+    if (C <= 0 || N <= 0 || B <= 0) return 0;
+    if (dtype == QI_F32) return qi::cwt_layout<float>(C, N, B, n_tab, group, conv_mode).total;
+    return qi::cwt_layout<double>(C, N, B, n_tab, group, conv_mode).total;
+}
+
+int qi_cwt_fft(const void* sig, int64_t C, int64_t N, int64_t stride, const QiAtomBand* bands, int B, double fs,
+               int conv_mode, int dtype, void* out_cwt, void* out_power, double* band_sum, void* ws, size_t ws_bytes,
+               int group, void* stream) {
+    if (!sig || !bands || !ws || C <= 0 || N <= 0 || B <= 0 || stride < N) return QI_ERR_ARG;
+    if (N > (1ll << 29)) return QI_ERR_UNSUPPORTED;
+    if (conv_mode != QI_CONV_LINEAR_SAME && conv_mode != QI_CONV_CIRC_CORR) return QI_ERR_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == QI_F32)
+        return qi::cwt_fft_impl<float>(sig, C, N, stride, bands, B, fs, conv_mode, out_cwt, out_power, band_sum, ws,
+                                       ws_bytes, group, st);
+    if (dtype == QI_F64)
+        return qi::cwt_fft_impl<double>(sig, C, N, stride, bands, B, fs, conv_mode, out_cwt, out_power, band_sum, ws,
+                                        ws_bytes, group, st);
+    return QI_ERR_ARG;
+}
+
+int qi_atoms_time(const QiAtomBand* bands, int B, int64_t N, double fs, int dtype, void* out, void* ws,
+                  size_t ws_bytes, void* stream) {
+    if (!bands || !out || !ws || B <= 0 || N <= 0) return QI_ERR_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == QI_F32) return qi::atoms_time_impl<float>(bands, B, N, fs, out, ws, ws_bytes, st);
+    if (dtype == QI_F64) return qi::atoms_time_impl<double>(bands, B, N, fs, out, ws, ws_bytes, st);
+    return QI_ERR_ARG;
+}
+
+}  // extern "C"
