@@ -87,6 +87,40 @@ int qi_cwt_fft(const void* sig, int64_t n_channels, int64_t n_points, int64_t si
 int qi_atoms_time(const QiAtomBand* bands, int n_bands, int64_t n_points, double fs, int dtype,
                   void* out_atoms, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Stockwell transform ----------------------------------------------------------------------
+ * Replaces quantum_inferno/styx_stx.py:195-236 (stx_complex_any_scale_pow2) and the band loop of
+ * :52-192 (tfr_stx_fft :166-190):  tfr[b,:] = ifft( X[(k + shift_b) mod n] * exp(-0.5*sigma_b^2*w_k^2) ),
+ * w_k = 2*pi*fftfreq(n)[k].  n_points must be a power of two.  shift_b (the argmin of :233) and sigma_b
+ * are computed on the host in float64 exactly as the reference does. */
+typedef struct {
+    double sigma;
+    int64_t shift;
+} QiStxBand;
+
+size_t qi_stx_workspace_bytes(int64_t n_channels, int64_t n_points, int n_bands, int bands_per_group, int dtype);
+
+/* out_tfr complex [C,B,N] or NULL; out_power real [C,B,N] or NULL; band_sum double [C,B] or NULL */
+int qi_stx_fft(const void* sig, int64_t n_channels, int64_t n_points, int64_t sig_stride,
+               const QiStxBand* bands, int n_bands, int dtype,
+               void* out_tfr, void* out_power, double* band_sum,
+               void* workspace, size_t workspace_bytes, int bands_per_group, void* stream);
+
+/* windows_fft of tfr_stx_fft (styx_stx.py:179): out complex [n_bands, n_points], natural bin order */
+int qi_stx_windows(const QiStxBand* bands, int n_bands, int64_t n_points, int dtype, void* out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- STFT / Welch -----------------------------------------------------------------------------
+ * Replaces scipy.signal.stft / welch as called by quantum_inferno/styx_fft.py:175-187 (stft_complex_pow2),
+ * :215-227 (gtx_complex_pow2), :254-266 (welch_power_pow2).  Frame f covers extended-record samples
+ * [f*hop - pad_left, f*hop - pad_left + nperseg) with zeros outside [0, n_points); each frame has its mean
+ * removed (detrend != 0), is multiplied by window[nperseg] (device pointer), zero-padded to nfft = 2^m,
+ * transformed, and the one-sided bins multiplied by `scale`.
+ *   out     : complex [n_channels, nfft/2+1, n_frames] (time fastest, scipy's layout) or NULL
+ *   psd_acc : double  [n_channels, nfft/2+1] receives sum over frames of |X_k|^2 (unscaled) or NULL */
+int qi_stft(const void* sig, int64_t n_channels, int64_t n_points, int64_t sig_stride, const void* window,
+            int nperseg, int hop, int nfft, int64_t n_frames, int pad_left, double scale, int detrend, int dtype,
+            void* out, double* psd_acc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,3 +50,63 @@ def gabor_bands(band_order_nth, n_points, frequency_hz, frequency_sample_rate_hz
     else:
         bands["analytic"] = (n_points / scale >= ANALYTIC_MIN_POINTS_PER_SCALE[dtype_name]).astype(np.int32)
     return bands, scale, omega, amp
+
+
+def stx_bands(band_order_nth, n_points, frequency_sample_rate_hz):
+    """Band table of styx_stx.stx_complex_any_scale_pow2 (reference styx_stx.py:206-233).
+    sigma uses the exact band centre, the shift index is the first argmin over the fft bins.
+    Returns (frequency_stx_hz, bands[STX_BAND])."""
+    from ._lib import STX_BAND
+    f_stx = scales.log_frequency_hz_from_fft_points(frequency_sample_hz=frequency_sample_rate_hz,
+                                                    fft_points=n_points, scale_order=band_order_nth)
+    f_fft = np.fft.fftfreq(n_points, 1 / frequency_sample_rate_hz)
+    omega_stx = 2 * np.pi * f_stx / frequency_sample_rate_hz
+    bands = np.zeros(len(f_stx), dtype=STX_BAND)
+    bands["sigma"] = scales.cycles_from_order(scale_order=band_order_nth) / omega_stx
+    bands["shift"] = [int(np.abs(f_fft - f).argmin()) for f in f_stx]
+    return f_stx, bands
+
+
+# ----------------------------------------------------------------------------- STFT
+def periodic_window(kind, param, n_points):
+    """The DFT-even window scipy.signal.get_window((kind, param), n_points) returns: the symmetric
+    (n_points+1)-point window without its last sample.  kind: 'tukey' (param = alpha) or 'gaussian'
+    (param = sigma in samples) -- the two windows the reference asks for (styx_fft.py:178,218,257)."""
+    m = n_points + 1
+    k = np.arange(m, dtype=np.float64)
+    if kind == "tukey":
+        alpha = float(param)
+        if alpha <= 0:
+            w = np.ones(m)
+        elif alpha >= 1.0:
+            w = 0.5 - 0.5 * np.cos(2.0 * np.pi * k / (m - 1))
+        else:
+            edge = int(np.floor(alpha * (m - 1) / 2.0))
+            rise = 0.5 * (1 + np.cos(np.pi * (-1 + 2.0 * k[:edge + 1] / alpha / (m - 1))))
+            fall = 0.5 * (1 + np.cos(np.pi * (-2.0 / alpha + 1 + 2.0 * k[m - edge - 1:] / alpha / (m - 1))))
+            w = np.concatenate((rise, np.ones(m - 2 * edge - 2), fall))
+    elif kind == "gaussian":
+        w = np.exp(-0.5 * ((k - (m - 1.0) / 2.0) / float(param)) ** 2)
+    else:
+        raise ValueError(f"unsupported window {kind!r}")
+    return w[:-1]
+
+
+def stft_frames(n_points, nperseg, noverlap, boundary_zeros=True, padded=True):
+    """Frame bookkeeping of scipy's _spectral_helper: returns (n_frames, pad_left, extended_length)."""
+    hop = nperseg - noverlap
+    if hop <= 0:
+        raise ValueError("noverlap must be less than nperseg.")
+    pad_left = nperseg // 2 if boundary_zeros else 0
+    ext = n_points + 2 * pad_left
+    if padded:
+        ext += (-(ext - nperseg) % hop) % nperseg
+    n_frames = (ext - noverlap) // hop
+    return n_frames, pad_left, ext
+
+
+def stft_time_axis(ext_length, nperseg, noverlap, fs, boundary_zeros=True):
+    t = np.arange(nperseg / 2, ext_length - nperseg / 2 + 1, nperseg - noverlap) / float(fs)
+    if boundary_zeros:
+        t -= (nperseg / 2) / fs
+    return t

@@ -13,6 +13,7 @@
 #include "qi_fft.cuh"
 #include "qi_host.h"
 #include "qi_reduce.cuh"
+#include "qi_tfr.cuh"
 
 #include <vector>
 #include <math.h>
@@ -27,18 +28,6 @@ struct DevBand {
     long long table_off;   // element offset into the table buffer, -1 = analytic
     // time-domain atom (table bands)
     double omega, p_re, p_im, amp;
-};
-
-struct CwtGeom {
-    i64 n_points;      // N
-    i64 n_channels;    // C
-    int n_bands;       // B
-    int logL;
-    int half_shift;    // 1 if the 'same' slice leaves a half-sample offset (N even)
-    int conv_mode;
-    i64 d_min, d_max;  // kernel lag range placed circularly (linear mode)
-    i64 centre_idx;    // (N-1)//2
-    double fs;
 };
 
 // ---------------------------------------------------------------- on-the-fly Gabor response
@@ -115,32 +104,6 @@ template <typename T> struct SrcCwtSpec {
     }
 };
 
-// Sink of the last inverse pass: slice, optional rotation, complex / power planes, fp64 band sums.
-template <typename T> struct DstCwtOut {
-    cplx<T>* out_c; T* out_p; double* band_sum; int band0; CwtGeom geo; double acc;
-    QI_DEV void store(i64 batch, i64 n, cplx<T> v) {
-        if (n >= geo.n_points) return;
-        const i64 chan = batch % geo.n_channels;
-        const i64 band = band0 + batch / geo.n_channels;
-        i64 no = n;
-        if (geo.conv_mode == QI_CONV_CIRC_CORR) no = (n + (geo.n_points >> 1)) & (geo.n_points - 1);
-        const i64 o = (chan * geo.n_bands + band) * geo.n_points + no;
-        if (out_c) out_c[o] = v;
-        const T p = norm2(v);
-        if (out_p) out_p[o] = p;
-        acc += (double)p;
-    }
-    QI_DEV void finish(i64 batch, unsigned char* scratch) {
-        if (!band_sum) return;
-        const double s = block_sum(acc, reinterpret_cast<double*>(scratch));
-        if (threadIdx.x == 0) {
-            const i64 chan = batch % geo.n_channels;
-            const i64 band = band0 + batch / geo.n_channels;
-            atomicAdd(&band_sum[chan * geo.n_bands + band], s);
-        }
-    }
-};
-
 // plain kernel writing time-domain atoms (public API wavelet_centered_4cwt)
 template <typename T>
 __global__ void atoms_time_kernel(const DevBand* bands, int n_bands, i64 n_points, double fs, cplx<T>* out) {
@@ -151,9 +114,6 @@ __global__ void atoms_time_kernel(const DevBand* bands, int n_bands, i64 n_point
     atom_sample(bands[b], i, n_points, fs, &re, &im);
     out[(i64)b * n_points + i] = mk<T>((T)re, (T)im);
 }
-
-static int ceil_log2_i64(i64 v) { int l = 0; while ((1ll << l) < v) ++l; return l; }
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct CwtLayout {
     int logL; i64 L;

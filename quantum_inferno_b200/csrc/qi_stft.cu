@@ -1,0 +1,153 @@
+// qi_stft.cu -- short-time Fourier transform / Welch on the shared FFT tile core.
+//
+// One CTA transforms 2*TC consecutive frames of one channel: frames are gathered from the (virtually
+// zero-extended) record straight into shared memory, two real frames packed into one complex column,
+// the per-frame mean removed, the periodic window applied, one radix-8 tile FFT run, the two spectra
+// separated with the Hermitian split and the one-sided bins stored with time as the fastest axis (the
+// layout scipy returns).  Replaces scipy.signal.stft / welch as called by
+// quantum_inferno/styx_fft.py:175-187, :215-227, :254-266.
+#include "qi_fft.cuh"
+#include "qi_host.h"
+#include "qi_reduce.cuh"
+
+namespace qi {
+
+struct StftGeom {
+    i64 n_points, sig_stride, n_frames;
+    int nperseg, hop, logF, pad_left, TC, detrend;
+    double scale;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g, cplx<T>* __restrict__ out,
+            double* __restrict__ psd_acc) {
+    QI_DYN_SMEM(smem_raw);
+    const int R = 1 << g.logF;
+    const int TC = g.TC, TP = TC + 1;
+    cplx<T>* tile = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* tw = tile + (size_t)R * TP;
+    T* means = reinterpret_cast<T*>(tw + R);              // 2*TC means
+    const i64 chan = blockIdx.y;
+    const i64 frame0 = (i64)blockIdx.x * (2 * TC);
+    const T* x = sig + chan * g.sig_stride;
+
+    fill_twiddles<T>(tw, g.logF);
+    // gather (lanes along the sample axis -> coalesced global reads)
+    for (int idx = threadIdx.x; idx < R * TC; idx += blockDim.x) {
+        const int r = idx & (R - 1);
+        const int c = idx >> g.logF;
+        T va = (T)0, vb = (T)0;
+        if (r < g.nperseg) {
+            const i64 fa = frame0 + 2 * c, fb = fa + 1;
+            const i64 pa = fa * g.hop + r - g.pad_left, pb = fb * g.hop + r - g.pad_left;
+            if (fa < g.n_frames && pa >= 0 && pa < g.n_points) va = x[pa];
+            if (fb < g.n_frames && pb >= 0 && pb < g.n_points) vb = x[pb];
+        }
+        tile[r * TP + c] = mk<T>(va, vb);
+    }
+    __syncthreads();
+    // per-frame mean over the nperseg samples (scipy detrend='constant', after the zero extension)
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        for (int col = warp; col < 2 * TC; col += nw) {
+            double s = 0.0;
+            if (g.detrend) {
+                const int c = col >> 1;
+                for (int r = lane; r < g.nperseg; r += 32) {
+                    const cplx<T> v = tile[r * TP + c];
+                    s += (double)((col & 1) ? v.im : v.re);
+                }
+            }
+            s = warp_sum(s);
+            if (lane == 0) means[col] = (T)(s / (double)g.nperseg);
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < g.nperseg * TC; idx += blockDim.x) {
+        const int c = idx % TC;
+        const int r = idx / TC;
+        const T w = window[r];
+        cplx<T> v = tile[r * TP + c];
+        v.re = (v.re - means[2 * c]) * w;
+        v.im = (v.im - means[2 * c + 1]) * w;
+        tile[r * TP + c] = v;
+    }
+    __syncthreads();
+    tile_fft<T, FFT_FWD>(tile, tw, g.logF, TC, TP);
+    // Hermitian split + store, lanes along frames (time is the fastest output axis)
+    const int K = (R >> 1) + 1;
+    const T sc = (T)g.scale;
+    const int total = K * TC;
+    const int padded = (total + (int)blockDim.x - 1) / (int)blockDim.x * (int)blockDim.x;   // whole warps stay converged
+    for (int idx = threadIdx.x; idx < padded; idx += blockDim.x) {
+        const bool active = idx < total;
+        const int c = idx % TC;
+        const int k = active ? idx / TC : 0;
+        const cplx<T> z1 = tile[(int)brev_bits((unsigned)k, g.logF) * TP + c];
+        const cplx<T> z2 = tile[(int)brev_bits((unsigned)((R - k) & (R - 1)), g.logF) * TP + c];
+        const cplx<T> xa = mk<T>((T)0.5 * (z1.re + z2.re), (T)0.5 * (z1.im - z2.im));
+        const cplx<T> xb = mk<T>((T)0.5 * (z1.im + z2.im), (T)-0.5 * (z1.re - z2.re));
+        const i64 fa = frame0 + 2 * c;
+        if (out && active) {
+            cplx<T>* o = out + (chan * K + k) * g.n_frames + fa;
+            if (fa < g.n_frames) o[0] = xa * sc;
+            if (fa + 1 < g.n_frames) o[1] = xb * sc;
+        }
+        if (psd_acc) {
+            double p = 0.0;
+            if (active && fa < g.n_frames) p += (double)norm2(xa);
+            if (active && fa + 1 < g.n_frames) p += (double)norm2(xb);
+            // reduce over the TC lanes that share k before touching HBM
+            for (int o2 = TC >> 1; o2 > 0; o2 >>= 1) p += __shfl_down_sync(0xffffffffu, p, o2);
+            if (active && c == 0) atomicAdd(&psd_acc[chan * K + k], p);
+        }
+    }
+}
+
+template <typename T>
+static int stft_impl(const void* sig, i64 C, i64 n_points, i64 stride, const void* window, int nperseg, int hop,
+                     int nfft, i64 n_frames, int pad_left, double scale, int detrend, void* out, double* psd_acc,
+                     cudaStream_t st) {
+    int logF = 0;
+    while ((1 << logF) < nfft) ++logF;
+    if ((1 << logF) != nfft) return QI_ERR_ARG;
+    const size_t budget = 200 * 1024;
+    int TC = 16;
+    auto need = [&](int tc) { return ((size_t)nfft * (tc + 2)) * sizeof(cplx<T>) + 2 * tc * sizeof(T) + 64; };
+    while (TC > 1 && need(TC) > budget) TC >>= 1;
+    if (need(TC) > budget) return QI_ERR_UNSUPPORTED;
+    // the psd reduction uses shuffles across the TC lanes of one k: needs TC | 32 (true: power of two <= 16)
+    StftGeom g;
+    g.n_points = n_points; g.sig_stride = stride; g.n_frames = n_frames;
+    g.nperseg = nperseg; g.hop = hop; g.logF = logF; g.pad_left = pad_left; g.TC = TC; g.detrend = detrend;
+    g.scale = scale;
+    if (C > 65535) return QI_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)((n_frames + 2 * TC - 1) / (2 * TC)), (unsigned)C);
+    const size_t smem = need(TC);
+#ifndef QI_EMUL
+    cudaFuncSetAttribute(stft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    if (psd_acc) cudaMemsetAsync(psd_acc, 0, sizeof(double) * (size_t)C * (nfft / 2 + 1), st);
+    QI_LAUNCH((stft_kernel<T>), grid, dim3(256), smem, st, static_cast<const T*>(sig), static_cast<const T*>(window),
+              g, static_cast<cplx<T>*>(out), psd_acc);
+    return check_cuda("qi_stft");
+}
+
+}  // namespace qi
+
+extern "C" int qi_stft(const void* sig, int64_t C, int64_t n_points, int64_t stride, const void* window, int nperseg,
+                       int hop, int nfft, int64_t n_frames, int pad_left, double scale, int detrend, int dtype,
+                       void* out, double* psd_acc, void* stream) {
+    if (!sig || !window || C <= 0 || n_points <= 0 || nperseg <= 0 || hop <= 0 || nfft < nperseg || n_frames <= 0)
+        return QI_ERR_ARG;
+    if (!out && !psd_acc) return QI_ERR_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == QI_F32)
+        return qi::stft_impl<float>(sig, C, n_points, stride, window, nperseg, hop, nfft, n_frames, pad_left, scale,
+                                    detrend, out, psd_acc, st);
+    if (dtype == QI_F64)
+        return qi::stft_impl<double>(sig, C, n_points, stride, window, nperseg, hop, nfft, n_frames, pad_left, scale,
+                                     detrend, out, psd_acc, st);
+    return QI_ERR_ARG;
+}
