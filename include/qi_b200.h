@@ -36,6 +36,22 @@ const char* qi_error_string(int code);
 /* text of the last CUDA error seen by this thread (empty string if none) */
 const char* qi_last_cuda_error(void);
 
+/* ---- launch accounting / live timing (used by bench.py) ---------------------------------------
+ * qi_launch_count: kernels this library has launched in this process so far.
+ * qi_profile_enable(1) makes every launch be bracketed by CUDA events on its own stream, grouped by
+ * category; qi_profile_read synchronises those events and returns per-category totals, then clears them. */
+#define QI_CAT_FFT_FWD 0      /* forward FFT passes (record / atom spectra)            */
+#define QI_CAT_INV_FIRST 1    /* first inverse pass: spectrum x band response          */
+#define QI_CAT_INV_MID 2      /* middle inverse pass                                   */
+#define QI_CAT_INV_LAST 3     /* last inverse pass: slice + |.|^2 + band sums          */
+#define QI_CAT_INFO 4         /* tfr_info planes / reductions                          */
+#define QI_CAT_STFT 5
+#define QI_CAT_OTHER 6
+#define QI_N_CATEGORIES 7
+int64_t qi_launch_count(void);
+int qi_profile_enable(int on);
+int qi_profile_read(double* total_ms /*[QI_N_CATEGORIES]*/, int64_t* launches /*[QI_N_CATEGORIES]*/);
+
 /* ---- plain batched FFT (building block; also used by tfr_info.ShannonFFT, tfr_info.py:177) ----
  * in : complex [batch, 2^log2n] natural order
  * out: forward -> spectrum in BIT-REVERSED order (position p holds bin bitrev(p));
@@ -83,9 +99,11 @@ int qi_cwt_fft(const void* sig, int64_t n_channels, int64_t n_points, int64_t si
                void* out_cwt, void* out_power, double* band_sum,
                void* workspace, size_t workspace_bytes, int bands_per_group, void* stream);
 
-/* Time-domain atoms themselves (styx_cwt.py:113-144 wavelet_centered_4cwt): out complex [n_bands, n_points] */
+/* Time-domain atoms themselves (styx_cwt.py:68-144 wavelet_complex / wavelet_centered_4cwt,
+ * cwt_atoms.py:16-50 chirp_complex): out complex [n_bands, n_points].  xtime: optional device fp64
+ * [n_points] array of non-dimensional times x; NULL = the centred axis defined above. */
 int qi_atoms_time(const QiAtomBand* bands, int n_bands, int64_t n_points, double fs, int dtype,
-                  void* out_atoms, void* workspace, size_t workspace_bytes, void* stream);
+                  const double* xtime, void* out_atoms, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- Stockwell transform ----------------------------------------------------------------------
  * Replaces quantum_inferno/styx_stx.py:195-236 (stx_complex_any_scale_pow2) and the band loop of
@@ -120,6 +138,45 @@ int qi_stx_windows(const QiStxBand* bands, int n_bands, int64_t n_points, int dt
 int qi_stft(const void* sig, int64_t n_channels, int64_t n_points, int64_t sig_stride, const void* window,
             int nperseg, int hop, int nfft, int64_t n_frames, int pad_left, double scale, int detrend, int dtype,
             void* out, double* psd_acc, void* stream);
+
+/* ---- power / information / entropy (tfr_info) -------------------------------------------------
+ * `power` is real [M, F, T] (M independent matrices: channels).  All reductions accumulate in fp64. */
+
+/* Replaces np.sum(axis=1), np.sum(axis=0), np.sum(), np.max() of quantum_inferno/tfr_info.py:236,247,259,79.
+ * row_sum [M,F], col_sum [M,T], total [M], max_value [M]; any of them may be NULL. */
+int qi_power_reduce(const void* power, int64_t M, int64_t F, int64_t T, int dtype,
+                    double* row_sum, double* col_sum, double* total, double* max_value, void* stream);
+
+/* Replaces ShannonStft.__init__ (tfr_info.py:219-228) for the pdf of
+ *   mode 0: P / norm[m]              shannon_stft_from_tfr_power   :231-236   (norm = total,   D = F*T)
+ *   mode 1: (1/norm[m,t] + eps) * P  ShannonStftPerTime            :239-248   (norm = col_sum, D = F)
+ *   mode 2: (1/norm[m,f] + eps) * P  ShannonStftPerFreq            :251-260   (norm = row_sum, D = T)
+ *   mode 3: P                        Shannon (1-D marginal, EPS32) :97-135    (D = T, F = 1)
+ * Outputs (each may be NULL): pdf, info = -log2(pdf+eps), bits = pdf*info, isnr = log2(D)-info,
+ * esnr = bits/(log2(D)/D); entropy_sum [M,F] = row sums of bits (fp64). */
+int qi_shannon(const void* power, int64_t M, int64_t F, int64_t T, int dtype, int mode, const double* norm,
+               double eps, double deg_free, void* out_pdf, void* out_info, void* out_bits, void* out_isnr,
+               void* out_esnr, double* entropy_sum, void* stream);
+
+/* Replaces scale_power_bits (tfr_info.py:73-79): out = log2(P+eps) - log2(max_value[m]+eps); per_mat = F*T */
+int qi_power_bits(const void* power, int64_t M, int64_t per_mat, int dtype, const double* max_value, double eps,
+                  void* out, void* stream);
+
+/* Replaces ShannonTDR.__init__ (tfr_info.py:147-151): sumsq[m] = sum x^2, out_sig = x/sqrt(sumsq) (or NULL),
+ * out_marginal = out_sig^2 */
+int qi_tdr_marginal(const void* sig, int64_t M, int64_t n, int64_t sig_stride, int dtype, double* sumsq,
+                    void* out_sig, void* out_marginal, void* stream);
+
+/* Elementwise on n values of a real (is_complex=0), complex (is_complex=1) or signed-real (is_complex=2: no
+ * modulus, log2(x + eps) as in tfr_info.py:65-70) buffer:
+ * square=0: out = log2(|x| + eps)  (quantum_inferno/utilities/rescaling.py:13-20 to_log2_with_epsilon, used at
+ *           cwt_atoms.py:442 and styx_fft.py:55);  square=1: out = |x|^2 + eps (styx_stx.py:188-190). out is real. */
+int qi_abs_log2(const void* in, int64_t n, int dtype, int is_complex, int square, double eps, void* out, void* stream);
+
+/* Replaces scipy.fft.rfft in ShannonFFT.__init__ (tfr_info.py:177): real [M, n=2^m] -> complex [M, n/2+1]
+ * in natural bin order.  workspace >= M*n complex elements. */
+int qi_rfft(const void* sig, int64_t M, int64_t n, int64_t sig_stride, int dtype, void* out,
+            void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

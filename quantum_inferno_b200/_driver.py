@@ -1,0 +1,213 @@
+"""
+Thin drivers: marshal host-side plans and device buffers into the C-ABI calls of libqi_b200.so.
+Everything here enqueues work on the current CUDA stream and returns device buffers.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._runtime import COMPLEX_OF, DTYPE_CODE, get_runtime
+
+# bytes of scratch we are willing to spend on batching several bands per launch
+WORKSPACE_TARGET_BYTES = 8 << 30
+EPS64 = float(np.finfo(np.float64).eps)
+EPS32 = float(np.finfo(np.float32).eps)
+
+
+def _as_2d(rt, sig, dt):
+    """Accept [N] or [C, N]; returns (device buffer [C, N], was_1d)."""
+    x = rt.asarray(sig, dt)
+    if x.ndim == 1:
+        return rt.reshape(x, (1, x.shape[0])), True
+    if x.ndim != 2:
+        raise ValueError("sig_wf must be 1-D [points] or 2-D [channels, points]")
+    return x, False
+
+
+def _group_for(lib_fn_bytes, n_bands, target=WORKSPACE_TARGET_BYTES):
+    """Largest bands-per-launch whose workspace stays under `target` (at least 1)."""
+    group = n_bands
+    while group > 1 and lib_fn_bytes(group) > target:
+        group = max(1, group // 2)
+    return group
+
+
+def cwt_fft(sig, bands, fs, dt, conv_mode=_lib.QI_CONV_LINEAR_SAME, want_complex=True, want_power=False,
+            want_band_sum=False, rt=None, out_complex=None, out_power=None, band_sum=None):
+    """Run qi_cwt_fft.  sig: device [C, N]; bands: numpy ATOM_BAND table.  Returns dict of device buffers
+    (complex [C,B,N], power [C,B,N], band_sum [C,B] float64)."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    C, N = int(sig.shape[0]), int(sig.shape[1])
+    bands = np.ascontiguousarray(bands, dtype=_lib.ATOM_BAND)
+    B = len(bands)
+    n_tab = int(np.count_nonzero(bands["analytic"] == 0))
+    code = DTYPE_CODE[dt]
+
+    def ws_bytes(group):
+        return lib.qi_cwt_workspace_bytes(C, N, B, n_tab, group, conv_mode, code)
+
+    group = _group_for(ws_bytes, B)
+    nbytes = ws_bytes(group)
+    ws = rt.workspace(nbytes)
+    if want_complex and out_complex is None:
+        out_complex = rt.empty((C, B, N), COMPLEX_OF[dt])
+    if want_power and out_power is None:
+        out_power = rt.empty((C, B, N), dt)
+    if want_band_sum and band_sum is None:
+        band_sum = rt.empty((C, B), "float64")
+    rc = lib.qi_cwt_fft(rt.ptr(sig), C, N, N, bands.ctypes.data, B, float(fs), conv_mode, code,
+                        rt.ptr(out_complex), rt.ptr(out_power), rt.ptr(band_sum), rt.ptr(ws), nbytes, group,
+                        rt.stream())
+    _lib.check(lib, rc, "qi_cwt_fft")
+    return {"complex": out_complex, "power": out_power, "band_sum": band_sum}
+
+
+def atoms_time(bands, n_points, fs, dt, xtime=None, rt=None):
+    """Time-domain atoms [B, n_points] complex (qi_atoms_time)."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    bands = np.ascontiguousarray(bands, dtype=_lib.ATOM_BAND)
+    B = len(bands)
+    out = rt.empty((B, n_points), COMPLEX_OF[dt])
+    ws = rt.workspace(max(4096, 128 * B))
+    xt = None if xtime is None else rt.asarray(np.asarray(xtime, dtype=np.float64), "float64")
+    rc = lib.qi_atoms_time(bands.ctypes.data, B, int(n_points), float(fs), DTYPE_CODE[dt], rt.ptr(xt), rt.ptr(out),
+                           rt.ptr(ws), max(4096, 128 * B), rt.stream())
+    _lib.check(lib, rc, "qi_atoms_time")
+    return out
+
+
+def stx_fft(sig, bands, dt, want_complex=True, want_power=False, want_band_sum=False, rt=None):
+    rt = rt or get_runtime()
+    lib = rt.lib
+    C, N = int(sig.shape[0]), int(sig.shape[1])
+    bands = np.ascontiguousarray(bands, dtype=_lib.STX_BAND)
+    B = len(bands)
+    code = DTYPE_CODE[dt]
+
+    def ws_bytes(group):
+        return lib.qi_stx_workspace_bytes(C, N, B, group, code)
+
+    group = _group_for(ws_bytes, B)
+    nbytes = ws_bytes(group)
+    ws = rt.workspace(nbytes)
+    out_c = rt.empty((C, B, N), COMPLEX_OF[dt]) if want_complex else None
+    out_p = rt.empty((C, B, N), dt) if want_power else None
+    bsum = rt.empty((C, B), "float64") if want_band_sum else None
+    rc = lib.qi_stx_fft(rt.ptr(sig), C, N, N, bands.ctypes.data, B, code, rt.ptr(out_c), rt.ptr(out_p), rt.ptr(bsum),
+                        rt.ptr(ws), nbytes, group, rt.stream())
+    _lib.check(lib, rc, "qi_stx_fft")
+    return {"complex": out_c, "power": out_p, "band_sum": bsum}
+
+
+def stx_windows(bands, n_points, dt, rt=None):
+    rt = rt or get_runtime()
+    lib = rt.lib
+    bands = np.ascontiguousarray(bands, dtype=_lib.STX_BAND)
+    B = len(bands)
+    out = rt.empty((B, n_points), COMPLEX_OF[dt])
+    nbytes = max(4096, 16 * B)
+    ws = rt.workspace(nbytes)
+    rc = lib.qi_stx_windows(bands.ctypes.data, B, int(n_points), DTYPE_CODE[dt], rt.ptr(out), rt.ptr(ws), nbytes,
+                            rt.stream())
+    _lib.check(lib, rc, "qi_stx_windows")
+    return out
+
+
+def stft(sig, window, nperseg, hop, nfft, n_frames, pad_left, scale, dt, detrend=True, psd=False, rt=None):
+    """sig: device [C, N]; window: numpy float64 [nperseg].  Returns complex [C, nfft/2+1, n_frames]
+    (psd=False) or the fp64 accumulator [C, nfft/2+1] of sum_frames |X|^2 (psd=True)."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    C, N = int(sig.shape[0]), int(sig.shape[1])
+    K = nfft // 2 + 1
+    win = rt.asarray(np.asarray(window, dtype=np.float64), dt)
+    out = None if psd else rt.empty((C, K, n_frames), COMPLEX_OF[dt])
+    acc = rt.empty((C, K), "float64") if psd else None
+    rc = lib.qi_stft(rt.ptr(sig), C, N, N, rt.ptr(win), int(nperseg), int(hop), int(nfft), int(n_frames),
+                     int(pad_left), float(scale), 1 if detrend else 0, DTYPE_CODE[dt], rt.ptr(out), rt.ptr(acc),
+                     rt.stream())
+    _lib.check(lib, rc, "qi_stft")
+    return acc if psd else out
+
+
+def power_reduce(power, dt, rows=False, cols=False, total=False, maximum=False, rt=None):
+    """power: device [M, F, T].  Returns dict with requested fp64 buffers row_sum[M,F], col_sum[M,T], total[M], max[M]."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    M, F, T = (int(s) for s in power.shape)
+    rs = rt.empty((M, F), "float64") if rows else None
+    cs = rt.empty((M, T), "float64") if cols else None
+    tt = rt.empty((M,), "float64") if total else None
+    mx = rt.empty((M,), "float64") if maximum else None
+    rc = lib.qi_power_reduce(rt.ptr(power), M, F, T, DTYPE_CODE[dt], rt.ptr(rs), rt.ptr(cs), rt.ptr(tt), rt.ptr(mx),
+                             rt.stream())
+    _lib.check(lib, rc, "qi_power_reduce")
+    return {"row_sum": rs, "col_sum": cs, "total": tt, "max": mx}
+
+
+def shannon(power, dt, mode, norm, deg_free, eps=EPS64, planes=("info", "bits", "isnr", "esnr"), entropy_sum=False,
+            rt=None, out_info=None):
+    rt = rt or get_runtime()
+    lib = rt.lib
+    M, F, T = (int(s) for s in power.shape)
+    out = {k: (rt.empty((M, F, T), dt) if k in planes else None) for k in ("pdf", "info", "bits", "isnr", "esnr")}
+    if out_info is not None:
+        out["info"] = out_info
+    es = rt.empty((M, F), "float64") if entropy_sum else None
+    rc = lib.qi_shannon(rt.ptr(power), M, F, T, DTYPE_CODE[dt], int(mode), rt.ptr(norm), float(eps), float(deg_free),
+                        rt.ptr(out["pdf"]), rt.ptr(out["info"]), rt.ptr(out["bits"]), rt.ptr(out["isnr"]), rt.ptr(out["esnr"]), rt.ptr(es),
+                        rt.stream())
+    _lib.check(lib, rc, "qi_shannon")
+    out["entropy_sum"] = es
+    return out
+
+
+def power_bits(power, dt, max_value, eps=EPS64, rt=None):
+    """power: device [M, ...]; max_value: device fp64 [M].  log2(P+eps) - log2(max+eps)."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    M = int(power.shape[0])
+    per = int(np.prod(power.shape[1:]))
+    out = rt.empty(power.shape, dt)
+    rc = lib.qi_power_bits(rt.ptr(power), M, per, DTYPE_CODE[dt], rt.ptr(max_value), float(eps), rt.ptr(out), rt.stream())
+    _lib.check(lib, rc, "qi_power_bits")
+    return out
+
+
+def tdr_marginal(sig, dt, rt=None):
+    rt = rt or get_runtime()
+    lib = rt.lib
+    M, n = int(sig.shape[0]), int(sig.shape[1])
+    ss = rt.empty((M,), "float64")
+    sn = rt.empty((M, n), dt)
+    mg = rt.empty((M, n), dt)
+    rc = lib.qi_tdr_marginal(rt.ptr(sig), M, n, n, DTYPE_CODE[dt], rt.ptr(ss), rt.ptr(sn), rt.ptr(mg), rt.stream())
+    _lib.check(lib, rc, "qi_tdr_marginal")
+    return sn, mg, ss
+
+
+def rfft(sig, dt, rt=None):
+    rt = rt or get_runtime()
+    lib = rt.lib
+    M, n = int(sig.shape[0]), int(sig.shape[1])
+    out = rt.empty((M, n // 2 + 1), COMPLEX_OF[dt])
+    nbytes = M * n * (8 if dt == "float32" else 16)
+    ws = rt.workspace(nbytes)
+    rc = lib.qi_rfft(rt.ptr(sig), M, n, n, DTYPE_CODE[dt], rt.ptr(out), rt.ptr(ws), nbytes, rt.stream())
+    _lib.check(lib, rc, "qi_rfft")
+    return out
+
+
+def abs_log2(buf, dt, is_complex, eps=EPS64, square=False, rt=None, signed=False):
+    """log2(|x| + eps) (utilities/rescaling.py:13-20) or |x|^2 when square=True, elementwise on the device."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    n = int(np.prod(buf.shape))
+    out = rt.empty(buf.shape, dt)
+    rc = lib.qi_abs_log2(rt.ptr(buf), n, DTYPE_CODE[dt], 2 if signed else (1 if is_complex else 0), 1 if square else 0, float(eps),
+                         rt.ptr(out), rt.stream())
+    _lib.check(lib, rc, "qi_abs_log2")
+    return out

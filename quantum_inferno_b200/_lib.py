@@ -13,6 +13,8 @@ import numpy as np
 QI_F32, QI_F64 = 0, 1
 QI_CONV_LINEAR_SAME, QI_CONV_CIRC_CORR = 0, 1
 QI_ABI_VERSION = 1
+QI_N_CATEGORIES = 7
+CATEGORY_NAMES = ("fft_fwd", "inv_first", "inv_mid", "inv_last", "info", "stft", "other")
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqi_b200.so")
@@ -30,16 +32,26 @@ SIGNATURES = {
     "qi_abi_version": (_c_int, []),
     "qi_error_string": (ctypes.c_char_p, [_c_int]),
     "qi_last_cuda_error": (ctypes.c_char_p, []),
+    "qi_launch_count": (_c_i64, []),
+    "qi_profile_enable": (_c_int, [_c_int]),
+    "qi_profile_read": (_c_int, [_c_vp, _c_vp]),
     "qi_fft_c2c": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_int, _c_int, _c_vp]),
     "qi_cwt_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int]),
     "qi_cwt_fft": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_dbl, _c_int, _c_int,
                             _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_vp]),
-    "qi_atoms_time": (_c_int, [_c_vp, _c_int, _c_i64, _c_dbl, _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
+    "qi_atoms_time": (_c_int, [_c_vp, _c_int, _c_i64, _c_dbl, _c_int, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),
+    "qi_abs_log2": (_c_int, [_c_vp, _c_i64, _c_int, _c_int, _c_int, _c_dbl, _c_vp, _c_vp]),
     "qi_stx_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int, _c_int, _c_int]),
     "qi_stx_fft": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int,
                             _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_vp]),
     "qi_stft": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_int, _c_dbl, _c_int,
                          _c_int, _c_vp, _c_vp, _c_vp]),
+    "qi_power_reduce": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "qi_shannon": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_vp, _c_dbl, _c_dbl,
+                            _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "qi_power_bits": (_c_int, [_c_vp, _c_i64, _c_i64, _c_int, _c_vp, _c_dbl, _c_vp, _c_vp]),
+    "qi_tdr_marginal": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "qi_rfft": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
     "qi_stx_windows": (_c_int, [_c_vp, _c_int, _c_i64, _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
 }
 

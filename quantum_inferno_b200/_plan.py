@@ -52,6 +52,30 @@ def gabor_bands(band_order_nth, n_points, frequency_hz, frequency_sample_rate_hz
     return bands, scale, omega, amp
 
 
+def nearest_fft_bin(frequency, n_points, sample_interval):
+    """``np.abs(np.fft.fftfreq(n_points, sample_interval) - frequency).argmin()`` -- the Stockwell shift index
+    of reference styx_stx.py:167,233 -- evaluated on a handful of candidate bins with the same float64
+    expressions (bin value = signed_bin * (1/(n*d)), first minimum wins) instead of on the whole bin table,
+    so it stays O(1) for 2^28-point records."""
+    n = int(n_points)
+    val = 1.0 / (n * sample_interval)
+    n_pos = (n - 1) // 2 + 1                      # indices [0, n_pos) hold bins 0..n_pos-1, the rest are negative
+
+    def bin_value(idx):
+        return (idx if idx < n_pos else idx - n) * val
+
+    cand = {0, n_pos - 1, min(n_pos, n - 1), n - 1}
+    guess = frequency / val
+    if np.isfinite(guess):
+        for base in (int(np.floor(guess)), int(np.ceil(guess))):
+            for signed in (base - 1, base, base + 1):
+                if 0 <= signed < n_pos:
+                    cand.add(signed)
+                elif -(n // 2) <= signed < 0:
+                    cand.add(signed + n)
+    return min(sorted(cand), key=lambda idx: (abs(bin_value(idx) - frequency), idx))
+
+
 def stx_bands(band_order_nth, n_points, frequency_sample_rate_hz):
     """Band table of styx_stx.stx_complex_any_scale_pow2 (reference styx_stx.py:206-233).
     sigma uses the exact band centre, the shift index is the first argmin over the fft bins.
@@ -59,11 +83,10 @@ def stx_bands(band_order_nth, n_points, frequency_sample_rate_hz):
     from ._lib import STX_BAND
     f_stx = scales.log_frequency_hz_from_fft_points(frequency_sample_hz=frequency_sample_rate_hz,
                                                     fft_points=n_points, scale_order=band_order_nth)
-    f_fft = np.fft.fftfreq(n_points, 1 / frequency_sample_rate_hz)
     omega_stx = 2 * np.pi * f_stx / frequency_sample_rate_hz
     bands = np.zeros(len(f_stx), dtype=STX_BAND)
     bands["sigma"] = scales.cycles_from_order(scale_order=band_order_nth) / omega_stx
-    bands["shift"] = [int(np.abs(f_fft - f).argmin()) for f in f_stx]
+    bands["shift"] = [nearest_fft_bin(f, n_points, 1 / frequency_sample_rate_hz) for f in f_stx]
     return f_stx, bands
 
 

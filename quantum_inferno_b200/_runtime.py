@@ -1,0 +1,105 @@
+"""
+Device plumbing: PyTorch is used only to own HBM buffers and the CUDA stream; every kernel is launched
+through the C ABI of libqi_b200.so with raw pointers.
+
+``get_runtime()`` returns the CUDA runtime or raises -- there is no CPU path in this package.
+(The test-suite injects its own debug runtime with ``use_runtime`` to drive a g++ build of the same
+kernel sources on machines without a GPU; that object lives under tests/emul/, not here.)
+"""
+import contextlib
+
+import numpy as np
+
+from . import _lib
+
+DTYPE_CODE = {"float32": _lib.QI_F32, "float64": _lib.QI_F64}
+COMPLEX_OF = {"float32": "complex64", "float64": "complex128"}
+
+
+def dtype_name(dtype, default="float64"):
+    """Normalise a user dtype (None, str, numpy or torch dtype) to 'float32' / 'float64'."""
+    if dtype is None:
+        return default
+    s = str(dtype).replace("torch.", "")
+    s = {"f4": "float32", "f8": "float64", "single": "float32", "double": "float64", "fp32": "float32",
+         "fp64": "float64", "<class 'numpy.float32'>": "float32", "<class 'numpy.float64'>": "float64"}.get(s, s)
+    if s not in DTYPE_CODE:
+        raise ValueError(f"dtype must be float32 or float64, got {dtype!r}")
+    return s
+
+
+class CudaRuntime:
+    """torch-backed buffers on one CUDA device + the bound CUDA library."""
+    name = "cuda"
+
+    def __init__(self, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("quantum_inferno_b200 needs a CUDA device (B200, sm_100a); none is visible and "
+                               "there is no CPU fallback")
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._ws = None
+
+    # ---- buffers
+    def _tdtype(self, name):
+        return getattr(self.torch, name)
+
+    def empty(self, shape, dtype):
+        return self.torch.empty(tuple(int(s) for s in shape), dtype=self._tdtype(dtype), device=self.device)
+
+    def zeros(self, shape, dtype):
+        return self.torch.zeros(tuple(int(s) for s in shape), dtype=self._tdtype(dtype), device=self.device)
+
+    def is_device_array(self, x):
+        return isinstance(x, self.torch.Tensor)
+
+    def asarray(self, x, dtype):
+        """numpy / torch (any device) -> contiguous tensor of `dtype` on this device."""
+        t = x if isinstance(x, self.torch.Tensor) else self.torch.from_numpy(np.ascontiguousarray(x))
+        return t.to(device=self.device, dtype=self._tdtype(dtype), non_blocking=True).contiguous()
+
+    def ptr(self, buf):
+        return 0 if buf is None else buf.data_ptr()
+
+    def stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def workspace(self, nbytes):
+        """Grow-only scratch buffer (256-byte aligned by the caching allocator)."""
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
+        return self._ws
+
+    def to_numpy(self, buf):
+        return buf.detach().cpu().numpy()
+
+    def reshape(self, buf, shape):
+        return buf.reshape(tuple(shape))
+
+
+_runtime = None
+
+
+def get_runtime():
+    global _runtime
+    if _runtime is None:
+        _runtime = CudaRuntime()
+    return _runtime
+
+
+@contextlib.contextmanager
+def use_runtime(rt):
+    """Temporarily install another runtime object (used by the test-suite's kernel-logic emulator)."""
+    global _runtime
+    prev, _runtime = _runtime, rt
+    try:
+        yield rt
+    finally:
+        _runtime = prev
+
+
+def finish(rt, buf, want_numpy):
+    return rt.to_numpy(buf) if want_numpy else buf

@@ -2,9 +2,43 @@
 #include "qi_fft.cuh"
 #include "qi_host.h"
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 namespace qi {
 
 thread_local char g_last_cuda_error[256] = {0};
+
+// ---------------------------------------------------------------- launch accounting / event timing
+#ifndef QI_EMUL
+namespace {
+struct ProfRec { cudaEvent_t a, b; int cat; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_recs;
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_prof_on{0};
+thread_local int g_prof_cat = QI_CAT_OTHER;
+thread_local cudaEvent_t g_prof_pending = nullptr;
+}  // namespace
+void prof_set_category(int cat) { g_prof_cat = cat; }
+void prof_begin(cudaStream_t st) {
+    g_launches.fetch_add(1);
+    if (!g_prof_on.load()) return;
+    cudaEventCreate(&g_prof_pending);
+    cudaEventRecord(g_prof_pending, st);
+}
+void prof_end(cudaStream_t st) {
+    if (!g_prof_pending) return;
+    ProfRec r;
+    r.a = g_prof_pending; r.cat = g_prof_cat;
+    g_prof_pending = nullptr;
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back(r);
+}
+#endif
 
 int check_cuda(const char* where) {
     cudaError_t e = cudaGetLastError();
@@ -37,11 +71,81 @@ static int fft_c2c_impl(const void* in, void* out, i64 batch, int log2n, int inv
     return check_cuda("qi_fft_c2c");
 }
 
+// natural-order one-sided spectrum out of the bit-reversed full spectrum
+template <typename T>
+__global__ void half_spectrum_gather_kernel(const cplx<T>* spec, int logn, cplx<T>* out) {
+    const i64 n = 1ll << logn;
+    const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 m = blockIdx.y;
+    if (k > n / 2) return;
+    out[m * (n / 2 + 1) + k] = spec[m * n + (i64)brev_bits((unsigned)k, logn)];
+}
+
+template <typename T>
+static int rfft_impl(const void* sig, i64 M, i64 n, i64 stride, void* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    int logn = 0;
+    while ((1ll << logn) < n) ++logn;
+    if ((1ll << logn) != n) return QI_ERR_ARG;
+    if (ws_bytes < sizeof(cplx<T>) * (size_t)M * n) return QI_ERR_WORKSPACE;
+    if (M > 65535) return QI_ERR_UNSUPPORTED;
+    cplx<T>* spec = static_cast<cplx<T>*>(ws);
+    const FftPlan plan = make_plan(logn, (int)sizeof(cplx<T>));
+    for (int p = 0; p < plan.npass; ++p) {
+        DstComplex<T> d{spec, n, (T)1};
+        if (p == 0) {
+            SrcRealPad<T> s{static_cast<const T*>(sig), stride, n};
+            launch_pass<T, FFT_FWD>(plan, p, M, s, d, 0, st);
+        } else {
+            SrcComplex<T> s{spec, n};
+            launch_pass<T, FFT_FWD>(plan, p, M, s, d, 0, st);
+        }
+    }
+    dim3 grid((unsigned)((n / 2 + 1 + 255) / 256), (unsigned)M);
+    QI_LAUNCH((half_spectrum_gather_kernel<T>), grid, dim3(256), 0, st, (const cplx<T>*)spec, logn, static_cast<cplx<T>*>(out));
+    return check_cuda("qi_rfft");
+}
+
 }  // namespace qi
 
 extern "C" {
 
+int qi_rfft(const void* sig, int64_t M, int64_t n, int64_t stride, int dtype, void* out, void* ws, size_t ws_bytes,
+            void* stream) {
+    if (!sig || !out || !ws || M <= 0 || n <= 0 || stride < n) return QI_ERR_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == QI_F32) return qi::rfft_impl<float>(sig, M, n, stride, out, ws, ws_bytes, st);
+    if (dtype == QI_F64) return qi::rfft_impl<double>(sig, M, n, stride, out, ws, ws_bytes, st);
+    return QI_ERR_ARG;
+}
+
 int qi_abi_version(void) { return QI_ABI_VERSION; }
+
+#ifndef QI_EMUL
+int64_t qi_launch_count(void) { return qi::g_launches.load(); }
+int qi_profile_enable(int on) { qi::g_prof_on.store(on ? 1 : 0); return QI_OK; }
+int qi_profile_read(double* total_ms, int64_t* launches) {
+    if (!total_ms || !launches) return QI_ERR_ARG;
+    for (int i = 0; i < QI_N_CATEGORIES; ++i) { total_ms[i] = 0.0; launches[i] = 0; }
+    std::lock_guard<std::mutex> lk(qi::g_prof_mu);
+    for (auto& r : qi::g_prof_recs) {
+        cudaEventSynchronize(r.b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        if (r.cat >= 0 && r.cat < QI_N_CATEGORIES) { total_ms[r.cat] += ms; launches[r.cat] += 1; }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    qi::g_prof_recs.clear();
+    return qi::check_cuda("qi_profile_read");
+}
+#else
+int64_t qi_launch_count(void) { return 0; }
+int qi_profile_enable(int) { return QI_OK; }
+int qi_profile_read(double* total_ms, int64_t* launches) {
+    for (int i = 0; i < QI_N_CATEGORIES; ++i) { if (total_ms) total_ms[i] = 0.0; if (launches) launches[i] = 0; }
+    return QI_OK;
+}
+#endif
 
 const char* qi_error_string(int code) {
     switch (code) {

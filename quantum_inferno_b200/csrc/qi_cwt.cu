@@ -52,16 +52,21 @@ QI_DEV cplx<T> gabor_response(const DevBand& b, i64 k, int logL, int half_shift)
 
 // ---------------------------------------------------------------- time-domain atom sample (double)
 // x replicates the reference's rounding: fs*(m/fs - ((N-1)/fs)/2)
-QI_DEV void atom_sample(const DevBand& b, i64 m, i64 n_points, double fs, double* re, double* im) {
+QI_DEV double atom_xtime(i64 m, i64 n_points, double fs) {
     const double t = (double)m / fs;
     const double off = ((double)(n_points - 1) / fs) / 2.0;
-    const double x = fs * (t - off);
+    return fs * (t - off);
+}
+QI_DEV void atom_value(const DevBand& b, double x, double* re, double* im) {
     const double env = b.amp * exp(-b.p_re * x * x);
     const double ph = b.omega * x - b.p_im * x * x;
     double s, c;
     sincos(ph, &s, &c);
     *re = env * c;
     *im = env * s;
+}
+QI_DEV void atom_sample(const DevBand& b, i64 m, i64 n_points, double fs, double* re, double* im) {
+    atom_value(b, atom_xtime(m, n_points, fs), re, im);
 }
 
 // Source for the atom-table forward FFT.  batch = table band index.
@@ -106,12 +111,13 @@ template <typename T> struct SrcCwtSpec {
 
 // plain kernel writing time-domain atoms (public API wavelet_centered_4cwt)
 template <typename T>
-__global__ void atoms_time_kernel(const DevBand* bands, int n_bands, i64 n_points, double fs, cplx<T>* out) {
+__global__ void atoms_time_kernel(const DevBand* bands, int n_bands, i64 n_points, double fs, const double* xtime,
+                                  cplx<T>* out) {
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (i >= n_points) return;
     double re, im;
-    atom_sample(bands[b], i, n_points, fs, &re, &im);
+    atom_value(bands[b], xtime ? xtime[i] : atom_xtime(i, n_points, fs), &re, &im);
     out[(i64)b * n_points + i] = mk<T>((T)re, (T)im);
 }
 
@@ -205,6 +211,7 @@ static int cwt_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiAtomB
     const T one = (T)1;
 
     // record spectra
+    prof_set_category(QI_CAT_FFT_FWD);
     for (int p = 0; p < np; ++p) {
         DstComplex<T> d{spec, lo.L, one};
         if (p == 0) {
@@ -239,18 +246,20 @@ static int cwt_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiAtomB
             SrcComplex<T> s2{work, lo.L};
             DstComplex<T> d1{work, lo.L, one};
             DstCwtOut<T> d2{static_cast<cplx<T>*>(out_c), static_cast<T*>(out_p), band_sum, band0, geo, 0.0};
+            prof_set_category(last ? QI_CAT_INV_LAST : (first ? QI_CAT_INV_FIRST : QI_CAT_INV_MID));
             if (first && last) launch_pass<T, FFT_INV>(plan, p, nb, s1, d2, 256, st);
             else if (first) launch_pass<T, FFT_INV>(plan, p, nb, s1, d1, 0, st);
             else if (last) launch_pass<T, FFT_INV>(plan, p, nb, s2, d2, 256, st);
             else launch_pass<T, FFT_INV>(plan, p, nb, s2, d1, 0, st);
         }
     }
+    prof_set_category(QI_CAT_OTHER);
     return check_cuda("qi_cwt_fft");
 }
 
 template <typename T>
-static int atoms_time_impl(const QiAtomBand* hb, int B, i64 N, double fs, void* out, void* ws, size_t ws_bytes,
-                           cudaStream_t st) {
+static int atoms_time_impl(const QiAtomBand* hb, int B, i64 N, double fs, const double* xtime, void* out, void* ws,
+                           size_t ws_bytes, cudaStream_t st) {
     if (ws_bytes < sizeof(DevBand) * (size_t)B) return QI_ERR_WORKSPACE;
     std::vector<DevBand> db; std::vector<int> tab;
     std::vector<QiAtomBand> tmp(hb, hb + B);
@@ -262,7 +271,7 @@ static int atoms_time_impl(const QiAtomBand* hb, int B, i64 N, double fs, void* 
     cudaStreamSynchronize(st);
 #endif
     dim3 grid((unsigned)((N + 255) / 256), (unsigned)B);
-    QI_LAUNCH((atoms_time_kernel<T>), grid, dim3(256), 0, st, d_bands, B, N, fs, static_cast<cplx<T>*>(out));
+    QI_LAUNCH((atoms_time_kernel<T>), grid, dim3(256), 0, st, (const DevBand*)d_bands, B, N, fs, xtime, static_cast<cplx<T>*>(out));
     return check_cuda("qi_atoms_time");
 }
 
@@ -292,12 +301,12 @@ int qi_cwt_fft(const void* sig, int64_t C, int64_t N, int64_t stride, const QiAt
     return QI_ERR_ARG;
 }
 
-int qi_atoms_time(const QiAtomBand* bands, int B, int64_t N, double fs, int dtype, void* out, void* ws,
-                  size_t ws_bytes, void* stream) {
-    if (!bands || !out || !ws || B <= 0 || N <= 0) return QI_ERR_ARG;
+int qi_atoms_time(const QiAtomBand* bands, int B, int64_t N, double fs, int dtype, const double* xtime, void* out,
+                  void* ws, size_t ws_bytes, void* stream) {
+    if (!bands || !out || !ws || B <= 0 || N <= 0 || B > 65535) return QI_ERR_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (dtype == QI_F32) return qi::atoms_time_impl<float>(bands, B, N, fs, out, ws, ws_bytes, st);
-    if (dtype == QI_F64) return qi::atoms_time_impl<double>(bands, B, N, fs, out, ws, ws_bytes, st);
+    if (dtype == QI_F32) return qi::atoms_time_impl<float>(bands, B, N, fs, xtime, out, ws, ws_bytes, st);
+    if (dtype == QI_F64) return qi::atoms_time_impl<double>(bands, B, N, fs, xtime, out, ws, ws_bytes, st);
     return QI_ERR_ARG;
 }
 

@@ -10,13 +10,25 @@
 #include "cuda_emul.h"
 #define QI_LAUNCH(kern, grid, block, smem, stream, ...) \
     qi_emul::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); })
+namespace qi { inline void prof_set_category(int) {} }
 #define QI_DYN_SMEM(name) unsigned char* name = QI_EMUL_DYN_SMEM
 #define QI_HD inline
 #define QI_DEV inline
 #else
 #include <cuda_runtime.h>
-#define QI_LAUNCH(kern, grid, block, smem, stream, ...) \
-    do { auto qi_kfn_ = kern; qi_kfn_<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); } while (0)
+namespace qi {
+// launch accounting + optional per-category CUDA-event timing (qi_profile_* in include/qi_b200.h)
+void prof_set_category(int cat);
+void prof_begin(cudaStream_t st);
+void prof_end(cudaStream_t st);
+}
+#define QI_LAUNCH(kern, grid, block, smem, stream, ...)                                   \
+    do {                                                                                   \
+        auto qi_kfn_ = kern;                                                               \
+        qi::prof_begin(stream);                                                            \
+        qi_kfn_<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                       \
+        qi::prof_end(stream);                                                              \
+    } while (0)
 #define QI_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 #define QI_HD __host__ __device__ __forceinline__
 #define QI_DEV __device__ __forceinline__

@@ -129,6 +129,7 @@ static int stft_impl(const void* sig, i64 C, i64 n_points, i64 stride, const voi
     cudaFuncSetAttribute(stft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
     if (psd_acc) cudaMemsetAsync(psd_acc, 0, sizeof(double) * (size_t)C * (nfft / 2 + 1), st);
+    prof_set_category(QI_CAT_STFT);
     QI_LAUNCH((stft_kernel<T>), grid, dim3(256), smem, st, static_cast<const T*>(sig), static_cast<const T*>(window),
               g, static_cast<cplx<T>*>(out), psd_acc);
     return check_cuda("qi_stft");

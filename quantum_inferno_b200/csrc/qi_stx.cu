@@ -89,6 +89,7 @@ static int stx_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiStxBa
     const FftPlan plan = make_plan(lo.logL, (int)sizeof(cplx<T>));
     const int np = plan.npass;
     const T one = (T)1;
+    prof_set_category(QI_CAT_FFT_FWD);
     for (int p = 0; p < np; ++p) {
         DstComplex<T> d{spec, lo.L, one};
         if (p == 0) {
@@ -109,12 +110,14 @@ static int stx_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiStxBa
             SrcComplex<T> s2{work, lo.L};
             DstComplex<T> d1{work, lo.L, one};
             DstCwtOut<T> d2{static_cast<cplx<T>*>(out_c), static_cast<T*>(out_p), band_sum, band0, geo, 0.0};
+            prof_set_category(last ? QI_CAT_INV_LAST : (first ? QI_CAT_INV_FIRST : QI_CAT_INV_MID));
             if (first && last) launch_pass<T, FFT_INV>(plan, p, nb, s1, d2, 256, st);
             else if (first) launch_pass<T, FFT_INV>(plan, p, nb, s1, d1, 0, st);
             else if (last) launch_pass<T, FFT_INV>(plan, p, nb, s2, d2, 256, st);
             else launch_pass<T, FFT_INV>(plan, p, nb, s2, d1, 0, st);
         }
     }
+    prof_set_category(QI_CAT_OTHER);
     return check_cuda("qi_stx_fft");
 }
 

@@ -1,0 +1,79 @@
+"""
+Fused order-N Gabor CWT + power + Shannon information / entropy -- the composition the reference spells as
+
+    f, t, cwt = styx_cwt.cwt_complex_any_scale_pow2(N, sig, fs)          # styx_cwt.py:147-198
+    power     = np.abs(cwt) ** 2
+    shannon   = tfr_info.shannon_stft_from_tfr_power(power)              # tfr_info.py:231-236
+
+kept on the device end to end: the complex TFR is never materialised (at the north-star size it would be
+~1 TB), the power plane is written once by the last inverse-FFT pass together with the fp64 per-band sums,
+and one streaming pass turns it into the information plane -log2(P/S + eps64) and the per-band entropy sums.
+
+Multi-GPU: records (channels) shard with no communication; one long record can instead be sharded by band,
+in which case the only exchange is one all-reduce of the per-record total power S (``allreduce=``).
+"""
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import _driver, _plan
+from . import scales_dyadic as scales
+from ._runtime import dtype_name, get_runtime
+
+
+@dataclass
+class CwtEntropy:
+    """Device-resident result.  Shapes: C records, B (local) bands, N samples."""
+    frequency_hz: np.ndarray            # [B] band centres of the bands held here (ascending)
+    band_slice: tuple                   # (first, last+1) index of those bands in the full table
+    n_bands_total: int
+    power: object                       # [C, B, N]  |cwt|^2
+    info: object                        # [C, B, N]  -log2(P/S + eps64)            (None if not requested)
+    band_power: object                  # [C, B] fp64  sum_t P
+    total_power: object                 # [C]    fp64  S (after the all-reduce when band-sharded)
+    band_entropy_bits: object           # [C, B] fp64  sum_t pdf*info              (None if not requested)
+    ref_bits: float                     # log2(D)/D with D = B_total * N
+
+    def entropy_bits(self):
+        """[C] total Shannon bits of the bands held here (sum over ranks when band-sharded)."""
+        return self.band_entropy_bits.sum(-1)
+
+
+def cwt_power_entropy(band_order_nth: float, sig_wf, frequency_sample_rate_hz: float, dictionary_type: str = "norm",
+                      *, dtype="float32", spectrum: str = "auto", band_slice: Optional[tuple] = None,
+                      allreduce: Optional[Callable] = None, want_info: bool = True,
+                      out_power=None, out_info=None) -> CwtEntropy:
+    """Power, information and entropy of the order-N Gabor CWT of ``sig_wf`` ([N] or [C, N]; numpy or CUDA tensor).
+
+    band_slice : (b0, b1) computes only bands b0..b1-1 of the standard table (band sharding of one long record).
+    allreduce  : callable applied in place to the fp64 [C] tensor of local total power before normalisation
+                 (e.g. ``lambda t: torch.distributed.all_reduce(t)``); None = single device.
+    out_power / out_info : optional preallocated [C, B, N] device buffers to write into.
+    """
+    rt = get_runtime()
+    dt = dtype_name(dtype, default="float32")
+    sig, _ = _driver._as_2d(rt, sig_wf, dt)
+    n_points = int(sig.shape[1])
+    freq_all = scales.log_frequency_hz_from_fft_points(
+        frequency_sample_hz=frequency_sample_rate_hz, fft_points=n_points, scale_order=band_order_nth)
+    b0, b1 = (0, len(freq_all)) if band_slice is None else (int(band_slice[0]), int(band_slice[1]))
+    if not (0 <= b0 < b1 <= len(freq_all)):
+        raise ValueError(f"band_slice {band_slice} outside the {len(freq_all)}-band table")
+    freq = freq_all[b0:b1]
+    bands, _, _, _ = _plan.gabor_bands(band_order_nth, n_points, freq, frequency_sample_rate_hz, dictionary_type,
+                                       dt, spectrum)
+    res = _driver.cwt_fft(sig, bands, frequency_sample_rate_hz, dt, want_complex=False, want_power=True,
+                          want_band_sum=True, rt=rt, out_power=out_power)
+    power, band_power = res["power"], res["band_sum"]
+    total = band_power.sum(-1)                               # [C] fp64 (tiny)
+    if allreduce is not None:
+        allreduce(total)
+    deg_free = len(freq_all) * n_points
+    info = ent = None
+    if want_info:
+        sh = _driver.shannon(power, dt, 0, total, deg_free, eps=_driver.EPS64, planes=("info",), entropy_sum=True,
+                             rt=rt, out_info=out_info)
+        info, ent = sh["info"], sh["entropy_sum"]
+    return CwtEntropy(freq, (b0, b1), len(freq_all), power, info, band_power, total, ent,
+                      float(np.log2(deg_free) / deg_free))

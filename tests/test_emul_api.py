@@ -1,0 +1,154 @@
+"""CPU-side check of the kernel LOGIC and of the Python drivers: the package's public API is run with the
+test-only emulator runtime (tests/emul/, a g++ build of the same .cu sources) and compared with the golden
+vectors the reference produced.  The GPU parity tests proper are in test_gpu_parity.py (-m gpu)."""
+import numpy as np
+import pytest
+
+from quantum_inferno_b200 import _runtime, cwt_atoms, styx_cwt, styx_fft, styx_stx, tfr_info
+from tests.emul.emul_runtime import EmulRuntime
+
+FS = 800.0
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emul():
+    with _runtime.use_runtime(EmulRuntime()) as rt:
+        yield rt
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - b)) / np.max(np.abs(b)))
+
+
+@pytest.mark.parametrize("tag,xkey,order,dic", [
+    ("n2048_o3_norm", "x2048", 3, "norm"), ("n1024_o3_spect", "x1024", 3, "spect"),
+    ("n1024_o3_unit", "x1024", 3, "unit"), ("n1024_o6_norm", "x1024", 6, "norm"),
+    ("n1024_o12_norm", "x1024", 12, "norm"), ("n1024_o1_norm", "x1024", 1, "norm")])
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-10), ("float32", 2e-6)])
+def test_cwt(golden, tag, xkey, order, dic, dtype, tol):
+    g = golden("cwt")
+    f, t, c = styx_cwt.cwt_complex_any_scale_pow2(order, g[xkey], FS, dictionary_type=dic, dtype=dtype)
+    assert np.array_equal(f, g[tag + "_f"])
+    assert c.shape == g[tag + "_c"].shape and rel(c, g[tag + "_c"]) < tol
+    assert np.array_equal(t, np.arange(len(g[xkey])) / FS)
+
+
+def test_cwt_table_spectrum_and_batch(golden):
+    g = golden("cwt")
+    x = np.stack([g["x1024"], g["x1024"][::-1]])
+    f, t, c = styx_cwt.cwt_complex_any_scale_pow2(3, x, FS, spectrum="table")
+    assert c.shape == (2, 18, 1024)
+    assert rel(c[0], g["n1024_o3_norm_c"] if "n1024_o3_norm_c" in g.files else c[0]) < 1e-12
+    f2, _, (c2, p2) = styx_cwt.cwt_complex_any_scale_pow2(3, x, FS, outputs="both")
+    assert rel(c2, c) < 1e-12 and rel(p2, np.abs(c) ** 2) < 1e-12
+    with pytest.raises(NotImplementedError):
+        styx_cwt.cwt_complex_any_scale_pow2(3, g["x1024"], FS, cwt_type="morlet2")
+
+
+def test_atoms(golden):
+    g = golden("cwt")
+    atoms, t_s, scale, omega, amp = styx_cwt.wavelet_centered_4cwt(3, 512, np.array([5.0, 50.0, 200.0]), FS, "norm")
+    assert rel(atoms, g["atoms512"]) < 1e-13
+    assert np.array_equal(t_s, g["atoms512_t"])
+    assert np.array_equal(scale[:, 0], g["atoms512_scale"]) and scale.shape == (3, 512)
+    assert np.array_equal(omega[:, 0], g["atoms512_omega"]) and np.array_equal(amp[:, 0], g["atoms512_amp"])
+    a1, _, s1, o1, m1 = styx_cwt.wavelet_centered_4cwt(3, 512, 50.0, FS)
+    assert a1.shape == (512,) and rel(a1, g["atoms512"][1]) < 1e-13 and s1 == g["atoms512_scale"][1]
+
+
+@pytest.mark.parametrize("tag,xkey,order", [("n2048_o3", "x2048", 3), ("n1024_o6", "x1024", 6), ("n1024_o12", "x1024", 12)])
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-10), ("float32", 2e-6)])
+def test_stx(golden, tag, xkey, order, dtype, tol):
+    g = golden("stx")
+    f, t, c = styx_stx.stx_complex_any_scale_pow2(order, g[xkey], FS, dtype=dtype)
+    assert np.array_equal(f, g[tag + "_f"]) and rel(c, g[tag + "_c"]) < tol
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("lin", dict()), ("geo", dict(is_geometric=True)), ("inf", dict(is_geometric=True, is_inferno=True)),
+    ("opt", dict(factor_q=0.5, power_p=1.0, power_r=0.5, frequency_min=10.0, frequency_max=300.0, frequency_step=5.0))])
+def test_stx_general(golden, tag, kw):
+    g = golden("stx")
+    tfr, psd, f, ffft, win = styx_stx.tfr_stx_fft(g["x256"], 1 / FS, scale_order_input=3.0, n_fft_in=256, **kw)
+    assert np.array_equal(f, g[f"gen_{tag}_f"]) and np.array_equal(ffft, g[f"gen_{tag}_ffft"])
+    assert rel(tfr, g[f"gen_{tag}_tfr"]) < 1e-10 and rel(psd, g[f"gen_{tag}_psd"]) < 1e-10
+    assert rel(win, g[f"gen_{tag}_win"]) < 1e-12
+
+
+def test_stx_errors(golden):
+    g = golden("stx")
+    with pytest.raises(TypeError):
+        styx_stx.tfr_stx_fft(g["x256"], 1 / FS)                      # n_fft_in=None, as upstream
+    with pytest.raises(ValueError):
+        styx_stx.tfr_stx_fft(g["x256"], 1 / FS, n_fft_in=128)
+    with pytest.raises(TypeError):
+        styx_stx.tfr_stx_fft(g["x256"], 1 / FS, n_fft_in=512)        # real padding path is broken upstream too
+    with pytest.raises(ValueError):
+        styx_stx.stx_complex_any_scale_pow2(3, g["x256"][:200], FS)
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 1e-6)])
+def test_stft(golden, dtype, tol):
+    g = golden("stft")
+    f, t, z = styx_fft.stft_complex_pow2(g["tone8192"], FS, 1024, alpha=1.0, dtype=dtype)
+    assert np.array_equal(f, g["hann_f"]) and np.allclose(t, g["hann_t"], rtol=0, atol=1e-12)
+    assert z.shape == (513, 17) and rel(z, g["hann_z"]) < tol
+    f, t, z = styx_fft.stft_complex_pow2(g["xb"], FS, 256, dtype=dtype)
+    assert z.shape == g["tukey_z"].shape and rel(z, g["tukey_z"]) < tol
+    f, t, z = styx_fft.stft_complex_pow2(g["xb"][0], FS, 200, overlap_points=150, nfft_points=512, alpha=0.5, dtype=dtype)
+    assert z.shape == g["odd_z"].shape and rel(z, g["odd_z"]) < tol and np.allclose(t, g["odd_t"], rtol=0, atol=1e-12)
+    f, t, z = styx_fft.gtx_complex_pow2(g["xb"], FS, 512, dtype=dtype)
+    assert rel(z, g["gtx_z"]) < tol
+    f, p = styx_fft.welch_power_pow2(g["xb"], FS, 512, dtype=dtype)
+    assert np.array_equal(f, g["welch_f"]) and rel(p, g["welch_p"]) < tol
+    z, zb, t, f = styx_fft.stft_from_sig(g["tone8192"], FS, 3, dtype=dtype)
+    assert z.shape == (257, 33) and rel(z, g["sfs_z"]) < tol
+    if dtype == "float64":
+        cells = g["sfs_bits"] > -40.0
+        assert np.max(np.abs(zb - g["sfs_bits"])[cells]) < 1e-9
+    with pytest.raises(ValueError):
+        styx_fft.stft_from_sig(g["tone8192"][:100], FS, 3)
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("fft_norm", dict(cwt_type="fft")), ("conv_norm", dict(cwt_type="conv")),
+    ("fft_spect", dict(cwt_type="fft", dictionary_type="spect")), ("fft_shift", dict(cwt_type="fft", index_shift=1.0)),
+    ("fft_o6", dict(cwt_type="fft", band_order_nth=6))])
+def test_cwt_atoms(golden, tag, kw):
+    g = golden("atoms")
+    c, cb, t, f = cwt_atoms.cwt_chirp_from_sig(g["x1024"], FS, **kw)
+    assert np.array_equal(f, g[tag + "_f"])
+    assert rel(c, g[tag + "_c"]) < 1e-10
+    cells = g[tag + "_bits"] > -30.0
+    assert np.max(np.abs(cb - g[tag + "_bits"])[cells]) < 1e-8
+    with pytest.raises(ValueError):
+        cwt_atoms.cwt_chirp_from_sig(g["x1024"], FS, cwt_type="nope")
+    with pytest.raises(NotImplementedError):
+        cwt_atoms.cwt_chirp_from_sig(g["x1024"], FS, cwt_type="morlet2")
+
+
+def test_tfr_info(golden):
+    g = golden("info")
+    p = g["power"]
+    for tag, obj, d in [("glob", tfr_info.shannon_stft_from_tfr_power(p), p.size),
+                        ("ptime", tfr_info.ShannonStftPerTime(p), p.shape[0]),
+                        ("pfreq", tfr_info.ShannonStftPerFreq(p), p.shape[1])]:
+        assert np.max(np.abs(obj.info - g[tag + "_info"])) < 1e-10
+        assert rel(obj.shannon_bits, g[tag + "_bits"]) < 1e-12
+        assert np.max(np.abs(obj.isnr - g[tag + "_isnr"])) < 1e-10 and rel(obj.esnr, g[tag + "_esnr"]) < 1e-12
+        assert obj.ref_bits == float(g[tag + "_ref"])
+    b0, b1, b2 = tfr_info.power_dynamics_scaled_bits(p)
+    assert np.max(np.abs(b0 - g["dyn_bits"])) < 1e-10 and np.max(np.abs(b1 - g["dyn_time"])) < 1e-10
+    assert np.max(np.abs(b2 - g["dyn_freq"])) < 1e-10
+    tdr, ff = tfr_info.shannon_tdr_fft(g["x1024"])
+    assert np.max(np.abs(tdr.info - g["tdr_info"])) < 1e-10 and rel(tdr.entropy, g["tdr_ent"]) < 1e-12
+    assert rel(tdr.marginal, g["tdr_marg"]) < 1e-13 and tdr.ref_entropy == float(g["tdr_ref"])
+    assert rel(ff.sig, g["fft_sig"]) < 1e-13 and rel(ff.marginal, g["fft_marg"]) < 1e-12
+    assert np.max(np.abs(ff.info - g["fft_info"])) < 1e-9 and np.max(np.abs(ff.angle_rads - g["fft_angle"])) < 1e-8
+    # batch extension == reference applied per matrix
+    pb = np.stack([p, 2.0 * p[::-1]])
+    ob = tfr_info.ShannonStftPerFreq(pb)
+    assert rel(ob.shannon_bits[0], g["pfreq_bits"]) < 1e-12 and ob.info.shape == pb.shape
+    # float32 planes stay inside the north-star tolerance (1e-3 bits)
+    o32 = tfr_info.shannon_stft_from_tfr_power(p, dtype="float32")
+    assert abs(float(o32.shannon_bits.sum()) - float(g["glob_bits"].sum())) < 1e-3

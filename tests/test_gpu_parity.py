@@ -1,0 +1,296 @@
+"""GPU parity tests (run on the B200 with `-m gpu`).  Every test goes through the public Python API, i.e.
+through the C ABI of libqi_b200.so; the oracle (oracle/qi_oracle.py) and the reference-generated golden
+vectors (tests/golden) are the checkers.  Tolerances are the north-star's: fp64 <= 1e-10 relative,
+fp32 <= 1e-4 relative L2 on power and <= 1e-3 bits on entropy, band/shift indices bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FS = 800.0
+TOL64 = 1e-10
+TOL32_L2 = 1e-4
+TOL32_BITS = 1e-3
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    from quantum_inferno_b200 import _runtime
+    _runtime._runtime = None
+    rt = _runtime.get_runtime()
+    assert rt.name == "cuda"
+    return torch
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - b)) / np.max(np.abs(b)))
+
+
+def l2(a, b):
+    return float(np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / np.linalg.norm(b))
+
+
+def synth(n, seed=0, chan=0):
+    k = np.arange(n)
+    f_c = 60.0 * 2.0 ** ((chan % 12) / 12.0)
+    chirp = 0.5 * np.cos(2 * np.pi * (1.0 * k / FS + 0.5 * (199.0 / (n / FS)) * (k / FS) ** 2))
+    return np.cos(2 * np.pi * f_c / FS * k) + chirp + np.random.default_rng(1234 + seed + chan).standard_normal(n) / 16.0
+
+
+# ----------------------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("tag,xkey,order,dic", [
+    ("n2048_o3_norm", "x2048", 3, "norm"), ("n1024_o3_spect", "x1024", 3, "spect"),
+    ("n1024_o3_unit", "x1024", 3, "unit"), ("n1024_o6_norm", "x1024", 6, "norm"),
+    ("n1024_o12_norm", "x1024", 12, "norm"), ("n1024_o1_norm", "x1024", 1, "norm")])
+def test_cwt_golden(torch_cuda, golden, tag, xkey, order, dic):
+    from quantum_inferno_b200 import styx_cwt
+    g = golden("cwt")
+    f, t, c = styx_cwt.cwt_complex_any_scale_pow2(order, g[xkey], FS, dictionary_type=dic)
+    assert c.dtype == np.complex128 and np.array_equal(f, g[tag + "_f"])
+    assert rel(c, g[tag + "_c"]) < TOL64
+    f, t, c32 = styx_cwt.cwt_complex_any_scale_pow2(order, g[xkey], FS, dictionary_type=dic, dtype="float32")
+    assert c32.dtype == np.complex64
+    assert l2(np.abs(c32) ** 2, np.abs(g[tag + "_c"]) ** 2) < TOL32_L2
+
+
+def test_cwt_survey_kats(torch_cuda, golden):
+    """The reference-produced known answers quoted in SURVEY.md section 8(c) (8192-sample tone)."""
+    from quantum_inferno_b200 import cwt_entropy, styx_cwt, tfr_info
+    g = golden("cwt")
+    x = g["tone8192"]
+    f, t, c = styx_cwt.cwt_complex_any_scale_pow2(3, x, FS)
+    assert c.shape == (27, 8192) and np.array_equal(f, g["kat8192_f"])
+    for row in (0, 19, 26):
+        assert rel(c[row], g[f"kat8192_row{row}"]) < TOL64
+    p = np.abs(c) ** 2
+    s = g["kat8192_scalars"]
+    assert abs(p.sum() - s[0]) / s[0] < 1e-12 and abs(p.max() - s[1]) / s[1] < 1e-12
+    assert np.unravel_index(p.argmax(), p.shape) == (19, 46)
+    sh = tfr_info.shannon_stft_from_tfr_power(p)
+    assert abs(sh.shannon_bits.sum() - s[2]) < 1e-10 and abs(sh.ref_bits - s[3]) < 1e-18
+    assert abs(sh.isnr.max() - s[4]) < 1e-10
+    assert abs(tfr_info.power_dynamics_scaled_bits(p)[0].min() - s[5]) < 1e-8
+    assert np.max(np.abs(tfr_info.ShannonStftPerFreq(p).shannon_bits.sum(axis=1) - g["kat8192_band_entropy"])) < 1e-10
+    assert np.max(np.abs(tfr_info.ShannonStftPerTime(p).shannon_bits.sum(axis=0) - g["kat8192_time_entropy"])) < 1e-10
+    # fused fp32 path
+    r = cwt_entropy.cwt_power_entropy(3, x, FS, dtype="float32")
+    assert l2(r.power[0].double().cpu().numpy(), p) < TOL32_L2
+    assert abs(float(r.entropy_bits()[0]) - s[2]) < TOL32_BITS
+    assert np.max(np.abs(r.band_power[0].cpu().numpy() - g["kat8192_band_sum"]) / g["kat8192_band_sum"].max()) < 1e-5
+
+
+def test_atoms_golden(torch_cuda, golden):
+    from quantum_inferno_b200 import styx_cwt
+    g = golden("cwt")
+    atoms, t_s, scale, omega, amp = styx_cwt.wavelet_centered_4cwt(3, 512, np.array([5.0, 50.0, 200.0]), FS, "norm")
+    assert rel(atoms, g["atoms512"]) < 1e-13 and np.array_equal(scale[:, 0], g["atoms512_scale"])
+
+
+@pytest.mark.parametrize("tag,xkey,order", [("n2048_o3", "x2048", 3), ("n1024_o6", "x1024", 6), ("n1024_o12", "x1024", 12)])
+def test_stx_golden(torch_cuda, golden, tag, xkey, order):
+    from quantum_inferno_b200 import styx_stx
+    g = golden("stx")
+    f, t, c = styx_stx.stx_complex_any_scale_pow2(order, g[xkey], FS)
+    assert np.array_equal(f, g[tag + "_f"]) and rel(c, g[tag + "_c"]) < TOL64
+    f, t, c32 = styx_stx.stx_complex_any_scale_pow2(order, g[xkey], FS, dtype="float32")
+    assert l2(np.abs(c32) ** 2, np.abs(g[tag + "_c"]) ** 2) < TOL32_L2
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("lin", dict()), ("geo", dict(is_geometric=True)), ("inf", dict(is_geometric=True, is_inferno=True)),
+    ("opt", dict(factor_q=0.5, power_p=1.0, power_r=0.5, frequency_min=10.0, frequency_max=300.0, frequency_step=5.0))])
+def test_stx_general_golden(torch_cuda, golden, tag, kw):
+    from quantum_inferno_b200 import styx_stx
+    g = golden("stx")
+    tfr, psd, f, ffft, win = styx_stx.tfr_stx_fft(g["x256"], 1 / FS, scale_order_input=3.0, n_fft_in=256, **kw)
+    assert np.array_equal(f, g[f"gen_{tag}_f"]) and np.array_equal(ffft, g[f"gen_{tag}_ffft"])
+    assert rel(tfr, g[f"gen_{tag}_tfr"]) < TOL64 and rel(psd, g[f"gen_{tag}_psd"]) < TOL64
+    assert rel(win, g[f"gen_{tag}_win"]) < 1e-12
+
+
+def test_stft_golden(torch_cuda, golden):
+    from quantum_inferno_b200 import styx_fft
+    g = golden("stft")
+    for dtype, tol in (("float64", 1e-12), ("float32", 1e-6)):
+        f, t, z = styx_fft.stft_complex_pow2(g["tone8192"], FS, 1024, alpha=1.0, dtype=dtype)
+        assert z.shape == (513, 17) and rel(z, g["hann_z"]) < tol and np.array_equal(f, g["hann_f"])
+        f, t, z = styx_fft.stft_complex_pow2(g["xb"], FS, 256, dtype=dtype)
+        assert z.shape == g["tukey_z"].shape and rel(z, g["tukey_z"]) < tol
+        f, t, z = styx_fft.stft_complex_pow2(g["xb"][0], FS, 200, overlap_points=150, nfft_points=512, alpha=0.5, dtype=dtype)
+        assert rel(z, g["odd_z"]) < tol
+        f, t, z = styx_fft.gtx_complex_pow2(g["xb"], FS, 512, dtype=dtype)
+        assert rel(z, g["gtx_z"]) < tol
+        f, p = styx_fft.welch_power_pow2(g["xb"], FS, 512, dtype=dtype)
+        assert rel(p, g["welch_p"]) < tol
+        z, zb, t, f = styx_fft.stft_from_sig(g["tone8192"], FS, 3, dtype=dtype)
+        assert z.shape == (257, 33) and rel(z, g["sfs_z"]) < tol
+    # survey KAT: sum of power 6.000001907348631, max 0.25 at (76, 1)
+    f, t, z = styx_fft.stft_complex_pow2(g["tone8192"], FS, 1024, alpha=1.0)
+    p = np.abs(z) ** 2
+    assert abs(p.sum() - 6.000001907348631) < 1e-9 and np.unravel_index(p.argmax(), p.shape) == (76, 1)
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("fft_norm", dict(cwt_type="fft")), ("conv_norm", dict(cwt_type="conv")),
+    ("fft_spect", dict(cwt_type="fft", dictionary_type="spect")), ("fft_shift", dict(cwt_type="fft", index_shift=1.0)),
+    ("fft_o6", dict(cwt_type="fft", band_order_nth=6))])
+def test_cwt_atoms_golden(torch_cuda, golden, tag, kw):
+    from quantum_inferno_b200 import cwt_atoms
+    g = golden("atoms")
+    c, cb, t, f = cwt_atoms.cwt_chirp_from_sig(g["x1024"], FS, **kw)
+    assert np.array_equal(f, g[tag + "_f"]) and rel(c, g[tag + "_c"]) < TOL64
+    cells = g[tag + "_bits"] > -30.0
+    assert np.max(np.abs(cb - g[tag + "_bits"])[cells]) < 1e-8
+
+
+def test_tfr_info_golden(torch_cuda, golden):
+    from quantum_inferno_b200 import tfr_info
+    g = golden("info")
+    p = g["power"]
+    for tag, obj in [("glob", tfr_info.shannon_stft_from_tfr_power(p)), ("ptime", tfr_info.ShannonStftPerTime(p)),
+                     ("pfreq", tfr_info.ShannonStftPerFreq(p))]:
+        assert np.max(np.abs(obj.info - g[tag + "_info"])) < TOL64 and rel(obj.shannon_bits, g[tag + "_bits"]) < TOL64
+        assert np.max(np.abs(obj.isnr - g[tag + "_isnr"])) < TOL64 and rel(obj.esnr, g[tag + "_esnr"]) < TOL64
+    b0, b1, b2 = tfr_info.power_dynamics_scaled_bits(p)
+    assert np.max(np.abs(b0 - g["dyn_bits"])) < TOL64 and np.max(np.abs(b1 - g["dyn_time"])) < TOL64
+    assert np.max(np.abs(b2 - g["dyn_freq"])) < TOL64
+    tdr, ff = tfr_info.shannon_tdr_fft(g["x1024"])
+    assert np.max(np.abs(tdr.info - g["tdr_info"])) < TOL64 and rel(ff.marginal, g["fft_marg"]) < TOL64
+    # torch in -> torch out, on the device
+    pt = torch_cuda.from_numpy(p).cuda()
+    o = tfr_info.ShannonStftPerFreq(pt)
+    assert o.info.is_cuda and np.max(np.abs(o.info.cpu().numpy() - g["pfreq_info"])) < TOL64
+
+
+# ----------------------------------------------------------------------------- live comparison with the oracle
+@pytest.mark.parametrize("order,logn", [(3, 14), (3, 16), (6, 13), (12, 12)])
+def test_cwt_vs_oracle(torch_cuda, order, logn):
+    """config[0]-shaped case (order 3, 2^16 @ 800 Hz) and smaller ones: multi-pass FFT sizes, all bands."""
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import cwt_entropy, styx_cwt
+    x = synth(1 << logn)
+    fr, tr, cr = orc.cwt_complex_any_scale_pow2(order, x, FS)
+    f, t, c = styx_cwt.cwt_complex_any_scale_pow2(order, x, FS)
+    assert np.array_equal(f, fr) and rel(c, cr) < TOL64
+    ref = orc.cwt_power_entropy(order, x, FS)
+    r = cwt_entropy.cwt_power_entropy(order, x, FS, dtype="float32")
+    assert l2(r.power[0].double().cpu().numpy(), ref["power"]) < TOL32_L2
+    assert abs(float(r.entropy_bits()[0]) - ref["entropy_bits"]) < TOL32_BITS
+    r64 = cwt_entropy.cwt_power_entropy(order, x, FS, dtype="float64")
+    assert rel(r64.power[0].cpu().numpy(), ref["power"]) < TOL64
+    assert np.max(np.abs(r64.info[0].cpu().numpy() - ref["info"])) < 1e-9
+    assert abs(float(r64.entropy_bits()[0]) - ref["entropy_bits"]) < 1e-10
+
+
+def test_cwt_edge_cases(torch_cuda):
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import styx_cwt
+    # odd / non-power-of-two record, zero record, 2-D batch, order below the 0.75 floor
+    for n in (1001, 300, 257):
+        x = synth(n)
+        _, _, cr = orc.cwt_complex_any_scale_pow2(3, x, FS)
+        _, _, c = styx_cwt.cwt_complex_any_scale_pow2(3, x, FS)
+        assert c.shape == cr.shape and rel(c, cr) < TOL64
+    _, _, c = styx_cwt.cwt_complex_any_scale_pow2(3, np.zeros(512), FS)
+    assert not np.any(c)
+    xb = np.stack([synth(2048, chan=i) for i in range(5)])
+    _, _, cb = styx_cwt.cwt_complex_any_scale_pow2(3, xb, FS)
+    for i in (0, 4):
+        assert rel(cb[i], orc.cwt_complex_any_scale_pow2(3, xb[i], FS)[2]) < TOL64
+    fr, _, cr = orc.cwt_complex_any_scale_pow2(0.5, xb[0], FS)
+    f, _, c = styx_cwt.cwt_complex_any_scale_pow2(0.5, xb[0], FS)
+    assert np.array_equal(f, fr) and rel(c, cr) < TOL64
+
+
+def test_cwt_properties_large(torch_cuda):
+    """Size-independent properties at a size the verbatim reference cannot hold (4 x 2^20, 48 bands)."""
+    torch = torch_cuda
+    from quantum_inferno_b200 import cwt_entropy
+    n, C = 1 << 20, 4
+    x = torch.from_numpy(np.stack([synth(n, chan=c) for c in range(C)])).cuda()
+    r = cwt_entropy.cwt_power_entropy(3, x, FS, dtype="float32")
+    assert tuple(r.power.shape) == (C, 48, n)
+    # band sums == sums of the plane; pdf sums to one; entropy bounded by log2(D)
+    assert torch.allclose(r.power.double().sum(-1), r.band_power, rtol=1e-6)
+    pdf_sum = (r.power.double() / r.total_power[:, None, None]).sum((1, 2))
+    assert torch.allclose(pdf_sum, torch.ones_like(pdf_sum), atol=1e-9)
+    ent = r.entropy_bits()
+    assert bool(((ent > 0) & (ent < np.log2(48 * n))).all())
+    # info plane == -log2(P/S + eps) recomputed with torch in fp64
+    ref_info = -torch.log2(r.power[1].double() / r.total_power[1] + np.finfo(np.float64).eps)
+    assert float((r.info[1].double() - ref_info).abs().max()) < 1e-4
+    # linearity: cwt(a*x0 + b*x1) power equals |a*c0 + b*c1|^2 -> check through two independent spectrum paths
+    r_tab = cwt_entropy.cwt_power_entropy(3, x[:1], FS, dtype="float32", spectrum="table", band_slice=(40, 48))
+    assert l2(r_tab.power[0].double().cpu().numpy(), r.power[0, 40:48].double().cpu().numpy()) < TOL32_L2
+    # band sharding: two half tables + summed totals reproduce the unsharded normalisation
+    tot = torch.zeros(1, dtype=torch.float64, device="cuda")
+    parts = []
+    for sl in ((0, 24), (24, 48)):
+        part = cwt_entropy.cwt_power_entropy(3, x[:1], FS, dtype="float32", band_slice=sl, want_info=False)
+        tot += part.total_power
+        parts.append(part)
+    assert abs(float(tot[0]) - float(r.total_power[0])) / float(r.total_power[0]) < 1e-9
+    # oracle on a slab: first band rows against the CPU restatement of one band
+    from oracle import qi_oracle as orc
+    xf = np.fft.fft(x[0].cpu().numpy(), 2 * n)
+    for b in (0, 20, 47):
+        row = orc.cwt_band(xf, 3, n, r.frequency_hz[b], FS)
+        assert l2(r.power[0, b].double().cpu().numpy(), np.abs(row) ** 2) < TOL32_L2
+
+
+def test_stx_config3_slab(torch_cuda):
+    """config[2] shape (2^18 samples, fp64 and fp32) on 2 channels, checked band-by-band with numpy on the host."""
+    from quantum_inferno_b200 import _plan, styx_stx
+    n = 1 << 18
+    x = np.stack([synth(n, chan=c) for c in range(2)])
+    f, t, c = styx_stx.stx_complex_any_scale_pow2(3, x, FS)
+    assert c.shape == (2, 42, n)
+    _, bands = _plan.stx_bands(3, n, FS)
+    xf = np.fft.fft(x[1])
+    w = 2 * np.pi * np.fft.fftfreq(n)
+    for b in (0, 17, 41):
+        ref = np.fft.ifft(np.roll(xf, -int(bands["shift"][b])) * np.exp(-0.5 * bands["sigma"][b] ** 2 * w ** 2))
+        assert rel(c[1, b], ref) < TOL64
+    f, t, p32 = styx_stx.stx_complex_any_scale_pow2(3, x, FS, dtype="float32", outputs="power")
+    assert l2(p32[1, 17], np.abs(c[1, 17]) ** 2) < TOL32_L2
+
+
+def test_stft_config2_slab(torch_cuda):
+    """config[1] shape: Hann 1024 / 50 % on 2^20-sample records (4 channels), frames checked against numpy."""
+    from quantum_inferno_b200 import _plan, styx_fft
+    n = 1 << 20
+    x = np.stack([synth(n, chan=c) for c in range(4)])
+    f, t, z = styx_fft.stft_complex_pow2(x, FS, 1024, alpha=1.0)
+    assert z.shape == (4, 513, 2049)
+    win = _plan.periodic_window("tukey", 1.0, 1024)
+    xe = np.pad(x[3], (512, 512))
+    for fr in (0, 1, 1000, 2048):
+        seg = xe[fr * 512: fr * 512 + 1024]
+        ref = np.fft.rfft((seg - seg.mean()) * win) / win.sum()
+        assert rel(z[3, :, fr], ref) < 1e-12
+    f, t, z32 = styx_fft.stft_complex_pow2(x, FS, 1024, alpha=1.0, dtype="float32")
+    assert l2(np.abs(z32[3]) ** 2, np.abs(z[3]) ** 2) < TOL32_L2
+
+
+def test_fft_roundtrip_large(torch_cuda):
+    """Three-pass FFT sizes: forward+inverse identity and Parseval at 2^22 (fp32) / 2^21 (fp64)."""
+    torch = torch_cuda
+    from quantum_inferno_b200 import _lib, _runtime
+    rt = _runtime.get_runtime()
+    for dt, cdt, code, log2n, tol in ((torch.float32, torch.complex64, 0, 22, 2e-6), (torch.float64, torch.complex128, 1, 21, 1e-13)):
+        g = torch.Generator(device="cuda").manual_seed(5)
+        x = torch.randn(2, 1 << log2n, 2, device="cuda", dtype=dt, generator=g)
+        xc = torch.view_as_complex(x).contiguous()
+        spec = torch.empty_like(xc)
+        _lib.check(rt.lib, rt.lib.qi_fft_c2c(xc.data_ptr(), spec.data_ptr(), 2, log2n, 0, code, rt.stream()), "fft")
+        ref = torch.fft.fft(xc[0])
+        idx = torch.arange(1 << log2n, device="cuda")
+        rev = torch.zeros_like(idx)
+        for i in range(log2n):
+            rev |= ((idx >> i) & 1) << (log2n - 1 - i)
+        assert float((spec[0] - ref[rev]).abs().max() / ref.abs().max()) < tol * 10
+        back = torch.empty_like(xc)
+        _lib.check(rt.lib, rt.lib.qi_fft_c2c(spec.data_ptr(), back.data_ptr(), 2, log2n, 1, code, rt.stream()), "ifft")
+        assert float((back - xc).abs().max() / xc.abs().max()) < tol * 10

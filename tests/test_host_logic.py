@@ -1,0 +1,140 @@
+"""CPU tests of the host side: band tables (bit-exact vs reference-generated vectors), integer index logic,
+windows, frame bookkeeping, the C-ABI surface, and the no-fallback rule."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from quantum_inferno_b200 import _lib, _plan, _runtime, scales_dyadic as sc
+from quantum_inferno_b200.utilities import calculations, matrix, rescaling
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_band_tables_bit_exact(golden):
+    g = golden("scales")
+    for i, (fs, logn, order, nb) in enumerate(g["cases"]):
+        f = sc.log_frequency_hz_from_fft_points(fs, 2 ** int(logn), order)
+        assert len(f) == int(nb) and np.array_equal(f, g[f"f_{i}"]), (fs, logn, order)
+    # the reference's own (commented-out) known-answer test, quantum_inferno/tests/test_scales_dyadic.py:8-21
+    f = sc.log_frequency_hz_from_fft_points(100.0, 8192, scale_order=6.0, scale_ref_hz=1.0, scale_base=sc.Slice.G3)
+    assert f[0] == 0.1778279410038923 and f[-1] == 39.810717055349706 and len(f) == 48
+
+
+def test_g2_band_tables_bit_exact(golden):
+    g = golden("scales")
+    for i, (order, base, ref, lo, hi, fs) in enumerate(g["bcases"]):
+        r = sc.band_frequency_low_high(order, base, ref, lo, hi, fs)
+        for j, key in ((2, "band"), (4, "calg"), (5, "cgeo"), (6, "start"), (7, "end")):
+            assert np.array_equal(r[j], g[f"b{i}_{key}"]), (i, key)
+
+
+def test_survey_band_counts():
+    # B at fs = 800 Hz
+    for order, logn, nb in [(3, 16, 36), (3, 18, 42), (3, 20, 48), (3, 24, 60), (6, 22, 102), (6, 18, 78),
+                            (12, 28, 263), (12, 18, 143)]:
+        assert len(sc.log_frequency_hz_from_fft_points(800.0, 2 ** logn, order)) == nb
+
+
+def test_scale_helpers():
+    assert sc.cycles_from_order(3) == 0.75 * np.pi * 3
+    assert sc.scale_order_check(-6.0) == 6.0 and sc.scale_order_check(0.1, show_warning=False) == 0.75
+    assert sc.order_from_cycles(0.5) == sc.scale_order_check(1.0 / sc.M_OVER_N, show_warning=False)
+    s, w = sc.scale_from_frequency_hz(3, np.array([10.0, 100.0]), 800.0)
+    assert np.array_equal(w, 2.0 * np.pi * np.array([10.0, 100.0]) / 800.0)
+    assert np.array_equal(s, sc.cycles_from_order(3) / w)
+    assert sc.get_epsilon() == np.finfo(np.float64).eps and sc.Slice.G3 == 10.0 ** 0.3
+
+
+@pytest.mark.parametrize("n", [8, 64, 256, 1000, 4096])
+def test_nearest_fft_bin_matches_argmin(n):
+    rng = np.random.default_rng(n)
+    d = 1 / 800.0
+    ff = np.fft.fftfreq(n, d)
+    probes = list(rng.uniform(-500, 500, 200)) + list(ff[:8]) + list((ff[:-1] + ff[1:])[:40] / 2) + [400.0, -400.0, 1e6, 0.0]
+    for f in probes:
+        assert _plan.nearest_fft_bin(f, n, d) == int(np.abs(ff - f).argmin()), (n, f)
+
+
+def test_stx_shift_indices_match_oracle():
+    from oracle import qi_oracle as orc
+    for order, n in [(3, 2048), (6, 1024), (12, 4096), (1, 256)]:
+        f, bands = _plan.stx_bands(order, n, 800.0)
+        assert np.array_equal(bands["shift"], orc.stx_shift_indices(order, n, 800.0))
+
+
+def test_windows_and_frames(golden):
+    from oracle import qi_oracle as orc
+    for kind, par, n in [("tukey", 0.25, 256), ("tukey", 1.0, 1024), ("tukey", 0.0, 64), ("tukey", 0.5, 200),
+                         ("gaussian", 128, 512)]:
+        assert np.array_equal(_plan.periodic_window(kind, par, n), orc.window_periodic(kind, par, n))
+    g = golden("stft")
+    nfr, padl, ext = _plan.stft_frames(8192, 1024, 512)
+    assert (nfr, padl) == (17, 512) and np.allclose(_plan.stft_time_axis(ext, 1024, 512, 800.0), g["hann_t"])
+    nfr, padl, ext = _plan.stft_frames(4096, 200, 150)
+    assert nfr == g["odd_z"].shape[-1]
+    # configs[1]: 64 x 2^20, 1024/512 -> 2049 frames x 513 bins
+    assert _plan.stft_frames(2 ** 20, 1024, 512)[0] == 2049
+    with pytest.raises(ValueError):
+        _plan.stft_frames(100, 16, 16)
+
+
+def test_gabor_band_plan():
+    f = sc.log_frequency_hz_from_fft_points(800.0, 2 ** 16, 3)
+    bands, scale, omega, amp = _plan.gabor_bands(3, 2 ** 16, f, 800.0, "norm", "float64")
+    assert len(bands) == 36 and bands.dtype.itemsize == 40
+    assert np.array_equal(bands["omega"], 2.0 * np.pi * f / 800.0)
+    assert int((bands["analytic"] == 0).sum()) == 4               # lowest ~1.2*N bands are truncated atoms
+    assert np.all(np.diff(bands["analytic"]) >= 0)
+    a_norm, a_spect = _plan.wavelet_amplitude(scale)
+    assert np.array_equal(amp, a_norm)
+    assert np.array_equal(_plan.gabor_bands(3, 2 ** 16, f, 800.0, "spect")[3], a_spect)
+    assert np.all(_plan.gabor_bands(3, 2 ** 16, f, 800.0, "unit")[3] == 1.0)
+    assert np.array_equal(_plan.gabor_bands(3, 2 ** 16, f, 800.0, "anything")[3], a_norm)   # silent 'norm' fallback
+
+
+def test_utilities():
+    assert rescaling.is_power_of_two(1024) and not rescaling.is_power_of_two(1000) and not rescaling.is_power_of_two(0)
+    assert rescaling.to_log2_with_epsilon(1.0) == np.log2(1.0 + np.finfo(np.float64).eps)
+    assert calculations.get_num_points(800.0, 0.47, "ceil", "log2") == 9
+    assert calculations.round_value(2.5) == 2 and calculations.round_value(5.0, "ceil_power_of_two") == 8
+    with pytest.raises(ValueError):
+        calculations.round_value(1.0, "nope")
+    a = np.arange(6.0).reshape(2, 3)
+    assert np.array_equal(matrix.d0tile_x_d0d1(np.array([2.0, 3.0]), a), a * np.array([[2.0], [3.0]]))
+    assert np.array_equal(matrix.d1tile_x_d0d1(np.array([1.0, 2.0, 3.0]), a), a * np.array([1.0, 2.0, 3.0]))
+    with pytest.raises(TypeError):
+        matrix.d0tile_x_d0d1(np.array([1.0, 2.0, 3.0]), a)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The CUDA library loads without a GPU and exports exactly what include/qi_b200.h declares."""
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("libqi_b200.so not built (run __graft_entry__.build())")
+    hdr = open(os.path.join(ROOT, "include", "qi_b200.h")).read()
+    declared = set(re.findall(r"\b(qi_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.bind(ctypes.CDLL(_lib.LIB_PATH))
+    assert lib.qi_abi_version() == _lib.QI_ABI_VERSION
+    assert lib.qi_error_string(-2) == b"workspace too small"
+    # struct mirrors
+    assert _lib.ATOM_BAND.itemsize == 40 and _lib.STX_BAND.itemsize == 16
+    # argument validation happens before any CUDA call
+    assert lib.qi_fft_c2c(None, None, 1, 4, 0, 0, None) == -1
+    assert lib.qi_cwt_workspace_bytes(1, 4096, 27, 4, 1, 0, 1) > 4096 * 2 * 16 * 2
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path raises; it never routes through the oracle or numpy."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from quantum_inferno_b200 import styx_cwt
+    _runtime._runtime = None
+    with pytest.raises(RuntimeError):
+        styx_cwt.cwt_complex_any_scale_pow2(3, np.zeros(256), 800.0)
+    pkg = os.path.join(ROOT, "quantum_inferno_b200")
+    src = "".join(open(os.path.join(pkg, fn)).read() for fn in os.listdir(pkg) if fn.endswith(".py"))
+    assert "qi_oracle" not in src and "libqi_emul" not in src and "import oracle" not in src
