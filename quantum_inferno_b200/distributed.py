@@ -1,0 +1,68 @@
+"""
+Multi-GPU partitioning of the hot path: one process per GPU, ``torch.distributed`` (NCCL over NVLink) for the
+plumbing.
+
+* Records (channels) are independent in every transform and every ``tfr_info`` reduction is per record
+  (reference tfr_info.py:236,247,259), so a batch shards by channel with NO data-path collective.
+* One long record can instead be sharded by band (bands never interact: styx_cwt.py:195 is row-wise,
+  styx_stx.py:231-234 loops bands).  The only exchange is then ONE all-reduce (sum, fp64, one scalar per
+  record) of the total power S that normalises the global pdf of ``shannon_stft_from_tfr_power``.
+"""
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def channel_shard(n_channels: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block [c0, c1) of records for this rank (sizes differ by at most one)."""
+    base, extra = divmod(int(n_channels), int(world))
+    c0 = rank * base + min(rank, extra)
+    return c0, c0 + base + (1 if rank < extra else 0)
+
+
+def band_shard(n_bands: int, rank: int, world: int, cost: Optional[Sequence[float]] = None) -> Tuple[int, int]:
+    """Contiguous band range [b0, b1) for this rank, balanced on ``cost`` (default: equal cost per band, which is
+    what the full-length inverse FFT per band costs).  Every rank gets at least one band when n_bands >= world."""
+    n_bands, world = int(n_bands), int(world)
+    if n_bands < world:
+        raise ValueError(f"cannot shard {n_bands} bands over {world} ranks")
+    w = np.ones(n_bands) if cost is None else np.asarray(cost, dtype=np.float64)
+    cum = np.concatenate(([0.0], np.cumsum(w)))
+    edges = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        e = int(np.searchsorted(cum, target, side="left"))
+        e = max(e, edges[-1] + 1)                       # at least one band per rank
+        e = min(e, n_bands - (world - r))               # leave one for every later rank
+        edges.append(e)
+    edges.append(n_bands)
+    return edges[rank], edges[rank + 1]
+
+
+def sum_allreduce(group=None):
+    """Returns the callable ``cwt_entropy.cwt_power_entropy(allreduce=...)`` expects: an in-place SUM all-reduce
+    of the fp64 per-record total power over ``group`` (NCCL for CUDA tensors, gloo for host buffers)."""
+    import torch
+    import torch.distributed as dist
+
+    def _reduce(total):
+        t = total if isinstance(total, torch.Tensor) else torch.from_numpy(total)    # shares memory with numpy
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return total
+
+    return _reduce
+
+
+def cwt_power_entropy_band_sharded(band_order_nth, sig_wf, frequency_sample_rate_hz, rank=None, world=None,
+                                   group=None, **kwargs):
+    """Band-sharded ``cwt_entropy.cwt_power_entropy``: every rank holds the whole record(s), computes its own band
+    range and joins the single total-power all-reduce.  Returns this rank's ``CwtEntropy`` (its bands only)."""
+    import torch.distributed as dist
+    from . import cwt_entropy, scales_dyadic as scales
+    rank = dist.get_rank(group) if rank is None else rank
+    world = dist.get_world_size(group) if world is None else world
+    n_points = int(sig_wf.shape[-1])
+    n_bands = len(scales.log_frequency_hz_from_fft_points(frequency_sample_rate_hz, n_points, band_order_nth))
+    return cwt_entropy.cwt_power_entropy(band_order_nth, sig_wf, frequency_sample_rate_hz,
+                                         band_slice=band_shard(n_bands, rank, world),
+                                         allreduce=sum_allreduce(group), **kwargs)
