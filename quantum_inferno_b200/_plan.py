@@ -10,6 +10,7 @@ from ._lib import ATOM_BAND
 # N/s below which the Gaussian has NOT decayed at the record edge and the truncated atom's exact
 # spectrum is used instead of the closed form.  erfc(x/sqrt(2)) at x = N/(2s).
 ANALYTIC_MIN_POINTS_PER_SCALE = {"float64": 15.0, "float32": 10.0}
+ANALYTIC_MIN_SCALE = 1.0
 
 
 def wavelet_amplitude(scale_atom):
@@ -48,7 +49,10 @@ def gabor_bands(band_order_nth, n_points, frequency_hz, frequency_sample_rate_hz
     elif spectrum == "analytic":
         bands["analytic"] = 1
     else:
-        bands["analytic"] = (n_points / scale >= ANALYTIC_MIN_POINTS_PER_SCALE[dtype_name]).astype(np.int32)
+        # closed form = Gaussian + 5 Poisson alias terms: exact only if the atom has decayed at the record edge
+        # and is at least one sample wide (narrower atoms -- orders <= 1 near Nyquist -- need more alias terms)
+        ok = (n_points / scale >= ANALYTIC_MIN_POINTS_PER_SCALE[dtype_name]) & (scale >= ANALYTIC_MIN_SCALE)
+        bands["analytic"] = ok.astype(np.int32)
     return bands, scale, omega, amp
 
 

@@ -146,7 +146,8 @@ static CwtLayout cwt_layout(i64 C, i64 N, int B, int n_tab, int group, int conv_
     return lo;
 }
 
-static void fill_dev_bands(const QiAtomBand* hb, int B, int logL, std::vector<DevBand>& db, std::vector<int>& tab) {
+static void fill_dev_bands(const QiAtomBand* hb, int B, int logL, int half_shift, std::vector<DevBand>& db,
+                           std::vector<int>& tab) {
     const double L = (double)(1ll << logL);
     db.resize(B);
     tab.clear();
@@ -154,9 +155,15 @@ static void fill_dev_bands(const QiAtomBand* hb, int B, int logL, std::vector<De
         DevBand d;
         d.omega = hb[b].omega; d.p_re = hb[b].p_re; d.p_im = hb[b].p_im; d.amp = hb[b].amp;
         if (hb[b].analytic) {
-            d.gain = hb[b].amp * sqrt(M_PI / hb[b].p_re) / L;
+            // centre frequency folded into [0, 2*pi): a centre beyond the sampling rate (orders below the 0.75
+            // floor produce such bands upstream) aliases onto omega - 2*pi*m, with a sign (-1)^m from the
+            // half-sample offset of the 'same' slice
+            const double wraps = floor(hb[b].omega / (2.0 * M_PI));
+            const double omega_r = hb[b].omega - 2.0 * M_PI * wraps;
+            const double sign = (half_shift && (((long long)wraps) & 1)) ? -1.0 : 1.0;
+            d.gain = sign * hb[b].amp * sqrt(M_PI / hb[b].p_re) / L;
             d.g = (2.0 * M_PI / L) / sqrt(2.0 * hb[b].p_re);
-            const double kappa = hb[b].omega * L / (2.0 * M_PI);
+            const double kappa = omega_r * L / (2.0 * M_PI);
             const double ki = floor(kappa);
             d.kappa_int = (long long)ki;
             d.kappa_frac = kappa - ki;
@@ -191,7 +198,7 @@ static int cwt_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiAtomB
     cplx<T>* work = reinterpret_cast<cplx<T>*>(base + lo.off_work);
 
     std::vector<DevBand> db; std::vector<int> tab;
-    fill_dev_bands(hb, B, lo.logL, db, tab);
+    fill_dev_bands(hb, B, lo.logL, (conv_mode == QI_CONV_LINEAR_SAME && (N % 2 == 0)) ? 1 : 0, db, tab);
     cudaMemcpyAsync(d_bands, db.data(), sizeof(DevBand) * (size_t)B, cudaMemcpyHostToDevice, st);
     if (n_tab) cudaMemcpyAsync(d_tab, tab.data(), sizeof(int) * (size_t)n_tab, cudaMemcpyHostToDevice, st);
 #ifndef QI_EMUL
@@ -264,7 +271,7 @@ static int atoms_time_impl(const QiAtomBand* hb, int B, i64 N, double fs, const 
     std::vector<DevBand> db; std::vector<int> tab;
     std::vector<QiAtomBand> tmp(hb, hb + B);
     for (auto& t : tmp) t.analytic = 0;
-    fill_dev_bands(tmp.data(), B, 0, db, tab);
+    fill_dev_bands(tmp.data(), B, 0, 0, db, tab);
     DevBand* d_bands = static_cast<DevBand*>(ws);
     cudaMemcpyAsync(d_bands, db.data(), sizeof(DevBand) * (size_t)B, cudaMemcpyHostToDevice, st);
 #ifndef QI_EMUL
