@@ -33,6 +33,17 @@ ORDER = 3
 LOG2_N = int(os.environ.get("QI_BENCH_LOG2N", "24"))
 CH_PER_GPU = int(os.environ.get("QI_BENCH_CHANNELS", "8"))
 ALG_BYTES_PER_CELL_F32 = 2 * 4 + 4.0 / 60.0       # power + info planes + input share
+METHOD = os.environ.get("QI_BENCH_METHOD", "multirate")     # 'multirate' (default fast path) or 'exact'
+ALGORITHMS = {
+    "multirate": "multirate fp32 path: half-band pyramid, per-level overlap-save FFT in shared memory, half-band "
+                 "interpolation fused with |.|^2 and band sums, then one streaming information pass",
+    "exact": "exact path: record FFT + per-band 3-pass inverse FFT through HBM"}
+KERNEL_OF = {
+    "multirate": {"fft_fwd": "mr_table_kernel+mr_decimate_kernel", "inv_first": "mr_level_kernel[level>=1]",
+                  "inv_mid": "mr_level_kernel[level 0]", "inv_last": "mr_expand_kernel", "info": "shannon_kernel"},
+    "exact": {"fft_fwd": "fft_pass_kernel[forward]", "inv_first": "fft_pass_kernel[spectrum x response]",
+              "inv_mid": "fft_pass_kernel[middle]", "inv_last": "fft_pass_kernel[slice + power]",
+              "info": "shannon_kernel"}}
 METRIC = "tfr_cells_per_s"
 UNIT = "cells/s"
 
@@ -196,7 +207,8 @@ def run_gpu_arm(args):
     info = torch.empty_like(power)
 
     def step(src):
-        return cwt_entropy.cwt_power_entropy(ORDER, src, FS, dtype="float32", out_power=power, out_info=info)
+        return cwt_entropy.cwt_power_entropy(ORDER, src, FS, dtype="float32", out_power=power, out_info=info,
+                                             method=METHOD)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -281,9 +293,9 @@ def run_gpu_arm(args):
             "config": {"workload": workload_name(), "channels_total": world * CH_PER_GPU, "bands": n_bands,
                        "parallelism": f"channel-sharded x{world}, no data-path collective",
                        "l2": "inputs (0.5 GB) and planes (64 GB) per step are far larger than L2; no flush needed",
-                       "algorithm": "exact path: record FFT + per-band 3-pass inverse FFT through HBM"},
+                       "algorithm": ALGORITHMS[METHOD]},
             "samples_per_s": world * CH_PER_GPU * n / (ms_per_step * 1e-3),
-            "roofline": {"bound": "hbm", "kernel": "fft_pass_kernel[" + _lib.CATEGORY_NAMES[dom] + "]",
+            "roofline": {"bound": "hbm", "kernel": KERNEL_OF[METHOD].get(_lib.CATEGORY_NAMES[dom], _lib.CATEGORY_NAMES[dom]),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "avg_launch_ms": dom_avg_ms, "launches": dom_launches,

@@ -105,6 +105,29 @@ int qi_cwt_fft(const void* sig, int64_t n_channels, int64_t n_points, int64_t si
 int qi_atoms_time(const QiAtomBand* bands, int n_bands, int64_t n_points, double fs, int dtype,
                   const double* xtime, void* out_atoms, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- multirate fp32 Gabor CWT (fast path) ------------------------------------------------------
+ * Same quantity as qi_cwt_fft(QI_CONV_LINEAR_SAME) for Gaussian (p_im = 0) atoms, float32 only, to the
+ * north-star fp32 tolerance (power relative L2 <= 1e-4): half-band decimation pyramid of the record, each band
+ * convolved (overlap-save FFT in shared memory) at the deepest level whose alias-free band holds its response,
+ * then half-band interpolation back to the full rate fused with |.|^2 and the fp64 band sums.
+ * Replaces quantum_inferno/styx_cwt.py:147-198 followed by np.abs(cwt)**2.
+ * bands: HOST array sorted by ascending centre frequency; level = log2 of the decimation the host planner chose
+ * (non-increasing along the array, 0 <= level <= log2(n_points) - 10).  n_points = 2^m, m >= 11. */
+typedef struct {
+    double omega;    /* centre, rad/sample at the full rate */
+    double scale;    /* atom scale s in samples             */
+    double amp;
+    int32_t level;
+    int32_t reserved;
+} QiMrBand;
+
+size_t qi_cwt_multirate_workspace_bytes(int64_t n_channels, int64_t n_points, const QiMrBand* bands, int n_bands);
+
+/* out_power float [C,B,N] or NULL; out_cwt complex64 [C,B,N] or NULL; band_sum double [C,B] or NULL */
+int qi_cwt_multirate(const void* sig, int64_t n_channels, int64_t n_points, int64_t sig_stride,
+                     const QiMrBand* bands, int n_bands, void* out_power, void* out_cwt, double* band_sum,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Stockwell transform ----------------------------------------------------------------------
  * Replaces quantum_inferno/styx_stx.py:195-236 (stx_complex_any_scale_pow2) and the band loop of
  * :52-192 (tfr_stx_fft :166-190):  tfr[b,:] = ifft( X[(k + shift_b) mod n] * exp(-0.5*sigma_b^2*w_k^2) ),

@@ -211,3 +211,24 @@ def abs_log2(buf, dt, is_complex, eps=EPS64, square=False, rt=None, signed=False
                          rt.ptr(out), rt.stream())
     _lib.check(lib, rc, "qi_abs_log2")
     return out
+
+
+def cwt_multirate(sig, bands, want_power=True, want_complex=False, want_band_sum=False, rt=None, out_power=None):
+    """Run qi_cwt_multirate (float32).  sig: device float32 [C, N]; bands: numpy MR_BAND table."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    C, N = int(sig.shape[0]), int(sig.shape[1])
+    bands = np.ascontiguousarray(bands, dtype=_lib.MR_BAND)
+    B = len(bands)
+    nbytes = lib.qi_cwt_multirate_workspace_bytes(C, N, bands.ctypes.data, B)
+    if nbytes == 0:
+        raise ValueError("qi_cwt_multirate: unsupported size or band table")
+    ws = rt.workspace(nbytes)
+    if want_power and out_power is None:
+        out_power = rt.empty((C, B, N), "float32")
+    out_c = rt.empty((C, B, N), "complex64") if want_complex else None
+    bsum = rt.empty((C, B), "float64") if want_band_sum else None
+    rc = lib.qi_cwt_multirate(rt.ptr(sig), C, N, N, bands.ctypes.data, B, rt.ptr(out_power), rt.ptr(out_c),
+                              rt.ptr(bsum), rt.ptr(ws), nbytes, rt.stream())
+    _lib.check(lib, rc, "qi_cwt_multirate")
+    return {"complex": out_c, "power": out_power, "band_sum": bsum}

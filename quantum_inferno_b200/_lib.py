@@ -24,6 +24,8 @@ ATOM_BAND = np.dtype([("omega", "<f8"), ("p_re", "<f8"), ("p_im", "<f8"), ("amp"
                       ("analytic", "<i4"), ("reserved", "<i4")], align=True)
 
 STX_BAND = np.dtype([("sigma", "<f8"), ("shift", "<i8")], align=True)
+MR_BAND = np.dtype([("omega", "<f8"), ("scale", "<f8"), ("amp", "<f8"), ("level", "<i4"), ("reserved", "<i4")],
+                   align=True)
 
 _c_vp, _c_i64, _c_int, _c_sz, _c_dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t, ctypes.c_double
 
@@ -41,6 +43,9 @@ SIGNATURES = {
                             _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_vp]),
     "qi_atoms_time": (_c_int, [_c_vp, _c_int, _c_i64, _c_dbl, _c_int, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),
     "qi_abs_log2": (_c_int, [_c_vp, _c_i64, _c_int, _c_int, _c_int, _c_dbl, _c_vp, _c_vp]),
+    "qi_cwt_multirate_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_vp, _c_int]),
+    "qi_cwt_multirate": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz,
+                                  _c_vp]),
     "qi_stx_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int, _c_int, _c_int]),
     "qi_stx_fft": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int,
                             _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_vp]),

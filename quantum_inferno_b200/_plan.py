@@ -137,3 +137,32 @@ def stft_time_axis(ext_length, nperseg, noverlap, fs, boundary_zeros=True):
     if boundary_zeros:
         t -= (nperseg / 2) / fs
     return t
+
+
+# ----------------------------------------------------------------------------- multirate fp32 CWT
+MR_KAPPA = 4.8           # half-width (in 1/s) of the band response that must sit inside a level's alias-free band
+MR_PASS = np.pi / 2      # alias-free band of every pyramid level, in radians at that level's rate
+MR_MIN_LOG2_POINTS = 11
+
+
+def multirate_supported(n_points, scale):
+    """The multirate path needs a 2^m record (m >= 11) and atoms at least one sample wide."""
+    n = int(n_points)
+    return n >= (1 << MR_MIN_LOG2_POINTS) and (n & (n - 1)) == 0 and bool(np.all(np.asarray(scale) >= ANALYTIC_MIN_SCALE))
+
+
+def multirate_bands(band_order_nth, n_points, frequency_hz, frequency_sample_rate_hz, dictionary_type="norm"):
+    """Level assignment of the multirate CWT: band b runs at level l_b = the largest l with
+    (omega_b + kappa/s_b) * 2^l <= pi/2, capped so the deepest level still has 1024 samples.
+    Returns (bands[MR_BAND] ascending in frequency, scale, omega, amp)."""
+    from ._lib import MR_BAND
+    f = np.atleast_1d(np.asarray(frequency_hz, dtype=np.float64))
+    scale, omega = scales.scale_from_frequency_hz(band_order_nth, f, frequency_sample_rate_hz)
+    amp = np.broadcast_to(np.asarray(dictionary_amplitude(scale, dictionary_type), dtype=np.float64), f.shape)
+    cap = int(np.log2(n_points)) - 10
+    upper_edge = omega * (1.0 + MR_KAPPA / (omega * scale))
+    level = np.floor(np.log2(MR_PASS / upper_edge)).astype(np.int64)
+    bands = np.zeros(len(f), dtype=MR_BAND)
+    bands["omega"], bands["scale"], bands["amp"] = omega, scale, amp
+    bands["level"] = np.clip(level, 0, cap)
+    return bands, scale, omega, amp

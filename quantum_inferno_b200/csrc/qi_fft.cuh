@@ -91,10 +91,11 @@ QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int
     const int logH = logB - STEP;
     const int h = 1 << logH;
     const int ntask = (1 << (logR - STEP)) * TC;
+    const int logTC = 31 - __clz(TC);
     const int twshift = logR - logB;
     for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
-        const int c = task % TC;
-        const int u = task / TC;
+        const int c = task & (TC - 1);              // TC is a power of two
+        const int u = task >> logTC;
         const int j = u & (h - 1);
         const int g = u >> logH;
         cplx<T>* p = tile + (size_t)(((g << logB) + j) * TP + c);
@@ -188,6 +189,7 @@ fft_pass_kernel(PassGeom g, Src src, Dst dst) {
     const i64 batch = blockIdx.y;
     const i64 col0 = (i64)blockIdx.x * TC;
     const int nelem = R * TC;
+    const int logTC = 31 - __clz(TC);
     const int twlog = g.logR + g.logS;           // modulus of the inter-pass twiddle
 
     fill_twiddles<T>(tw, g.logR);
@@ -196,7 +198,7 @@ fft_pass_kernel(PassGeom g, Src src, Dst dst) {
     for (int idx = threadIdx.x; idx < nelem; idx += blockDim.x) {
         int r, c;
         if (row_major) { r = idx & (R - 1); c = idx >> g.logR; }
-        else { c = idx % TC; r = idx / TC; }
+        else { c = idx & (TC - 1); r = idx >> logTC; }
         const i64 col = col0 + c;
         const i64 e = pass_elem(g, r, col);
         cplx<T> v = src.load(batch, e);
@@ -212,7 +214,7 @@ fft_pass_kernel(PassGeom g, Src src, Dst dst) {
     for (int idx = threadIdx.x; idx < nelem; idx += blockDim.x) {
         int r, c;
         if (row_major) { r = idx & (R - 1); c = idx >> g.logR; }
-        else { c = idx % TC; r = idx / TC; }
+        else { c = idx & (TC - 1); r = idx >> logTC; }
         const i64 col = col0 + c;
         const i64 e = pass_elem(g, r, col);
         cplx<T> v = tile[r * TP + c];

@@ -97,6 +97,41 @@ shannon_kernel(const T* __restrict__ p, const double* __restrict__ norm, Shannon
     }
 }
 
+// Streaming special case of the above for the fused north-star pass: float32 plane, mode 0, only the information
+// plane and the per-band entropy sums.  128-bit loads/stores, MUFU log2, one fp64 add per four cells.
+QI_DEV float fast_log2f(float v) {
+#ifdef QI_EMUL
+    return std::log2(v);
+#else
+    return __log2f(v);
+#endif
+}
+
+__global__ void __launch_bounds__(256)
+info_plane_f32_kernel(const float4* __restrict__ p, const double* __restrict__ norm, i64 F, i64 T4, float eps,
+                      float4* __restrict__ o_info, double* __restrict__ ent_sum) {
+    __shared__ double scratch[32];
+    const i64 m = blockIdx.z, f = blockIdx.y;
+    const i64 row = (m * F + f) * T4;
+    const float inv = (float)(1.0 / norm[m]);
+    const i64 chunk = (T4 + gridDim.x - 1) / gridDim.x;
+    const i64 t0 = (i64)blockIdx.x * chunk;
+    const i64 t1 = t0 + chunk < T4 ? t0 + chunk : T4;
+    double acc = 0.0;
+    for (i64 t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        const float4 v = p[row + t];
+        const float d0 = v.x * inv, d1 = v.y * inv, d2 = v.z * inv, d3 = v.w * inv;
+        const float i0 = -fast_log2f(d0 + eps), i1 = -fast_log2f(d1 + eps);
+        const float i2 = -fast_log2f(d2 + eps), i3 = -fast_log2f(d3 + eps);
+        o_info[row + t] = make_float4(i0, i1, i2, i3);
+        acc += (double)((d0 * i0 + d1 * i1) + (d2 * i2 + d3 * i3));
+    }
+    if (ent_sum) {
+        acc = block_sum(acc, scratch);
+        if (threadIdx.x == 0) atomicAdd(&ent_sum[m * F + f], acc);
+    }
+}
+
 // bits = log2(P + eps) - log2(max[m] + eps)   (tfr_info.py:73-79)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -158,9 +193,9 @@ abs_log2_kernel(const T* __restrict__ in, i64 n, int is_complex, int square, dou
 }
 
 static unsigned splits_for(i64 Tn, i64 rows) {
-    // enough CTAs to fill 148 SMs a few times over, at least 4096 elements per CTA
-    i64 s = (148 * 8 + rows - 1) / rows;
-    const i64 cap = (Tn + 4095) / 4096;
+    // many short CTAs (>= 64 waves over 148 SMs x 8 resident CTAs, >= 32K elements each) so the tail wave is noise
+    i64 s = (148 * 8 * 64 + rows - 1) / rows;
+    const i64 cap = (Tn + 32767) / 32768;
     if (s > cap) s = cap;
     if (s < 1) s = 1;
     return (unsigned)s;
@@ -197,6 +232,12 @@ static int shannon_impl(const void* p, i64 M, i64 F, i64 Tn, int mode, const dou
     a.inv_ref_bits = 1.0 / (log2(deg_free) / deg_free);
     if (ent_sum) cudaMemsetAsync(ent_sum, 0, sizeof(double) * (size_t)M * F, st);
     dim3 grid(splits_for(Tn, M * F), (unsigned)F, (unsigned)M);
+    if (sizeof(T) == 4 && mode == 0 && o_info && !o_pdf && !o_bits && !o_isnr && !o_esnr && (Tn % 4) == 0 &&
+        ((uintptr_t)p % 16) == 0 && ((uintptr_t)o_info % 16) == 0) {
+        QI_LAUNCH(info_plane_f32_kernel, grid, dim3(256), 0, st, static_cast<const float4*>(p), norm, F, Tn / 4,
+                  (float)eps, static_cast<float4*>(o_info), ent_sum);
+        return check_cuda("qi_shannon");
+    }
     QI_LAUNCH((shannon_kernel<T>), grid, dim3(256), 0, st, static_cast<const T*>(p), norm, a, static_cast<T*>(o_pdf), static_cast<T*>(o_info),
               static_cast<T*>(o_bits), static_cast<T*>(o_isnr), static_cast<T*>(o_esnr), ent_sum);
     return check_cuda("qi_shannon");

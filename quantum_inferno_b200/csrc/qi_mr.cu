@@ -1,0 +1,572 @@
+// qi_mr.cu -- multirate fp32 Gabor CWT: the fast path behind cwt_entropy / styx_cwt(dtype=float32, method=multirate).
+//
+// The output plane [bands x N] is compulsory HBM traffic (4 B/cell); everything else is kept far below it:
+//
+//   P  pyramid      x_(l+1)[q] = halfband(x_l)[2q]  (zero-phase minimax half-band FIR, |error| <= 1e-6, exact
+//                   zero extension of the record carried in a 16-sample halo).  Total work ~ N per channel.
+//   T  tables       every band lives at the deepest level l whose alias-free band [0, pi/2] still holds its whole
+//                   Gaussian response (|theta - omega| <= 4.8/s).  Its kernel at that rate,
+//                   2^l * psi(2^l d - 1/2) truncated like the reference's N-sample atom, is sampled in fp64,
+//                   transformed once in shared memory and kept (bit-reversed order, L2 resident) for all channels.
+//   A  level conv   overlap-save convolution of x_l with all bands of level l: one forward FFT of a 2048/4096-point
+//                   block in shared memory, then per band multiply + inverse FFT in shared memory.  Level-0 bands
+//                   go straight to |.|^2 -> power plane (+ fp64 band sums); deeper bands leave their decimated
+//                   complex output w_b (8 B per 2^l cells) in HBM.
+//   E  expand       per (channel, band, 2048-cell tile): the tile's w_b samples are read once, interpolated by 2 l
+//                   times in shared memory with minimax half-band interpolators whose length shrinks as the signal
+//                   gets more oversampled (7,4,3,3,2,2,... taps per side), and the last stage feeds |.|^2, the power
+//                   plane store and the band sums from registers.
+//
+// Replaces (fp32 tolerance of the north star: power rel. L2 <= 1e-4) quantum_inferno/styx_cwt.py:147-198 + np.abs()**2.
+// The numpy model of exactly this algorithm is tools/multirate_prototype.py.
+#include "qi_fft.cuh"
+#include "qi_host.h"
+#include "qi_reduce.cuh"
+#include "qi_tfr.cuh"
+#include "qi_halfband_coeffs.h"
+
+#include <vector>
+#include <math.h>
+
+namespace qi {
+
+constexpr int MR_HALO = 16;        // halo (samples per side) of every stored level array
+constexpr int MR_TILE = 2048;      // full-rate cells per CTA in the expand kernel
+constexpr int MR_MAX_LEVEL = 20;
+
+struct HbTaps {
+    int n[QI_HB_CLASSES];
+    float c[QI_HB_CLASSES][QI_HB_MAX_TAPS];
+};
+
+struct MrDevBand {
+    double omega, scale, amp;
+    int level;
+    int logF;            // FFT length of this band's level
+    long long table_off; // offset (complex elements) of its kernel table
+    long long w_off;     // offset (complex elements) of its decimated output, per channel stride w_stride
+    long long w_stride;
+    long long mid_off;   // level-MR_LMID copy (bands deeper than MR_LMID only), per channel stride mid_stride
+    long long mid_stride;
+};
+
+QI_DEV int hb_class(int j) { return j < 1 ? 0 : (j > QI_HB_CLASSES ? QI_HB_CLASSES - 1 : j - 1); }
+
+// ---------------------------------------------------------------- P: half-band decimation by 2
+// src: level l (with halo `src_halo`, length src_len incl. halo; level 0: halo 0), dst: level l+1 with MR_HALO.
+__global__ void __launch_bounds__(256)
+mr_decimate_kernel(const float* __restrict__ src, i64 src_stride, i64 src_len, int src_halo,
+                   float* __restrict__ dst, i64 dst_stride, i64 dst_len, HbTaps taps) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;      // dst index, q = i - MR_HALO
+    if (i >= dst_len) return;
+    const i64 c = blockIdx.y;
+    const float* s = src + c * src_stride;
+    const i64 centre = 2 * (i - MR_HALO) + src_halo;               // src index of sample 2q
+    auto at = [&](i64 k) -> float { return (k >= 0 && k < src_len) ? s[k] : 0.0f; };
+    float acc = 0.5f * at(centre);
+    const int nt = taps.n[0];
+#pragma unroll
+    for (int t = 0; t < QI_HB_MAX_TAPS; ++t) {
+        if (t < nt) acc += taps.c[0][t] * (at(centre + 2 * t + 1) + at(centre - 2 * t - 1));
+    }
+    dst[c * dst_stride + i] = acc;
+}
+
+// ---------------------------------------------------------------- T: kernel tables
+// One CTA per band: sample kappa[d] = 2^l * amp * exp(-t^2/2s^2) * exp(i*omega*t), t = 2^l d - 1/2, on the circular
+// lag grid of F points, keep |d| <= half_w and |t| <= (N-1)/2, forward FFT in shared memory, store * 1/F.
+__global__ void __launch_bounds__(256)
+mr_table_kernel(const MrDevBand* __restrict__ bands, i64 n_points, int half_w_cap, cplx<float>* __restrict__ tables) {
+    QI_DYN_SMEM(smem_raw);
+    const MrDevBand b = bands[blockIdx.x];
+    const int F = 1 << b.logF;
+    cplx<float>* tile = reinterpret_cast<cplx<float>*>(smem_raw);       // [F][2]
+    cplx<float>* tw = tile + (size_t)F * 2;
+    fill_twiddles<float>(tw, b.logF);
+    const double step = (double)(1ll << b.level);
+    const double tmax = 0.5 * (double)(n_points - 1);
+    // time support kept: 5.2 sigma (3e-6 of the peak) or the whole block half for record-long atoms
+    int half_w = (int)ceil(5.2 * b.scale / step) + 1;
+    if (half_w > half_w_cap) half_w = half_w_cap;
+    for (int p = threadIdx.x; p < F; p += blockDim.x) {
+        const int d = p < F / 2 ? p : p - F;
+        double re = 0.0, im = 0.0;
+        const double t = step * (double)d - 0.5;
+        if (d >= -half_w && d <= half_w && fabs(t) <= tmax) {
+            const double u = t / b.scale;
+            const double env = step * b.amp * exp(-0.5 * u * u);
+            double s, c;
+            sincos(b.omega * t, &s, &c);
+            re = env * c; im = env * s;
+        }
+        tile[p * 2] = mk<float>((float)re, (float)im);
+    }
+    __syncthreads();
+    tile_fft<float, FFT_FWD>(tile, tw, b.logF, 1, 2);
+    const float inv = 1.0f / (float)F;
+    for (int p = threadIdx.x; p < F; p += blockDim.x) tables[b.table_off + p] = tile[p * 2] * inv;
+}
+
+// ---------------------------------------------------------------- A: overlap-save level convolution
+struct MrLevelGeom {
+    int level, logF, TC;
+    int band_first, band_count, n_bands;
+    int wk;                 // two-sided kernel support reserved per block (even); valid outputs per block V = F - wk
+    i64 n_points;           // N
+    i64 n_level;            // N >> level
+    i64 q_first;            // first output index (level rate): -MR_HALO for level >= 1, 0 for level 0
+    i64 n_out;              // outputs per channel at this level
+    i64 n_blocks;
+    i64 x_stride, x_len;    // level signal: per-channel stride, stored length
+    int x_halo;             // halo of the stored level signal (0 for level 0)
+};
+
+__global__ void __launch_bounds__(1024)
+mr_level_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __restrict__ bands,
+                const cplx<float>* __restrict__ tables, cplx<float>* __restrict__ wbuf,
+                float* __restrict__ out_power, cplx<float>* __restrict__ out_complex, double* __restrict__ band_sum) {
+    QI_DYN_SMEM(smem_raw);
+    const int F = 1 << g.logF;
+    const int TC = g.TC, TP = TC + 1;
+    cplx<float>* tile_x = reinterpret_cast<cplx<float>*>(smem_raw);
+    cplx<float>* tile_y = tile_x + (size_t)F * TP;
+    cplx<float>* tw = tile_y + (size_t)F * TP;
+    double* scratch = reinterpret_cast<double*>(tw + F);
+    const i64 chan = blockIdx.y;
+    const i64 blk0 = (i64)blockIdx.x * TC;
+    const int V = F - g.wk;
+    const int logTC = 31 - __clz(TC);
+    const float* xs = x + chan * g.x_stride;
+
+    fill_twiddles<float>(tw, g.logF);
+    for (int idx = threadIdx.x; idx < F * TC; idx += blockDim.x) {
+        const int p = idx & (F - 1);
+        const int c = idx >> g.logF;
+        const i64 blk = blk0 + c;
+        float v = 0.0f;
+        if (blk < g.n_blocks) {
+            const i64 q = g.q_first + blk * V - g.wk / 2 + p;
+            const i64 k = q + g.x_halo;
+            if (k >= 0 && k < g.x_len) v = xs[k];
+        }
+        tile_x[p * TP + c] = mk<float>(v, 0.0f);
+    }
+    __syncthreads();
+    tile_fft<float, FFT_FWD>(tile_x, tw, g.logF, TC, TP);
+
+    for (int bi = 0; bi < g.band_count; ++bi) {
+        const int b = g.band_first + bi;
+        const MrDevBand band = bands[b];
+        const cplx<float>* K = tables + band.table_off;
+        for (int idx = threadIdx.x; idx < F * TC; idx += blockDim.x) {
+            const int c = idx & (TC - 1);
+            const int r = idx >> logTC;
+            tile_y[r * TP + c] = tile_x[r * TP + c] * K[r];
+        }
+        __syncthreads();
+        tile_fft<float, FFT_INV>(tile_y, tw, g.logF, TC, TP);
+        float acc_f = 0.0f;
+        for (int c = 0; c < TC; ++c) {
+            const i64 blk = blk0 + c;
+            if (blk >= g.n_blocks) break;
+            const i64 o0 = blk * V;                 // output ordinal of this block's first valid sample
+            const cplx<float>* ycol = tile_y + (g.wk / 2) * TP + c;
+            if (g.level == 0) {
+                const i64 cell0 = (chan * g.n_bands + b) * g.n_points + o0;
+                for (int pv = threadIdx.x; pv < V; pv += blockDim.x) {     // lanes along the output index
+                    if (o0 + pv < g.n_out) {
+                        const cplx<float> y = ycol[pv * TP];
+                        const float pw = norm2(y);
+                        if (out_power) out_power[cell0 + pv] = pw;
+                        if (out_complex) out_complex[cell0 + pv] = y;
+                        acc_f += pw;
+                    }
+                }
+            } else {
+                cplx<float>* wdst = wbuf + band.w_off + chan * band.w_stride + o0;
+                for (int pv = threadIdx.x; pv < V; pv += blockDim.x)
+                    if (o0 + pv < g.n_out) wdst[pv] = ycol[pv * TP];
+            }
+        }
+        double acc = (double)acc_f;
+        if (g.level == 0 && band_sum) {
+            acc = block_sum(acc, scratch);
+            if (threadIdx.x == 0) atomicAdd(&band_sum[chan * g.n_bands + b], acc);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- E: expand (interpolate by 2^level) + epilogue
+// One half-band interpolation stage in shared memory.  `in` holds level-m samples [a_in, ...), `out` receives level
+// m-1 samples [a_out, a_out + n_out) with a_out and n_out multiples of 8.  Each thread takes MR_PER consecutive input
+// positions q, keeps their MR_PER + 2*NT - 1 neighbours in registers and emits the 2*MR_PER outputs
+// (even = copy, odd = 2 * sum_t c_t (x[q-t] + x[q+t+1])).
+constexpr int MR_PER = 4;
+constexpr int MR_LMID = 5;         // deeper bands are first brought to this level by a (small) separate launch
+constexpr int MR_SEG = MR_TILE / 2 + 48;
+
+template <int NT>
+QI_DEV void hb_window(const cplx<float>* __restrict__ in, int j, const float* __restrict__ c, cplx<float>* ev,
+                      cplx<float>* od) {
+    cplx<float> w[MR_PER + 2 * NT - 1];
+#pragma unroll
+    for (int k = 0; k < MR_PER + 2 * NT - 1; ++k) w[k] = in[j - NT + 1 + k];
+#pragma unroll
+    for (int p = 0; p < MR_PER; ++p) {
+        float re = 0.0f, im = 0.0f;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            re += c[t] * (w[NT - 1 + p - t].re + w[NT + p + t].re);
+            im += c[t] * (w[NT - 1 + p - t].im + w[NT + p + t].im);
+        }
+        ev[p] = w[NT - 1 + p];
+        od[p] = mk<float>(2.0f * re, 2.0f * im);
+    }
+}
+
+template <int NT>
+QI_DEV void hb_stage_smem(const cplx<float>* __restrict__ in, i64 a_in, cplx<float>* __restrict__ out, i64 a_out,
+                          int n_out, const float* __restrict__ c) {
+    const int nq = n_out >> 1;
+    const int j0 = (int)((a_out >> 1) - a_in);
+    for (int i = threadIdx.x * MR_PER; i < nq; i += blockDim.x * MR_PER) {
+        cplx<float> ev[MR_PER], od[MR_PER];
+        hb_window<NT>(in, j0 + i, c, ev, od);
+#pragma unroll
+        for (int p = 0; p < MR_PER; ++p) { out[2 * (i + p)] = ev[p]; out[2 * (i + p) + 1] = od[p]; }
+    }
+}
+
+QI_DEV void hb_stage_dispatch(int nt, const cplx<float>* in, i64 a_in, cplx<float>* out, i64 a_out, int n_out,
+                              const float* c) {
+    switch (nt) {
+        case 2: hb_stage_smem<2>(in, a_in, out, a_out, n_out, c); break;
+        case 3: hb_stage_smem<3>(in, a_in, out, a_out, n_out, c); break;
+        case 4: hb_stage_smem<4>(in, a_in, out, a_out, n_out, c); break;
+        default: hb_stage_smem<7>(in, a_in, out, a_out, n_out, c); break;
+    }
+}
+
+QI_DEV i64 floor_div(i64 a, i64 d) { return a >= 0 ? a / d : -((-a + d - 1) / d); }
+
+struct MrExpandArgs {
+    const MrDevBand* bands;
+    const int* band_list;
+    int n_bands;            // B (row stride of the output planes)
+    int final_stage;        // 1: destination is level 0 (power plane / epilogue); 0: destination is level MR_LMID
+    i64 n_points;
+    const cplx<float>* wbuf;
+    cplx<float>* midbuf;
+    float* out_power;
+    cplx<float>* out_complex;
+    double* band_sum;
+};
+
+// Shared by both launches: bring the tile [t0, t0 + MR_TILE) of the destination level down from the source level.
+// Returns (through smem) the buffer holding the destination-level-plus-one segment and its first index.
+template <int FINAL>
+__global__ void __launch_bounds__(256)
+mr_expand_kernel(MrExpandArgs a, HbTaps taps) {
+    __shared__ cplx<float> buf[2][MR_SEG];
+    __shared__ i64 seg_a[MR_MAX_LEVEL + 2];
+    __shared__ int seg_n[MR_MAX_LEVEL + 2];
+    __shared__ double scratch[32];
+    const int b = a.band_list[blockIdx.y];
+    const MrDevBand band = a.bands[b];
+    const i64 chan = blockIdx.z;
+    const int L = band.level;
+    const int dst = FINAL ? 0 : MR_LMID;
+    const int src = FINAL ? (L < MR_LMID ? L : MR_LMID) : L;
+    const i64 t0 = (FINAL ? 0 : -MR_HALO) + (i64)blockIdx.x * MR_TILE;
+    const int ns = src - dst;                                   // number of stages (>= 1)
+
+    // segment k (k = 0 .. ns) lives at level dst + k; stage k -> k-1 has class L - (dst + k) + 1
+    if (threadIdx.x == 0) {
+        i64 lo = t0, hi = t0 + MR_TILE;
+        seg_a[0] = lo; seg_n[0] = MR_TILE;
+        for (int k = 1; k <= ns; ++k) {
+            const int nt = taps.n[hb_class(L - (dst + k) + 1)];
+            i64 na = (lo >> 1) - nt + 1, ne = (hi >> 1) + nt;       // lo, hi are even
+            if (k < ns) { na = floor_div(na, 8) * 8; ne = floor_div(ne + 7, 8) * 8; }
+            lo = na; hi = ne;
+            seg_a[k] = lo; seg_n[k] = (int)(hi - lo);
+        }
+    }
+    __syncthreads();
+    // load the source-level segment (zero outside the stored [-HALO, n + HALO))
+    const i64 n_src = (a.n_points >> src) + 2 * MR_HALO;
+    const cplx<float>* w = (FINAL && L > MR_LMID) ? a.midbuf + band.mid_off + chan * band.mid_stride
+                                                   : a.wbuf + band.w_off + chan * band.w_stride;
+    for (int i = threadIdx.x; i < seg_n[ns]; i += blockDim.x) {
+        const i64 k = seg_a[ns] + i + MR_HALO;
+        buf[0][i] = (k >= 0 && k < n_src) ? w[k] : mk<float>(0.0f, 0.0f);
+    }
+    __syncthreads();
+    int cur = 0;
+    for (int k = ns; k >= 2; --k) {
+        const int cls = hb_class(L - (dst + k) + 1);
+        hb_stage_dispatch(taps.n[cls], buf[cur], seg_a[k], buf[cur ^ 1], seg_a[k - 1], seg_n[k - 1], taps.c[cls]);
+        cur ^= 1;
+        __syncthreads();
+    }
+    // last stage straight to its destination
+    const int cls = hb_class(L - dst);
+    const int nt = taps.n[cls];
+    const float* c = taps.c[cls];
+    const cplx<float>* in = buf[cur];
+    const int j0 = (int)((t0 >> 1) - seg_a[1]);
+    float acc = 0.0f;
+    for (int i = threadIdx.x * MR_PER; i < MR_TILE / 2; i += blockDim.x * MR_PER) {
+        cplx<float> ev[MR_PER], od[MR_PER];
+        switch (nt) {
+            case 2: hb_window<2>(in, j0 + i, c, ev, od); break;
+            case 3: hb_window<3>(in, j0 + i, c, ev, od); break;
+            case 4: hb_window<4>(in, j0 + i, c, ev, od); break;
+            default: hb_window<7>(in, j0 + i, c, ev, od); break;
+        }
+        const i64 n = t0 + 2 * i;                                  // first of the 2*MR_PER outputs
+        if (FINAL) {
+            const i64 cell = (chan * a.n_bands + b) * a.n_points + n;
+            float pw[2 * MR_PER];
+#pragma unroll
+            for (int p = 0; p < MR_PER; ++p) { pw[2 * p] = norm2(ev[p]); pw[2 * p + 1] = norm2(od[p]); }
+            if (a.out_power) {
+                float4* o = reinterpret_cast<float4*>(a.out_power + cell);
+                o[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
+                o[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
+            }
+            if (a.out_complex) {
+#pragma unroll
+                for (int p = 0; p < MR_PER; ++p) { a.out_complex[cell + 2 * p] = ev[p]; a.out_complex[cell + 2 * p + 1] = od[p]; }
+            }
+#pragma unroll
+            for (int p = 0; p < 2 * MR_PER; ++p) acc += pw[p];
+        } else {
+            const i64 n_mid = (a.n_points >> MR_LMID) + 2 * MR_HALO;
+            cplx<float>* o = a.midbuf + band.mid_off + chan * band.mid_stride;
+#pragma unroll
+            for (int p = 0; p < MR_PER; ++p) {
+                const i64 k = n + 2 * p + MR_HALO;
+                if (k >= 0 && k < n_mid) o[k] = ev[p];
+                if (k + 1 >= 0 && k + 1 < n_mid) o[k + 1] = od[p];
+            }
+        }
+    }
+    if (FINAL && a.band_sum) {
+        const double s = block_sum((double)acc, scratch);
+        if (threadIdx.x == 0) atomicAdd(&a.band_sum[chan * a.n_bands + b], s);
+    }
+}
+
+
+// ---------------------------------------------------------------- host driver
+struct MrPlan {
+    int cap;                         // deepest level
+    std::vector<i64> lvl_off, lvl_len;   // pyramid arrays (levels 1..cap), float elements per channel / offsets
+    std::vector<MrDevBand> bands;
+    std::vector<int> expand_list;       // bands with level >= 1 (final expand launch)
+    std::vector<int> deep_list;         // bands with level > MR_LMID (first brought to level MR_LMID)
+    std::vector<MrLevelGeom> levels;
+    size_t off_bands, off_list, off_deep, off_pyr, off_tables, off_w, off_mid, total;
+    i64 pyr_per_chan, w_total, mid_total;
+};
+
+static HbTaps make_taps() {
+    HbTaps t;
+    for (int j = 0; j < QI_HB_CLASSES; ++j) {
+        t.n[j] = qi_hb_ntaps[j];
+        for (int i = 0; i < QI_HB_MAX_TAPS; ++i) t.c[j][i] = (float)qi_hb_taps[j][i];
+    }
+    return t;
+}
+
+static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl) {
+    int logN = 0;
+    while ((1ll << logN) < N) ++logN;
+    if ((1ll << logN) != N || logN < 11 || logN > 30) return QI_ERR_UNSUPPORTED;
+    pl.cap = logN - 10;
+    if (pl.cap > MR_MAX_LEVEL) return QI_ERR_UNSUPPORTED;
+    // bands must come sorted by ascending frequency => non-increasing level
+    for (int b = 0; b < B; ++b) {
+        if (hb[b].level < 0 || hb[b].level > pl.cap) return QI_ERR_ARG;
+        if (b && hb[b].level > hb[b - 1].level) return QI_ERR_ARG;
+    }
+    // pyramid arrays
+    pl.lvl_off.assign(pl.cap + 1, 0);
+    pl.lvl_len.assign(pl.cap + 1, 0);
+    i64 off = 0;
+    for (int l = 1; l <= pl.cap; ++l) {
+        pl.lvl_len[l] = (N >> l) + 2 * MR_HALO;
+        pl.lvl_off[l] = off;
+        off += (pl.lvl_len[l] + 63) / 64 * 64;
+    }
+    pl.pyr_per_chan = off;
+    // bands, tables, decimated outputs
+    pl.bands.resize(B);
+    pl.expand_list.clear();
+    pl.deep_list.clear();
+    pl.levels.clear();
+    i64 toff = 0, woff = 0, moff = 0;
+    for (int l = pl.cap; l >= 0; --l) {
+        int first = -1, count = 0;
+        double smax = 0.0;
+        for (int b = 0; b < B; ++b)
+            if (hb[b].level == l) { if (first < 0) first = b; ++count; smax = fmax(smax, hb[b].scale / (double)(1ll << l)); }
+        if (!count) continue;
+        MrLevelGeom g;
+        g.level = l; g.band_first = first; g.band_count = count; g.n_bands = B;
+        g.n_points = N; g.n_level = N >> l;
+        g.x_halo = l ? MR_HALO : 0;
+        g.x_len = l ? pl.lvl_len[l] : N;
+        g.q_first = l ? -MR_HALO : 0;
+        g.n_out = l ? (N >> l) + 2 * MR_HALO : N;
+        if (l == pl.cap) {
+            // record-long (possibly truncated) atoms: one block holds the whole level
+            g.wk = (int)(2 * (g.n_level + 2 * MR_HALO));
+            g.logF = 12;
+            if ((1 << g.logF) - g.wk < g.n_out) return QI_ERR_UNSUPPORTED;
+        } else {
+            int half = (int)ceil(5.2 * smax) + 1;
+            g.wk = 2 * half;
+            g.logF = g.wk <= 768 ? 11 : 12;
+            if (g.wk > 3072) return QI_ERR_UNSUPPORTED;
+        }
+        g.TC = g.logF == 11 ? 4 : 1;
+        const int V = (1 << g.logF) - g.wk;
+        g.n_blocks = (g.n_out + V - 1) / V;
+        pl.levels.push_back(g);
+        for (int b = first; b < first + count; ++b) {
+            MrDevBand d;
+            d.omega = hb[b].omega; d.scale = hb[b].scale; d.amp = hb[b].amp; d.level = l; d.logF = g.logF;
+            d.table_off = toff; toff += (1ll << g.logF);
+            d.w_off = 0; d.w_stride = 0; d.mid_off = 0; d.mid_stride = 0;
+            if (l) {
+                d.w_stride = (g.n_out + 63) / 64 * 64;
+                d.w_off = woff; woff += d.w_stride * C;
+                pl.expand_list.push_back(b);
+            }
+            if (l > MR_LMID) {
+                d.mid_stride = ((N >> MR_LMID) + 2 * MR_HALO + 63) / 64 * 64;
+                d.mid_off = moff; moff += d.mid_stride * C;
+                pl.deep_list.push_back(b);
+            }
+            pl.bands[b] = d;
+        }
+    }
+    pl.w_total = woff;
+    pl.mid_total = moff;
+    size_t o = 0;
+    pl.off_bands = o; o = align_up(o + sizeof(MrDevBand) * (size_t)B, 256);
+    pl.off_list = o; o = align_up(o + sizeof(int) * (size_t)(B + 1), 256);
+    pl.off_deep = o; o = align_up(o + sizeof(int) * (size_t)(B + 1), 256);
+    pl.off_pyr = o; o = align_up(o + sizeof(float) * (size_t)pl.pyr_per_chan * C, 256);
+    pl.off_tables = o; o = align_up(o + sizeof(cplx<float>) * (size_t)toff, 256);
+    pl.off_w = o; o = align_up(o + sizeof(cplx<float>) * (size_t)woff, 256);
+    pl.off_mid = o; o = align_up(o + sizeof(cplx<float>) * (size_t)moff, 256);
+    pl.total = o;
+    return QI_OK;
+}
+
+static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb, int B, float* out_power,
+                  cplx<float>* out_complex, double* band_sum, void* ws, size_t ws_bytes, cudaStream_t st) {
+    MrPlan pl;
+    int rc = mr_plan(C, N, hb, B, pl);
+    if (rc != QI_OK) return rc;
+    if (ws_bytes < pl.total) return QI_ERR_WORKSPACE;
+    if (C > 65535 || B > 65535) return QI_ERR_UNSUPPORTED;
+    unsigned char* base = static_cast<unsigned char*>(ws);
+    MrDevBand* d_bands = reinterpret_cast<MrDevBand*>(base + pl.off_bands);
+    int* d_list = reinterpret_cast<int*>(base + pl.off_list);
+    int* d_deep = reinterpret_cast<int*>(base + pl.off_deep);
+    cplx<float>* midbuf = reinterpret_cast<cplx<float>*>(base + pl.off_mid);
+    float* pyr = reinterpret_cast<float*>(base + pl.off_pyr);
+    cplx<float>* tables = reinterpret_cast<cplx<float>*>(base + pl.off_tables);
+    cplx<float>* wbuf = reinterpret_cast<cplx<float>*>(base + pl.off_w);
+    const HbTaps taps = make_taps();
+
+    cudaMemcpyAsync(d_bands, pl.bands.data(), sizeof(MrDevBand) * (size_t)B, cudaMemcpyHostToDevice, st);
+    if (!pl.expand_list.empty())
+        cudaMemcpyAsync(d_list, pl.expand_list.data(), sizeof(int) * pl.expand_list.size(), cudaMemcpyHostToDevice, st);
+    if (!pl.deep_list.empty())
+        cudaMemcpyAsync(d_deep, pl.deep_list.data(), sizeof(int) * pl.deep_list.size(), cudaMemcpyHostToDevice, st);
+#ifndef QI_EMUL
+    cudaStreamSynchronize(st);
+#endif
+    if (band_sum) cudaMemsetAsync(band_sum, 0, sizeof(double) * (size_t)C * B, st);
+
+    // T: kernel tables (one CTA per band)
+    prof_set_category(QI_CAT_FFT_FWD);
+    {
+        const size_t smem = (size_t)4096 * 3 * sizeof(cplx<float>);
+#ifndef QI_EMUL
+        cudaFuncSetAttribute(mr_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+        QI_LAUNCH(mr_table_kernel, dim3((unsigned)B), dim3(256), smem, st, (const MrDevBand*)d_bands, N, 2047, tables);
+    }
+    // P: pyramid
+    for (int l = 1; l <= pl.cap; ++l) {
+        const float* src = l == 1 ? sig : pyr + pl.lvl_off[l - 1];
+        const i64 src_stride = l == 1 ? stride : pl.pyr_per_chan;
+        const i64 src_len = l == 1 ? N : pl.lvl_len[l - 1];
+        dim3 grid((unsigned)((pl.lvl_len[l] + 255) / 256), (unsigned)C);
+        QI_LAUNCH(mr_decimate_kernel, grid, dim3(256), 0, st, src, src_stride, src_len, l == 1 ? 0 : MR_HALO,
+                  pyr + pl.lvl_off[l], pl.pyr_per_chan, pl.lvl_len[l], taps);
+    }
+    // A: level convolutions (deepest first; level 0 last so its epilogue traffic is contiguous in time)
+    for (const MrLevelGeom& g0 : pl.levels) {
+        MrLevelGeom g = g0;
+        const float* x = g.level ? pyr + pl.lvl_off[g.level] : sig;
+        g.x_stride = g.level ? pl.pyr_per_chan : stride;
+        const int F = 1 << g.logF;
+        const size_t smem = ((size_t)F * (g.TC + 1) * 2 + F) * sizeof(cplx<float>) + 256;
+#ifndef QI_EMUL
+        cudaFuncSetAttribute(mr_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+        prof_set_category(g.level ? QI_CAT_INV_FIRST : QI_CAT_INV_MID);
+        dim3 grid((unsigned)((g.n_blocks + g.TC - 1) / g.TC), (unsigned)C);
+        QI_LAUNCH(mr_level_kernel, grid, dim3(1024), smem, st, x, g, (const MrDevBand*)d_bands,
+                  (const cplx<float>*)tables, wbuf, out_power, out_complex, band_sum);
+    }
+    // E: expand -- deep bands first to level MR_LMID (1/32 of the cells), then everything to the full rate
+    MrExpandArgs ea;
+    ea.bands = d_bands; ea.n_bands = B; ea.n_points = N; ea.wbuf = wbuf; ea.midbuf = midbuf;
+    ea.out_power = out_power; ea.out_complex = out_complex; ea.band_sum = band_sum;
+    if (!pl.deep_list.empty()) {
+        prof_set_category(QI_CAT_INV_FIRST);
+        ea.band_list = d_deep; ea.final_stage = 0;
+        const i64 n_mid = (N >> MR_LMID) + 2 * MR_HALO;
+        dim3 grid((unsigned)((n_mid + MR_TILE - 1) / MR_TILE), (unsigned)pl.deep_list.size(), (unsigned)C);
+        QI_LAUNCH((mr_expand_kernel<0>), grid, dim3(256), 0, st, ea, taps);
+    }
+    if (!pl.expand_list.empty()) {
+        prof_set_category(QI_CAT_INV_LAST);
+        ea.band_list = d_list; ea.final_stage = 1;
+        dim3 grid((unsigned)(N / MR_TILE), (unsigned)pl.expand_list.size(), (unsigned)C);
+        QI_LAUNCH((mr_expand_kernel<1>), grid, dim3(256), 0, st, ea, taps);
+    }
+    prof_set_category(QI_CAT_OTHER);
+    return check_cuda("qi_cwt_multirate");
+}
+
+}  // namespace qi
+
+extern "C" {
+
+size_t qi_cwt_multirate_workspace_bytes(int64_t C, int64_t N, const QiMrBand* bands, int B) {
+    if (C <= 0 || N <= 0 || B <= 0 || !bands) return 0;
+    qi::MrPlan pl;
+    if (qi::mr_plan(C, N, bands, B, pl) != QI_OK) return 0;
+    return pl.total;
+}
+
+int qi_cwt_multirate(const void* sig, int64_t C, int64_t N, int64_t stride, const QiMrBand* bands, int B,
+                     void* out_power, void* out_complex, double* band_sum, void* ws, size_t ws_bytes, void* stream) {
+    if (!sig || !bands || !ws || C <= 0 || N <= 0 || B <= 0 || stride < N) return QI_ERR_ARG;
+    if (!out_power && !out_complex && !band_sum) return QI_ERR_ARG;
+    return qi::mr_run(static_cast<const float*>(sig), C, N, stride, bands, B, static_cast<float*>(out_power),
+                      static_cast<qi::cplx<float>*>(out_complex), band_sum, ws, ws_bytes,
+                      static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -43,13 +43,21 @@ class CwtEntropy:
 def cwt_power_entropy(band_order_nth: float, sig_wf, frequency_sample_rate_hz: float, dictionary_type: str = "norm",
                       *, dtype="float32", spectrum: str = "auto", band_slice: Optional[tuple] = None,
                       allreduce: Optional[Callable] = None, want_info: bool = True,
-                      out_power=None, out_info=None) -> CwtEntropy:
+                      out_power=None, out_info=None, method: str = "auto",
+                      truncated_bands: str = "multirate") -> CwtEntropy:
     """Power, information and entropy of the order-N Gabor CWT of ``sig_wf`` ([N] or [C, N]; numpy or CUDA tensor).
 
     band_slice : (b0, b1) computes only bands b0..b1-1 of the standard table (band sharding of one long record).
     allreduce  : callable applied in place to the fp64 [C] tensor of local total power before normalisation
                  (e.g. ``lambda t: torch.distributed.all_reduce(t)``); None = single device.
     out_power / out_info : optional preallocated [C, B, N] device buffers to write into.
+    method     : 'exact' (record FFT + per-band full-length inverse FFT, any dtype), 'multirate' (float32 only:
+                 decimation pyramid + shared-memory overlap-save + half-band interpolation) or 'auto' (multirate
+                 for float32 records of 2^m >= 2048 points, exact otherwise).
+    truncated_bands : what the multirate method does with the lowest bands, whose atoms are cut off by the record
+                 (N/s < 10).  'multirate' keeps them on the fast path (whole-plane power L2 ~ 2e-6, but the
+                 out-of-band leakage the reference's hard truncation lets into those 2-4 bands, ~1e-3 of their
+                 peak, is not reproduced); 'exact' recomputes exactly those bands with the exact method.
     """
     rt = get_runtime()
     dt = dtype_name(dtype, default="float32")
@@ -61,10 +69,27 @@ def cwt_power_entropy(band_order_nth: float, sig_wf, frequency_sample_rate_hz: f
     if not (0 <= b0 < b1 <= len(freq_all)):
         raise ValueError(f"band_slice {band_slice} outside the {len(freq_all)}-band table")
     freq = freq_all[b0:b1]
-    bands, _, _, _ = _plan.gabor_bands(band_order_nth, n_points, freq, frequency_sample_rate_hz, dictionary_type,
-                                       dt, spectrum)
-    res = _driver.cwt_fft(sig, bands, frequency_sample_rate_hz, dt, want_complex=False, want_power=True,
-                          want_band_sum=True, rt=rt, out_power=out_power)
+    bands, scale, _, _ = _plan.gabor_bands(band_order_nth, n_points, freq, frequency_sample_rate_hz,
+                                           dictionary_type, dt, spectrum)
+    if method not in ("auto", "exact", "multirate"):
+        raise ValueError("method must be 'auto', 'exact' or 'multirate'")
+    can_mr = dt == "float32" and _plan.multirate_supported(n_points, scale)
+    if method == "multirate" and not can_mr:
+        raise ValueError("method='multirate' needs float32 and a record of 2^m >= 2048 points")
+    if method != "exact" and can_mr:
+        mr_bands, _, _, _ = _plan.multirate_bands(band_order_nth, n_points, freq, frequency_sample_rate_hz,
+                                                  dictionary_type)
+        res = _driver.cwt_multirate(sig, mr_bands, want_power=True, want_band_sum=True, rt=rt, out_power=out_power)
+        n_trunc = int(np.count_nonzero(bands["analytic"] == 0))
+        if truncated_bands == "exact" and n_trunc:
+            # the truncated atoms are the lowest-frequency rows [0, n_trunc)
+            sub = _driver.cwt_fft(sig, bands[:n_trunc], frequency_sample_rate_hz, dt, want_complex=False,
+                                  want_power=True, want_band_sum=True, rt=rt)
+            res["power"][:, :n_trunc, :] = sub["power"]
+            res["band_sum"][:, :n_trunc] = sub["band_sum"]
+    else:
+        res = _driver.cwt_fft(sig, bands, frequency_sample_rate_hz, dt, want_complex=False, want_power=True,
+                              want_band_sum=True, rt=rt, out_power=out_power)
     power, band_power = res["power"], res["band_sum"]
     total = band_power.sum(-1)                               # [C] fp64 (tiny)
     if allreduce is not None:

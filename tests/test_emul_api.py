@@ -152,3 +152,49 @@ def test_tfr_info(golden):
     # float32 planes stay inside the north-star tolerance (1e-3 bits)
     o32 = tfr_info.shannon_stft_from_tfr_power(p, dtype="float32")
     assert abs(float(o32.shannon_bits.sum()) - float(g["glob_bits"].sum())) < 1e-3
+
+
+def _synth(n, seed=0):
+    k = np.arange(n)
+    chirp = 0.5 * np.cos(2 * np.pi * (1.0 * k / FS + 0.5 * (199.0 / (n / FS)) * (k / FS) ** 2))
+    return np.cos(2 * np.pi * 60.0 / FS * k) + chirp + np.random.default_rng(seed).standard_normal(n) / 16.0
+
+
+@pytest.mark.parametrize("order,logn", [(3, 12), (3, 14), (6, 13), (12, 12), (1, 13)])
+def test_multirate_fused_path(order, logn):
+    """The fp32 fast path (pyramid + overlap-save + half-band interpolation) against the fp64 oracle, inside the
+    north-star fp32 tolerance: power rel. L2 <= 1e-4, entropy <= 1e-3 bits."""
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import cwt_entropy
+    x = np.stack([_synth(1 << logn, 1), _synth(1 << logn, 2)[::-1]])
+    r = cwt_entropy.cwt_power_entropy(order, x, FS, dtype="float32", method="multirate")
+    rx = cwt_entropy.cwt_power_entropy(order, x, FS, dtype="float32", method="multirate", truncated_bands="exact")
+    for c in range(2):
+        ref = orc.cwt_power_entropy(order, x[c], FS)
+        l2 = np.linalg.norm(r.power[c] - ref["power"]) / np.linalg.norm(ref["power"])
+        assert l2 < 2e-5, l2
+        assert abs(float(r.entropy_bits()[c]) - ref["entropy_bits"]) < 1e-4
+        assert np.max(np.abs(r.band_power[c] - ref["band_sum"]) / ref["band_sum"].max()) < 1e-5
+        assert abs(r.total_power[c] - ref["total"]) / ref["total"] < 1e-5
+        per_band = np.linalg.norm(r.power[c] - ref["power"], axis=1) / np.linalg.norm(ref["power"], axis=1)
+        n_trunc = int(np.sum((1 << logn) / (orc.cycles_from_order(order) / (2 * np.pi * ref["freq"] / FS)) < 10.0))
+        assert per_band[n_trunc:].max() < 1e-4          # every untruncated band individually
+        assert per_band.max() < 5e-3                     # documented deviation of the record-long atoms
+        per_band_x = np.linalg.norm(rx.power[c] - ref["power"], axis=1) / np.linalg.norm(ref["power"], axis=1)
+        assert per_band_x.max() < 1e-4                   # ...removed by truncated_bands='exact'
+
+
+def test_multirate_method_selection():
+    from quantum_inferno_b200 import cwt_entropy
+    x = _synth(4096)
+    a = cwt_entropy.cwt_power_entropy(3, x, FS, dtype="float32")                  # auto -> multirate
+    b = cwt_entropy.cwt_power_entropy(3, x, FS, dtype="float32", method="exact")
+    assert np.linalg.norm(a.power - b.power) / np.linalg.norm(b.power) < 2e-5
+    assert not np.array_equal(a.power, b.power)
+    with pytest.raises(ValueError):
+        cwt_entropy.cwt_power_entropy(3, x, FS, dtype="float64", method="multirate")
+    with pytest.raises(ValueError):
+        cwt_entropy.cwt_power_entropy(3, x[:1000], FS, dtype="float32", method="multirate")
+    # non power-of-two records silently use the exact method under 'auto'
+    c = cwt_entropy.cwt_power_entropy(3, x[:3000], FS, dtype="float32")
+    assert c.power.shape == (1, len(c.frequency_hz), 3000)

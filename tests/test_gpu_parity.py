@@ -188,6 +188,55 @@ def test_cwt_vs_oracle(torch_cuda, order, logn):
     assert abs(float(r64.entropy_bits()[0]) - ref["entropy_bits"]) < 1e-10
 
 
+@pytest.mark.parametrize("order,logn", [(3, 12), (3, 16), (6, 14), (12, 13), (1, 13)])
+def test_multirate_vs_oracle(torch_cuda, order, logn):
+    """The fp32 fast path (method='multirate', what 'auto' picks for float32 2^m records) against the fp64 oracle."""
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import cwt_entropy
+    n = 1 << logn
+    x = np.stack([synth(n, chan=0), synth(n, chan=5)[::-1].copy()])
+    r = cwt_entropy.cwt_power_entropy(order, x, FS, dtype="float32", method="multirate")
+    rx = cwt_entropy.cwt_power_entropy(order, x, FS, dtype="float32", method="multirate", truncated_bands="exact")
+    for c in range(2):
+        ref = orc.cwt_power_entropy(order, x[c], FS)
+        p = r.power[c].double().cpu().numpy()
+        assert l2(p, ref["power"]) < 2e-5                                         # tolerance is 1e-4
+        assert abs(float(r.entropy_bits()[c]) - ref["entropy_bits"]) < 1e-4      # tolerance is 1e-3 bits
+        assert abs(float(r.total_power[c]) - ref["total"]) / ref["total"] < 1e-5
+        per_band = np.linalg.norm(p - ref["power"], axis=1) / np.linalg.norm(ref["power"], axis=1)
+        n_trunc = int(np.sum(n / (orc.cycles_from_order(order) / (2 * np.pi * ref["freq"] / FS)) < 10.0))
+        assert per_band[n_trunc:].max() < TOL32_L2 and per_band.max() < 5e-3      # documented record-long-atom deviation
+        px = rx.power[c].double().cpu().numpy()
+        assert (np.linalg.norm(px - ref["power"], axis=1) / np.linalg.norm(ref["power"], axis=1)).max() < TOL32_L2
+        strong = ref["power"] > 1e-4 * ref["power"].max()
+        assert np.abs(r.info[c].double().cpu().numpy() - ref["info"])[strong].max() < 1e-2
+
+
+def test_multirate_properties_north_star_size(torch_cuda):
+    """Size-independent checks at the bench size (2^24 samples, 60 bands): agreement of the two independent CUDA
+    algorithms, sum rules, and the oracle on single bands."""
+    torch = torch_cuda
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import cwt_entropy
+    n = 1 << 24
+    x = torch.from_numpy(synth(n, chan=3)).cuda()
+    a = cwt_entropy.cwt_power_entropy(3, x, FS, dtype="float32", method="multirate")
+    assert tuple(a.power.shape) == (1, 60, n)
+    assert torch.allclose(a.power.double().sum(-1), a.band_power, rtol=1e-5)
+    pdf_sum = (a.power.double() / a.total_power[:, None, None]).sum()
+    assert abs(float(pdf_sum) - 1.0) < 1e-6
+    pa = a.power[0].clone()
+    ent_a = float(a.entropy_bits()[0])
+    del a
+    b = cwt_entropy.cwt_power_entropy(3, x, FS, dtype="float32", method="exact", want_info=True)
+    assert float((pa.double() - b.power[0].double()).norm() / b.power[0].double().norm()) < 2e-5
+    assert abs(ent_a - float(b.entropy_bits()[0])) < 1e-4
+    xf = np.fft.fft(x.cpu().numpy().astype(np.float64), 2 * n)
+    for band in (10, 35, 59):
+        row = np.abs(orc.cwt_band(xf, 3, n, b.frequency_hz[band], FS)) ** 2
+        assert l2(pa[band].double().cpu().numpy(), row) < TOL32_L2
+
+
 def test_cwt_edge_cases(torch_cuda):
     from oracle import qi_oracle as orc
     from quantum_inferno_b200 import styx_cwt

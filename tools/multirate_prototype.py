@@ -56,7 +56,7 @@ def interpolate(y, cls):
     even = y[q]
     odd = np.zeros(len(q), dtype=complex)
     for i, ci in enumerate(c, start=1):
-        odd += ci * (y[q + i] + y[q - i + 1])
+        odd += 2.0 * ci * (y[q + i] + y[q - i + 1])      # interpolator = 2 x the half-band low-pass
     out = np.empty(2 * len(q), dtype=complex)
     out[0::2] = even
     out[1::2] = odd
