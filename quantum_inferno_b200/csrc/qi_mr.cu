@@ -24,33 +24,12 @@
 #include "qi_reduce.cuh"
 #include "qi_tfr.cuh"
 #include "qi_halfband_coeffs.h"
+#include "qi_mr_expand.cuh"
 
 #include <vector>
 #include <math.h>
 
 namespace qi {
-
-constexpr int MR_HALO = 16;        // halo (samples per side) of every stored level array
-constexpr int MR_TILE = 2048;      // full-rate cells per CTA in the expand kernel
-constexpr int MR_MAX_LEVEL = 20;
-
-struct HbTaps {
-    int n[QI_HB_CLASSES];
-    float c[QI_HB_CLASSES][QI_HB_MAX_TAPS];
-};
-
-struct MrDevBand {
-    double omega, scale, amp;
-    int level;
-    int logF;            // FFT length of this band's level
-    long long table_off; // offset (complex elements) of its kernel table
-    long long w_off;     // offset (complex elements) of its decimated output, per channel stride w_stride
-    long long w_stride;
-    long long mid_off;   // level-MR_LMID copy (bands deeper than MR_LMID only), per channel stride mid_stride
-    long long mid_stride;
-};
-
-QI_DEV int hb_class(int j) { return j < 1 ? 0 : (j > QI_HB_CLASSES ? QI_HB_CLASSES - 1 : j - 1); }
 
 // ---------------------------------------------------------------- P: half-band decimation by 2
 // src: level l (with halo `src_halo`, length src_len incl. halo; level 0: halo 0), dst: level l+1 with MR_HALO.
@@ -196,169 +175,6 @@ mr_level_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __r
         __syncthreads();
     }
 }
-
-// ---------------------------------------------------------------- E: expand (interpolate by 2^level) + epilogue
-// One half-band interpolation stage in shared memory.  `in` holds level-m samples [a_in, ...), `out` receives level
-// m-1 samples [a_out, a_out + n_out) with a_out and n_out multiples of 8.  Each thread takes MR_PER consecutive input
-// positions q, keeps their MR_PER + 2*NT - 1 neighbours in registers and emits the 2*MR_PER outputs
-// (even = copy, odd = 2 * sum_t c_t (x[q-t] + x[q+t+1])).
-constexpr int MR_PER = 4;
-constexpr int MR_LMID = 5;         // deeper bands are first brought to this level by a (small) separate launch
-constexpr int MR_SEG = MR_TILE / 2 + 48;
-
-template <int NT>
-QI_DEV void hb_window(const cplx<float>* __restrict__ in, int j, const float* __restrict__ c, cplx<float>* ev,
-                      cplx<float>* od) {
-    cplx<float> w[MR_PER + 2 * NT - 1];
-#pragma unroll
-    for (int k = 0; k < MR_PER + 2 * NT - 1; ++k) w[k] = in[j - NT + 1 + k];
-#pragma unroll
-    for (int p = 0; p < MR_PER; ++p) {
-        float re = 0.0f, im = 0.0f;
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            re += c[t] * (w[NT - 1 + p - t].re + w[NT + p + t].re);
-            im += c[t] * (w[NT - 1 + p - t].im + w[NT + p + t].im);
-        }
-        ev[p] = w[NT - 1 + p];
-        od[p] = mk<float>(2.0f * re, 2.0f * im);
-    }
-}
-
-template <int NT>
-QI_DEV void hb_stage_smem(const cplx<float>* __restrict__ in, i64 a_in, cplx<float>* __restrict__ out, i64 a_out,
-                          int n_out, const float* __restrict__ c) {
-    const int nq = n_out >> 1;
-    const int j0 = (int)((a_out >> 1) - a_in);
-    for (int i = threadIdx.x * MR_PER; i < nq; i += blockDim.x * MR_PER) {
-        cplx<float> ev[MR_PER], od[MR_PER];
-        hb_window<NT>(in, j0 + i, c, ev, od);
-#pragma unroll
-        for (int p = 0; p < MR_PER; ++p) { out[2 * (i + p)] = ev[p]; out[2 * (i + p) + 1] = od[p]; }
-    }
-}
-
-QI_DEV void hb_stage_dispatch(int nt, const cplx<float>* in, i64 a_in, cplx<float>* out, i64 a_out, int n_out,
-                              const float* c) {
-    switch (nt) {
-        case 2: hb_stage_smem<2>(in, a_in, out, a_out, n_out, c); break;
-        case 3: hb_stage_smem<3>(in, a_in, out, a_out, n_out, c); break;
-        case 4: hb_stage_smem<4>(in, a_in, out, a_out, n_out, c); break;
-        default: hb_stage_smem<7>(in, a_in, out, a_out, n_out, c); break;
-    }
-}
-
-QI_DEV i64 floor_div(i64 a, i64 d) { return a >= 0 ? a / d : -((-a + d - 1) / d); }
-
-struct MrExpandArgs {
-    const MrDevBand* bands;
-    const int* band_list;
-    int n_bands;            // B (row stride of the output planes)
-    int final_stage;        // 1: destination is level 0 (power plane / epilogue); 0: destination is level MR_LMID
-    i64 n_points;
-    const cplx<float>* wbuf;
-    cplx<float>* midbuf;
-    float* out_power;
-    cplx<float>* out_complex;
-    double* band_sum;
-};
-
-// Shared by both launches: bring the tile [t0, t0 + MR_TILE) of the destination level down from the source level.
-// Returns (through smem) the buffer holding the destination-level-plus-one segment and its first index.
-template <int FINAL>
-__global__ void __launch_bounds__(256)
-mr_expand_kernel(MrExpandArgs a, HbTaps taps) {
-    __shared__ cplx<float> buf[2][MR_SEG];
-    __shared__ i64 seg_a[MR_MAX_LEVEL + 2];
-    __shared__ int seg_n[MR_MAX_LEVEL + 2];
-    __shared__ double scratch[32];
-    const int b = a.band_list[blockIdx.y];
-    const MrDevBand band = a.bands[b];
-    const i64 chan = blockIdx.z;
-    const int L = band.level;
-    const int dst = FINAL ? 0 : MR_LMID;
-    const int src = FINAL ? (L < MR_LMID ? L : MR_LMID) : L;
-    const i64 t0 = (FINAL ? 0 : -MR_HALO) + (i64)blockIdx.x * MR_TILE;
-    const int ns = src - dst;                                   // number of stages (>= 1)
-
-    // segment k (k = 0 .. ns) lives at level dst + k; stage k -> k-1 has class L - (dst + k) + 1
-    if (threadIdx.x == 0) {
-        i64 lo = t0, hi = t0 + MR_TILE;
-        seg_a[0] = lo; seg_n[0] = MR_TILE;
-        for (int k = 1; k <= ns; ++k) {
-            const int nt = taps.n[hb_class(L - (dst + k) + 1)];
-            i64 na = (lo >> 1) - nt + 1, ne = (hi >> 1) + nt;       // lo, hi are even
-            if (k < ns) { na = floor_div(na, 8) * 8; ne = floor_div(ne + 7, 8) * 8; }
-            lo = na; hi = ne;
-            seg_a[k] = lo; seg_n[k] = (int)(hi - lo);
-        }
-    }
-    __syncthreads();
-    // load the source-level segment (zero outside the stored [-HALO, n + HALO))
-    const i64 n_src = (a.n_points >> src) + 2 * MR_HALO;
-    const cplx<float>* w = (FINAL && L > MR_LMID) ? a.midbuf + band.mid_off + chan * band.mid_stride
-                                                   : a.wbuf + band.w_off + chan * band.w_stride;
-    for (int i = threadIdx.x; i < seg_n[ns]; i += blockDim.x) {
-        const i64 k = seg_a[ns] + i + MR_HALO;
-        buf[0][i] = (k >= 0 && k < n_src) ? w[k] : mk<float>(0.0f, 0.0f);
-    }
-    __syncthreads();
-    int cur = 0;
-    for (int k = ns; k >= 2; --k) {
-        const int cls = hb_class(L - (dst + k) + 1);
-        hb_stage_dispatch(taps.n[cls], buf[cur], seg_a[k], buf[cur ^ 1], seg_a[k - 1], seg_n[k - 1], taps.c[cls]);
-        cur ^= 1;
-        __syncthreads();
-    }
-    // last stage straight to its destination
-    const int cls = hb_class(L - dst);
-    const int nt = taps.n[cls];
-    const float* c = taps.c[cls];
-    const cplx<float>* in = buf[cur];
-    const int j0 = (int)((t0 >> 1) - seg_a[1]);
-    float acc = 0.0f;
-    for (int i = threadIdx.x * MR_PER; i < MR_TILE / 2; i += blockDim.x * MR_PER) {
-        cplx<float> ev[MR_PER], od[MR_PER];
-        switch (nt) {
-            case 2: hb_window<2>(in, j0 + i, c, ev, od); break;
-            case 3: hb_window<3>(in, j0 + i, c, ev, od); break;
-            case 4: hb_window<4>(in, j0 + i, c, ev, od); break;
-            default: hb_window<7>(in, j0 + i, c, ev, od); break;
-        }
-        const i64 n = t0 + 2 * i;                                  // first of the 2*MR_PER outputs
-        if (FINAL) {
-            const i64 cell = (chan * a.n_bands + b) * a.n_points + n;
-            float pw[2 * MR_PER];
-#pragma unroll
-            for (int p = 0; p < MR_PER; ++p) { pw[2 * p] = norm2(ev[p]); pw[2 * p + 1] = norm2(od[p]); }
-            if (a.out_power) {
-                float4* o = reinterpret_cast<float4*>(a.out_power + cell);
-                o[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
-                o[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
-            }
-            if (a.out_complex) {
-#pragma unroll
-                for (int p = 0; p < MR_PER; ++p) { a.out_complex[cell + 2 * p] = ev[p]; a.out_complex[cell + 2 * p + 1] = od[p]; }
-            }
-#pragma unroll
-            for (int p = 0; p < 2 * MR_PER; ++p) acc += pw[p];
-        } else {
-            const i64 n_mid = (a.n_points >> MR_LMID) + 2 * MR_HALO;
-            cplx<float>* o = a.midbuf + band.mid_off + chan * band.mid_stride;
-#pragma unroll
-            for (int p = 0; p < MR_PER; ++p) {
-                const i64 k = n + 2 * p + MR_HALO;
-                if (k >= 0 && k < n_mid) o[k] = ev[p];
-                if (k + 1 >= 0 && k + 1 < n_mid) o[k + 1] = od[p];
-            }
-        }
-    }
-    if (FINAL && a.band_sum) {
-        const double s = block_sum((double)acc, scratch);
-        if (threadIdx.x == 0) atomicAdd(&a.band_sum[chan * a.n_bands + b], s);
-    }
-}
-
 
 // ---------------------------------------------------------------- host driver
 struct MrPlan {
@@ -534,14 +350,14 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     ea.out_power = out_power; ea.out_complex = out_complex; ea.band_sum = band_sum;
     if (!pl.deep_list.empty()) {
         prof_set_category(QI_CAT_INV_FIRST);
-        ea.band_list = d_deep; ea.final_stage = 0;
+        ea.band_list = d_deep;
         const i64 n_mid = (N >> MR_LMID) + 2 * MR_HALO;
         dim3 grid((unsigned)((n_mid + MR_TILE - 1) / MR_TILE), (unsigned)pl.deep_list.size(), (unsigned)C);
         QI_LAUNCH((mr_expand_kernel<0>), grid, dim3(256), 0, st, ea, taps);
     }
     if (!pl.expand_list.empty()) {
         prof_set_category(QI_CAT_INV_LAST);
-        ea.band_list = d_list; ea.final_stage = 1;
+        ea.band_list = d_list;
         dim3 grid((unsigned)(N / MR_TILE), (unsigned)pl.expand_list.size(), (unsigned)C);
         QI_LAUNCH((mr_expand_kernel<1>), grid, dim3(256), 0, st, ea, taps);
     }
