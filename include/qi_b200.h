@@ -112,7 +112,7 @@ int qi_atoms_time(const QiAtomBand* bands, int n_bands, int64_t n_points, double
  * then half-band interpolation back to the full rate fused with |.|^2 and the fp64 band sums.
  * Replaces quantum_inferno/styx_cwt.py:147-198 followed by np.abs(cwt)**2.
  * bands: HOST array sorted by ascending centre frequency; level = log2 of the decimation the host planner chose
- * (non-increasing along the array, 0 <= level <= log2(n_points) - 10).  n_points = 2^m, m >= 11. */
+ * (non-increasing along the array, 0 <= level <= log2(n_points) - 10).  n_points = 2^m, m >= 13. */
 typedef struct {
     double omega;    /* centre, rad/sample at the full rate */
     double scale;    /* atom scale s in samples             */

@@ -142,11 +142,11 @@ def stft_time_axis(ext_length, nperseg, noverlap, fs, boundary_zeros=True):
 # ----------------------------------------------------------------------------- multirate fp32 CWT
 MR_KAPPA = 4.8           # half-width (in 1/s) of the band response that must sit inside a level's alias-free band
 MR_PASS = np.pi / 2      # alias-free band of every pyramid level, in radians at that level's rate
-MR_MIN_LOG2_POINTS = 11
+MR_MIN_LOG2_POINTS = 13
 
 
 def multirate_supported(n_points, scale):
-    """The multirate path needs a 2^m record (m >= 11) and atoms at least one sample wide."""
+    """The multirate path needs a 2^m record (m >= 13) and atoms at least one sample wide."""
     n = int(n_points)
     return n >= (1 << MR_MIN_LOG2_POINTS) and (n & (n - 1)) == 0 and bool(np.all(np.asarray(scale) >= ANALYTIC_MIN_SCALE))
 

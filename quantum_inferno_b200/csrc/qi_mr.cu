@@ -200,7 +200,7 @@ static HbTaps make_taps() {
 static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl) {
     int logN = 0;
     while ((1ll << logN) < N) ++logN;
-    if ((1ll << logN) != N || logN < 11 || logN > 30) return QI_ERR_UNSUPPORTED;
+    if ((1ll << logN) != N || logN < 13 || logN > 30) return QI_ERR_UNSUPPORTED;
     pl.cap = logN - 10;
     if (pl.cap > MR_MAX_LEVEL) return QI_ERR_UNSUPPORTED;
     // bands must come sorted by ascending frequency => non-increasing level
@@ -348,18 +348,33 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     MrExpandArgs ea;
     ea.bands = d_bands; ea.n_bands = B; ea.n_points = N; ea.wbuf = wbuf; ea.midbuf = midbuf;
     ea.out_power = out_power; ea.out_complex = out_complex; ea.band_sum = band_sum;
+    // both lists are ordered deepest level first, so the bands sharing a polyphase factor 2^k are contiguous
+    auto launch_groups = [&](const std::vector<int>& list, const int* d_idx, int dst_level, i64 n_dst, bool final) {
+        size_t pos = 0;
+        while (pos < list.size()) {
+            const int lr0 = pl.bands[list[pos]].level - dst_level;
+            const int k = lr0 < 3 ? lr0 : 3;
+            size_t end = pos;
+            while (end < list.size()) {
+                const int lr = pl.bands[list[end]].level - dst_level;
+                if ((lr < 3 ? lr : 3) != k) break;
+                ++end;
+            }
+            ea.band_list = d_idx + pos;
+            const i64 tile = (i64)MR_SEGQ << k;
+            dim3 grid((unsigned)((n_dst + tile - 1) / tile), (unsigned)(end - pos), (unsigned)C);
+            if (final) QI_LAUNCH((mr_expand_kernel<1>), grid, dim3(256), 0, st, ea, taps);
+            else QI_LAUNCH((mr_expand_kernel<0>), grid, dim3(256), 0, st, ea, taps);
+            pos = end;
+        }
+    };
     if (!pl.deep_list.empty()) {
         prof_set_category(QI_CAT_INV_FIRST);
-        ea.band_list = d_deep;
-        const i64 n_mid = (N >> MR_LMID) + 2 * MR_HALO;
-        dim3 grid((unsigned)((n_mid + MR_TILE - 1) / MR_TILE), (unsigned)pl.deep_list.size(), (unsigned)C);
-        QI_LAUNCH((mr_expand_kernel<0>), grid, dim3(256), 0, st, ea, taps);
+        launch_groups(pl.deep_list, d_deep, MR_LMID, (N >> MR_LMID) + 2 * MR_HALO, false);
     }
     if (!pl.expand_list.empty()) {
         prof_set_category(QI_CAT_INV_LAST);
-        ea.band_list = d_list;
-        dim3 grid((unsigned)(N / MR_TILE), (unsigned)pl.expand_list.size(), (unsigned)C);
-        QI_LAUNCH((mr_expand_kernel<1>), grid, dim3(256), 0, st, ea, taps);
+        launch_groups(pl.expand_list, d_list, 0, N, true);
     }
     prof_set_category(QI_CAT_OTHER);
     return check_cuda("qi_cwt_multirate");

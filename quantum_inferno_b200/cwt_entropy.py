@@ -53,7 +53,7 @@ def cwt_power_entropy(band_order_nth: float, sig_wf, frequency_sample_rate_hz: f
     out_power / out_info : optional preallocated [C, B, N] device buffers to write into.
     method     : 'exact' (record FFT + per-band full-length inverse FFT, any dtype), 'multirate' (float32 only:
                  decimation pyramid + shared-memory overlap-save + half-band interpolation) or 'auto' (multirate
-                 for float32 records of 2^m >= 2048 points, exact otherwise).
+                 for float32 records of 2^m >= 8192 points, exact otherwise).
     truncated_bands : what the multirate method does with the lowest bands, whose atoms are cut off by the record
                  (N/s < 10).  'multirate' keeps them on the fast path (whole-plane power L2 ~ 2e-6, but the
                  out-of-band leakage the reference's hard truncation lets into those 2-4 bands, ~1e-3 of their
@@ -75,7 +75,7 @@ def cwt_power_entropy(band_order_nth: float, sig_wf, frequency_sample_rate_hz: f
         raise ValueError("method must be 'auto', 'exact' or 'multirate'")
     can_mr = dt == "float32" and _plan.multirate_supported(n_points, scale)
     if method == "multirate" and not can_mr:
-        raise ValueError("method='multirate' needs float32 and a record of 2^m >= 2048 points")
+        raise ValueError("method='multirate' needs float32 and a record of 2^m >= 8192 points")
     if method != "exact" and can_mr:
         mr_bands, _, _, _ = _plan.multirate_bands(band_order_nth, n_points, freq, frequency_sample_rate_hz,
                                                   dictionary_type)

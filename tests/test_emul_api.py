@@ -160,7 +160,7 @@ def _synth(n, seed=0):
     return np.cos(2 * np.pi * 60.0 / FS * k) + chirp + np.random.default_rng(seed).standard_normal(n) / 16.0
 
 
-@pytest.mark.parametrize("order,logn", [(3, 12), (3, 14), (6, 13), (12, 12), (1, 13)])
+@pytest.mark.parametrize("order,logn", [(3, 13), (3, 15), (6, 13), (12, 13), (1, 14)])
 def test_multirate_fused_path(order, logn):
     """The fp32 fast path (pyramid + overlap-save + half-band interpolation) against the fp64 oracle, inside the
     north-star fp32 tolerance: power rel. L2 <= 1e-4, entropy <= 1e-3 bits."""
@@ -186,7 +186,7 @@ def test_multirate_fused_path(order, logn):
 
 def test_multirate_method_selection():
     from quantum_inferno_b200 import cwt_entropy
-    x = _synth(4096)
+    x = _synth(8192)
     a = cwt_entropy.cwt_power_entropy(3, x, FS, dtype="float32")                  # auto -> multirate
     b = cwt_entropy.cwt_power_entropy(3, x, FS, dtype="float32", method="exact")
     assert np.linalg.norm(a.power - b.power) / np.linalg.norm(b.power) < 2e-5
