@@ -123,10 +123,24 @@ typedef struct {
 
 size_t qi_cwt_multirate_workspace_bytes(int64_t n_channels, int64_t n_points, const QiMrBand* bands, int n_bands);
 
-/* out_power float [C,B,N] or NULL; out_cwt complex64 [C,B,N] or NULL; band_sum double [C,B] or NULL */
+/* out_power float [C,B,N] or NULL; out_cwt complex64 [C,B,N] or NULL; band_sum double [C,B] (exact sums of the
+ * stored power) or NULL.
+ *
+ * Fused information / entropy (replaces tfr_info.py:231-236 on top of the CWT, one pass over the planes):
+ * pass out_info float [C,B,N]; then out_power, band_sum, band_sum_est [C,B] and total_power [C] are required and
+ * entropy_sum double [C,B] (sum_t pdf*info per band) is optional.  info = -log2(P/S + eps) with S = total_power[c].
+ * S must be known before the planes are written, so it is first estimated from the decimated band outputs
+ * (relative error ~1e-6, see qi_mr_expand.cuh); `phase` lets a band-sharded caller all-reduce it in between:
+ *   QI_MR_PHASE_ALL      everything; total_power is written, then used
+ *   QI_MR_PHASE_ESTIMATE up to band_sum_est [C,B] (and total_power = its row sums); nothing expanded yet
+ *   QI_MR_PHASE_EXPAND   expand with the total_power the caller provides (same workspace, untouched in between) */
+#define QI_MR_PHASE_ALL 0
+#define QI_MR_PHASE_ESTIMATE 1
+#define QI_MR_PHASE_EXPAND 2
 int qi_cwt_multirate(const void* sig, int64_t n_channels, int64_t n_points, int64_t sig_stride,
                      const QiMrBand* bands, int n_bands, void* out_power, void* out_cwt, double* band_sum,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     void* out_info, double* entropy_sum, double* band_sum_est, double* total_power, double eps,
+                     int phase, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- Stockwell transform ----------------------------------------------------------------------
  * Replaces quantum_inferno/styx_stx.py:195-236 (stx_complex_any_scale_pow2) and the band loop of

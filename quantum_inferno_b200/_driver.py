@@ -213,8 +213,13 @@ def abs_log2(buf, dt, is_complex, eps=EPS64, square=False, rt=None, signed=False
     return out
 
 
-def cwt_multirate(sig, bands, want_power=True, want_complex=False, want_band_sum=False, rt=None, out_power=None):
-    """Run qi_cwt_multirate (float32).  sig: device float32 [C, N]; bands: numpy MR_BAND table."""
+def cwt_multirate(sig, bands, want_power=True, want_complex=False, want_band_sum=False, rt=None, out_power=None,
+                  want_info=False, out_info=None, allreduce=None, eps=EPS64):
+    """Run qi_cwt_multirate (float32).  sig: device float32 [C, N]; bands: numpy MR_BAND table.
+
+    want_info fuses the information plane -log2(P/S + eps) and the per-band entropy sums into the pass that writes
+    the power plane.  S (per record) is estimated from the decimated band outputs first; with ``allreduce`` (band
+    sharding) the call is split in two phases and the estimate is all-reduced in between."""
     rt = rt or get_runtime()
     lib = rt.lib
     C, N = int(sig.shape[0]), int(sig.shape[1])
@@ -224,11 +229,27 @@ def cwt_multirate(sig, bands, want_power=True, want_complex=False, want_band_sum
     if nbytes == 0:
         raise ValueError("qi_cwt_multirate: unsupported size or band table")
     ws = rt.workspace(nbytes)
-    if want_power and out_power is None:
+    if (want_power or want_info) and out_power is None:
         out_power = rt.empty((C, B, N), "float32")
     out_c = rt.empty((C, B, N), "complex64") if want_complex else None
-    bsum = rt.empty((C, B), "float64") if want_band_sum else None
-    rc = lib.qi_cwt_multirate(rt.ptr(sig), C, N, N, bands.ctypes.data, B, rt.ptr(out_power), rt.ptr(out_c),
-                              rt.ptr(bsum), rt.ptr(ws), nbytes, rt.stream())
-    _lib.check(lib, rc, "qi_cwt_multirate")
-    return {"complex": out_c, "power": out_power, "band_sum": bsum}
+    bsum = rt.empty((C, B), "float64") if (want_band_sum or want_info) else None
+    ent = est = total = None
+    if want_info:
+        if out_info is None:
+            out_info = rt.empty((C, B, N), "float32")
+        ent, est, total = rt.empty((C, B), "float64"), rt.empty((C, B), "float64"), rt.empty((C,), "float64")
+
+    def call(phase):
+        rc = lib.qi_cwt_multirate(rt.ptr(sig), C, N, N, bands.ctypes.data, B, rt.ptr(out_power), rt.ptr(out_c),
+                                  rt.ptr(bsum), rt.ptr(out_info) if want_info else None, rt.ptr(ent), rt.ptr(est),
+                                  rt.ptr(total), float(eps), phase, rt.ptr(ws), nbytes, rt.stream())
+        _lib.check(lib, rc, "qi_cwt_multirate")
+
+    if want_info and allreduce is not None:
+        call(1)                     # QI_MR_PHASE_ESTIMATE
+        allreduce(total)            # the one collective of the band-sharded case
+        call(2)                     # QI_MR_PHASE_EXPAND
+    else:
+        call(0)
+    return {"complex": out_c, "power": out_power, "band_sum": bsum, "info": out_info if want_info else None,
+            "entropy_sum": ent, "band_sum_est": est, "total": total}

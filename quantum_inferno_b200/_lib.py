@@ -44,8 +44,8 @@ SIGNATURES = {
     "qi_atoms_time": (_c_int, [_c_vp, _c_int, _c_i64, _c_dbl, _c_int, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),
     "qi_abs_log2": (_c_int, [_c_vp, _c_i64, _c_int, _c_int, _c_int, _c_dbl, _c_vp, _c_vp]),
     "qi_cwt_multirate_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_vp, _c_int]),
-    "qi_cwt_multirate": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz,
-                                  _c_vp]),
+    "qi_cwt_multirate": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
+                                  _c_vp, _c_vp, _c_dbl, _c_int, _c_vp, _c_sz, _c_vp]),
     "qi_stx_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int, _c_int, _c_int]),
     "qi_stx_fft": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int,
                             _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_vp]),

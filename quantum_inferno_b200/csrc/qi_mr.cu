@@ -25,6 +25,7 @@
 #include "qi_tfr.cuh"
 #include "qi_halfband_coeffs.h"
 #include "qi_mr_expand.cuh"
+#include "qi_fft_tc4.cuh"
 
 #include <vector>
 #include <math.h>
@@ -176,6 +177,83 @@ mr_level_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __r
     }
 }
 
+// ---------------------------------------------------------------- A': the same for 2048-point blocks, 4 per CTA
+// Compile-time geometry + XOR-swizzled tile (qi_fft_tc4.cuh): every shared-memory access of the kernel is bank
+// conflict free.  Used for every level except the deepest (whose single 4096-point block goes through the
+// generic kernel above).
+__global__ void __launch_bounds__(1024)
+mr_level4_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __restrict__ bands,
+                 const cplx<float>* __restrict__ tables, cplx<float>* __restrict__ wbuf,
+                 float* __restrict__ out_power, cplx<float>* __restrict__ out_complex, double* __restrict__ band_sum) {
+    constexpr int LOGF = 11, F = 1 << LOGF, TC = 4;
+    QI_DYN_SMEM(smem_raw);
+    cplx<float>* tile_x = reinterpret_cast<cplx<float>*>(smem_raw);
+    cplx<float>* tile_y = tile_x + F * TC;
+    cplx<float>* tw = tile_y + F * TC;
+    double* scratch = reinterpret_cast<double*>(tw + F);
+    const i64 chan = blockIdx.y;
+    const i64 blk0 = (i64)blockIdx.x * TC;
+    const int V = F - g.wk;
+    const int half = g.wk / 2;
+    const float* xs = x + chan * g.x_stride;
+
+    fill_twiddles<float>(tw, LOGF);
+    for (int idx = threadIdx.x; idx < F * TC; idx += blockDim.x) {
+        const int p = idx & (F - 1);                 // lanes along the samples -> coalesced global loads
+        const int c = idx >> LOGF;
+        const i64 blk = blk0 + c;
+        float v = 0.0f;
+        if (blk < g.n_blocks) {
+            const i64 k = g.q_first + blk * V - half + p + g.x_halo;
+            if (k >= 0 && k < g.x_len) v = xs[k];
+        }
+        tile_x[sw4(p, c)] = mk<float>(v, 0.0f);
+    }
+    __syncthreads();
+    tc4_fft_fwd<LOGF>(tile_x, tw);
+
+    for (int bi = 0; bi < g.band_count; ++bi) {
+        const int b = g.band_first + bi;
+        const MrDevBand band = bands[b];
+        const cplx<float>* K = tables + band.table_off;
+        // slots are visited linearly: slot -> (row, column) is only needed for the table index
+        for (int slot = threadIdx.x; slot < F * TC; slot += blockDim.x) {
+            const int rs = slot >> 2;                                  // r ^ s with s = (r >> 2) & 3 = (rs >> 2) & 3
+            const int r = rs ^ ((rs >> 2) & 3);
+            tile_y[slot] = tile_x[slot] * K[r];
+        }
+        __syncthreads();
+        tc4_fft_inv<LOGF>(tile_y, tw);
+        float acc_f = 0.0f;
+        for (int c = 0; c < TC; ++c) {
+            const i64 blk = blk0 + c;
+            if (blk >= g.n_blocks) break;
+            const i64 o0 = blk * V;
+            if (g.level == 0) {
+                const i64 cell0 = (chan * g.n_bands + b) * g.n_points + o0;
+                for (int pv = threadIdx.x; pv < V; pv += blockDim.x) {
+                    if (o0 + pv < g.n_out) {
+                        const cplx<float> y = tile_y[sw4(pv + half, c)];
+                        const float pw = norm2(y);
+                        if (out_power) out_power[cell0 + pv] = pw;
+                        if (out_complex) out_complex[cell0 + pv] = y;
+                        acc_f += pw;
+                    }
+                }
+            } else {
+                cplx<float>* wdst = wbuf + band.w_off + chan * band.w_stride + o0;
+                for (int pv = threadIdx.x; pv < V; pv += blockDim.x)
+                    if (o0 + pv < g.n_out) wdst[pv] = tile_y[sw4(pv + half, c)];
+            }
+        }
+        if (g.level == 0 && band_sum) {
+            const double acc = block_sum((double)acc_f, scratch);
+            if (threadIdx.x == 0) atomicAdd(&band_sum[chan * g.n_bands + b], acc);
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- host driver
 struct MrPlan {
     int cap;                         // deepest level
@@ -284,8 +362,87 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl) {
     return QI_OK;
 }
 
+// total[c] = sum of the level-0 bands' exact sums + the deeper bands' estimates; the estimate table is completed
+// with the exact level-0 entries so the caller sees one [C, B] table.
+__global__ void mr_total_kernel(const MrDevBand* __restrict__ bands, int B, const double* __restrict__ band_sum,
+                                double* __restrict__ band_sum_est, double* __restrict__ total) {
+    __shared__ double scratch[32];
+    const i64 c = blockIdx.x;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        if (bands[b].level == 0) band_sum_est[c * B + b] = band_sum[c * B + b];
+        s += band_sum_est[c * B + b];
+    }
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) total[c] = s;
+}
+
+// Band-sum estimate straight from a band's decimated output w (level L, h = 2^L), needed before the planes are
+// written:  sum_{n<N} P(n) ~= h * sum_{q<N/h} P(h q) + (h - 1)/2 * (P(N) - P(0))   (Euler-Maclaurin; |w|^2 is
+// band-limited below the level's Nyquist rate, the next term is O(h/(12 s)) smaller than the correction).
+__global__ void __launch_bounds__(256)
+mr_sums_kernel(const MrDevBand* __restrict__ bands, const int* __restrict__ band_list, int B, i64 n_points,
+               const cplx<float>* __restrict__ wbuf, const cplx<float>* __restrict__ midbuf,
+               double* __restrict__ band_sum_est) {
+    __shared__ double scratch[32];
+    const int b = band_list[blockIdx.y];
+    const MrDevBand band = bands[b];
+    const i64 c = blockIdx.z;
+    // deep bands are summed on their level-MR_LMID copy (smaller h => smaller Euler-Maclaurin remainder)
+    const int lvl = band.level > MR_LMID ? MR_LMID : band.level;
+    const i64 m = n_points >> lvl;
+    const cplx<float>* w = (band.level > MR_LMID ? midbuf + band.mid_off + c * band.mid_stride
+                                                  : wbuf + band.w_off + c * band.w_stride) + MR_HALO;
+    const i64 chunk = (m + gridDim.x - 1) / gridDim.x;
+    const i64 q0 = (i64)blockIdx.x * chunk;
+    const i64 q1 = q0 + chunk < m ? q0 + chunk : m;
+    double s = 0.0;
+    for (i64 q = q0 + threadIdx.x; q < q1; q += blockDim.x) s += (double)norm2(w[q]);
+    const double h = (double)(1ll << lvl);
+    s *= h;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // Euler-Maclaurin end corrections: + (h-1)/2 (P(N) - P(0)) - (h^2-1)/12 (P'(N) - P'(0)), P' by central differences
+        const double p0 = norm2(w[0]), pn = norm2(w[m]);
+        const double d0 = ((double)norm2(w[1]) - (double)norm2(w[-1])) / (2.0 * h);
+        const double dn = ((double)norm2(w[m + 1]) - (double)norm2(w[m - 1])) / (2.0 * h);
+        s += 0.5 * (h - 1.0) * (pn - p0) - (h * h - 1.0) / 12.0 * (dn - d0);
+    }
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) atomicAdd(&band_sum_est[c * B + b], s);
+}
+
+// information plane + entropy sums of the rows the level-0 kernel wrote (their power is already in HBM)
+__global__ void __launch_bounds__(256)
+mr_info_rows_kernel(const float4* __restrict__ p, const double* __restrict__ total, int B, int b_first, i64 T4,
+                    float eps, float4* __restrict__ o_info, double* __restrict__ ent_sum) {
+    __shared__ double scratch[32];
+    const i64 c = blockIdx.z;
+    const int b = b_first + blockIdx.y;
+    const i64 row = (c * B + b) * T4;
+    const float inv = (float)(1.0 / total[c]);
+    const i64 chunk = (T4 + gridDim.x - 1) / gridDim.x;
+    const i64 t0 = (i64)blockIdx.x * chunk;
+    const i64 t1 = t0 + chunk < T4 ? t0 + chunk : T4;
+    double acc = 0.0;
+    for (i64 t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        const float4 v = p[row + t];
+        const float d0 = v.x * inv, d1 = v.y * inv, d2 = v.z * inv, d3 = v.w * inv;
+        const float i0 = -mr_fast_log2f(d0 + eps), i1 = -mr_fast_log2f(d1 + eps);
+        const float i2 = -mr_fast_log2f(d2 + eps), i3 = -mr_fast_log2f(d3 + eps);
+        o_info[row + t] = make_float4(i0, i1, i2, i3);
+        acc += (double)((d0 * i0 + d1 * i1) + (d2 * i2 + d3 * i3));
+    }
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0 && ent_sum) atomicAdd(&ent_sum[c * B + b], acc);
+}
+
 static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb, int B, float* out_power,
-                  cplx<float>* out_complex, double* band_sum, void* ws, size_t ws_bytes, cudaStream_t st) {
+                  cplx<float>* out_complex, double* band_sum, float* out_info, double* entropy_sum,
+                  double* band_sum_est, double* total_power, double eps, int phase, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+    const bool fused = out_info != nullptr;
+    if (fused && (!out_power || !band_sum || !band_sum_est || !total_power)) return QI_ERR_ARG;
+    if (!fused && phase != QI_MR_PHASE_ALL) return QI_ERR_ARG;
     MrPlan pl;
     int rc = mr_plan(C, N, hb, B, pl);
     if (rc != QI_OK) return rc;
@@ -309,11 +466,17 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
 #ifndef QI_EMUL
     cudaStreamSynchronize(st);
 #endif
-    if (band_sum) cudaMemsetAsync(band_sum, 0, sizeof(double) * (size_t)C * B, st);
+    const bool do_front = phase != QI_MR_PHASE_EXPAND;      // tables, pyramid, level convolutions, estimates
+    const bool do_back = phase != QI_MR_PHASE_ESTIMATE;     // expansion to the full rate
+    if (do_front) {
+        if (band_sum) cudaMemsetAsync(band_sum, 0, sizeof(double) * (size_t)C * B, st);
+        if (band_sum_est) cudaMemsetAsync(band_sum_est, 0, sizeof(double) * (size_t)C * B, st);
+    }
+    if (do_back && entropy_sum) cudaMemsetAsync(entropy_sum, 0, sizeof(double) * (size_t)C * B, st);
 
     // T: kernel tables (one CTA per band)
     prof_set_category(QI_CAT_FFT_FWD);
-    {
+    if (do_front) {
         const size_t smem = (size_t)4096 * 3 * sizeof(cplx<float>);
 #ifndef QI_EMUL
         cudaFuncSetAttribute(mr_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -321,7 +484,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
         QI_LAUNCH(mr_table_kernel, dim3((unsigned)B), dim3(256), smem, st, (const MrDevBand*)d_bands, N, 2047, tables);
     }
     // P: pyramid
-    for (int l = 1; l <= pl.cap; ++l) {
+    for (int l = 1; do_front && l <= pl.cap; ++l) {
         const float* src = l == 1 ? sig : pyr + pl.lvl_off[l - 1];
         const i64 src_stride = l == 1 ? stride : pl.pyr_per_chan;
         const i64 src_len = l == 1 ? N : pl.lvl_len[l - 1];
@@ -330,17 +493,29 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
                   pyr + pl.lvl_off[l], pl.pyr_per_chan, pl.lvl_len[l], taps);
     }
     // A: level convolutions (deepest first; level 0 last so its epilogue traffic is contiguous in time)
+    int level0_first = 0, level0_count = 0;
     for (const MrLevelGeom& g0 : pl.levels) {
+        if (g0.level == 0) { level0_first = g0.band_first; level0_count = g0.band_count; }
+        if (!do_front) continue;
         MrLevelGeom g = g0;
         const float* x = g.level ? pyr + pl.lvl_off[g.level] : sig;
         g.x_stride = g.level ? pl.pyr_per_chan : stride;
         const int F = 1 << g.logF;
+        prof_set_category(g.level ? QI_CAT_INV_FIRST : QI_CAT_INV_MID);
+        dim3 grid((unsigned)((g.n_blocks + g.TC - 1) / g.TC), (unsigned)C);
+        if (g.logF == 11 && g.TC == 4) {
+            const size_t smem = ((size_t)F * 4 * 2 + F) * sizeof(cplx<float>) + 256;
+#ifndef QI_EMUL
+            cudaFuncSetAttribute(mr_level4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+            QI_LAUNCH(mr_level4_kernel, grid, dim3(1024), smem, st, x, g, (const MrDevBand*)d_bands,
+                      (const cplx<float>*)tables, wbuf, out_power, out_complex, band_sum);
+            continue;
+        }
         const size_t smem = ((size_t)F * (g.TC + 1) * 2 + F) * sizeof(cplx<float>) + 256;
 #ifndef QI_EMUL
         cudaFuncSetAttribute(mr_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-        prof_set_category(g.level ? QI_CAT_INV_FIRST : QI_CAT_INV_MID);
-        dim3 grid((unsigned)((g.n_blocks + g.TC - 1) / g.TC), (unsigned)C);
         QI_LAUNCH(mr_level_kernel, grid, dim3(1024), smem, st, x, g, (const MrDevBand*)d_bands,
                   (const cplx<float>*)tables, wbuf, out_power, out_complex, band_sum);
     }
@@ -348,8 +523,10 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     MrExpandArgs ea;
     ea.bands = d_bands; ea.n_bands = B; ea.n_points = N; ea.wbuf = wbuf; ea.midbuf = midbuf;
     ea.out_power = out_power; ea.out_complex = out_complex; ea.band_sum = band_sum;
+    ea.out_info = out_info; ea.band_sum_est = band_sum_est; ea.entropy_sum = entropy_sum;
+    ea.total_power = total_power; ea.eps = (float)eps;
     // both lists are ordered deepest level first, so the bands sharing a polyphase factor 2^k are contiguous
-    auto launch_groups = [&](const std::vector<int>& list, const int* d_idx, int dst_level, i64 n_dst, bool final) {
+    auto launch_groups = [&](const std::vector<int>& list, const int* d_idx, int dst_level, i64 n_dst, int mode) {
         size_t pos = 0;
         while (pos < list.size()) {
             const int lr0 = pl.bands[list[pos]].level - dst_level;
@@ -363,18 +540,44 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
             ea.band_list = d_idx + pos;
             const i64 tile = (i64)MR_SEGQ << k;
             dim3 grid((unsigned)((n_dst + tile - 1) / tile), (unsigned)(end - pos), (unsigned)C);
-            if (final) QI_LAUNCH((mr_expand_kernel<1>), grid, dim3(256), 0, st, ea, taps);
-            else QI_LAUNCH((mr_expand_kernel<0>), grid, dim3(256), 0, st, ea, taps);
+            if (mode == MR_MODE_MID) QI_LAUNCH((mr_expand_kernel<MR_MODE_MID>), grid, dim3(256), 0, st, ea, taps);
+            else if (mode == MR_MODE_POWER) QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER>), grid, dim3(256), 0, st, ea, taps);
+            else if (mode == MR_MODE_SUMS) QI_LAUNCH((mr_expand_kernel<MR_MODE_SUMS>), grid, dim3(256), 0, st, ea, taps);
+            else QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER_INFO>), grid, dim3(256), 0, st, ea, taps);
             pos = end;
         }
     };
-    if (!pl.deep_list.empty()) {
+    if (do_front) {
         prof_set_category(QI_CAT_INV_FIRST);
-        launch_groups(pl.deep_list, d_deep, MR_LMID, (N >> MR_LMID) + 2 * MR_HALO, false);
+        if (!pl.deep_list.empty()) launch_groups(pl.deep_list, d_deep, MR_LMID, (N >> MR_LMID) + 2 * MR_HALO, MR_MODE_MID);
+        if (fused) {
+            // band-sum estimates from the level-k samples, then the per-record total that normalises the pdf
+            if (!pl.expand_list.empty()) {
+                i64 chunks = ((N >> 1) + 16383) / 16384;
+                if (chunks > 256) chunks = 256;
+                dim3 grid((unsigned)chunks, (unsigned)pl.expand_list.size(), (unsigned)C);
+                QI_LAUNCH(mr_sums_kernel, grid, dim3(256), 0, st, (const MrDevBand*)d_bands, (const int*)d_list, B, N,
+                          (const cplx<float>*)wbuf, (const cplx<float>*)midbuf, band_sum_est);
+            }
+            QI_LAUNCH(mr_total_kernel, dim3((unsigned)C), dim3(128), 0, st, (const MrDevBand*)d_bands, B,
+                      (const double*)band_sum, band_sum_est, total_power);
+        }
     }
-    if (!pl.expand_list.empty()) {
+    if (do_back) {
         prof_set_category(QI_CAT_INV_LAST);
-        launch_groups(pl.expand_list, d_list, 0, N, true);
+        if (!pl.expand_list.empty())
+            launch_groups(pl.expand_list, d_list, 0, N, fused ? MR_MODE_POWER_INFO : MR_MODE_POWER);
+        if (fused && level0_count > 0) {
+            prof_set_category(QI_CAT_INFO);
+            const i64 T4 = N / 4;
+            i64 splits = (148 * 8 * 16 + (i64)level0_count * C - 1) / ((i64)level0_count * C);
+            if (splits > (T4 + 8191) / 8192) splits = (T4 + 8191) / 8192;
+            if (splits < 1) splits = 1;
+            dim3 grid((unsigned)splits, (unsigned)level0_count, (unsigned)C);
+            QI_LAUNCH(mr_info_rows_kernel, grid, dim3(256), 0, st, reinterpret_cast<const float4*>(out_power),
+                      (const double*)total_power, B, level0_first, T4, (float)eps, reinterpret_cast<float4*>(out_info),
+                      entropy_sum);
+        }
     }
     prof_set_category(QI_CAT_OTHER);
     return check_cuda("qi_cwt_multirate");
@@ -392,11 +595,15 @@ size_t qi_cwt_multirate_workspace_bytes(int64_t C, int64_t N, const QiMrBand* ba
 }
 
 int qi_cwt_multirate(const void* sig, int64_t C, int64_t N, int64_t stride, const QiMrBand* bands, int B,
-                     void* out_power, void* out_complex, double* band_sum, void* ws, size_t ws_bytes, void* stream) {
+                     void* out_power, void* out_complex, double* band_sum, void* out_info, double* entropy_sum,
+                     double* band_sum_est, double* total_power, double eps, int phase, void* ws, size_t ws_bytes,
+                     void* stream) {
     if (!sig || !bands || !ws || C <= 0 || N <= 0 || B <= 0 || stride < N) return QI_ERR_ARG;
     if (!out_power && !out_complex && !band_sum) return QI_ERR_ARG;
+    if (phase < QI_MR_PHASE_ALL || phase > QI_MR_PHASE_EXPAND) return QI_ERR_ARG;
     return qi::mr_run(static_cast<const float*>(sig), C, N, stride, bands, B, static_cast<float*>(out_power),
-                      static_cast<qi::cplx<float>*>(out_complex), band_sum, ws, ws_bytes,
+                      static_cast<qi::cplx<float>*>(out_complex), band_sum, static_cast<float*>(out_info),
+                      entropy_sum, band_sum_est, total_power, eps, phase, ws, ws_bytes,
                       static_cast<cudaStream_t>(stream));
 }
 

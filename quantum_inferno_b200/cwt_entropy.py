@@ -76,11 +76,18 @@ def cwt_power_entropy(band_order_nth: float, sig_wf, frequency_sample_rate_hz: f
     can_mr = dt == "float32" and _plan.multirate_supported(n_points, scale)
     if method == "multirate" and not can_mr:
         raise ValueError("method='multirate' needs float32 and a record of 2^m >= 8192 points")
+    deg_free = len(freq_all) * n_points
     if method != "exact" and can_mr:
         mr_bands, _, _, _ = _plan.multirate_bands(band_order_nth, n_points, freq, frequency_sample_rate_hz,
                                                   dictionary_type)
-        res = _driver.cwt_multirate(sig, mr_bands, want_power=True, want_band_sum=True, rt=rt, out_power=out_power)
         n_trunc = int(np.count_nonzero(bands["analytic"] == 0))
+        if want_info and not (truncated_bands == "exact" and n_trunc):
+            # single fused pass: power plane, information plane, band sums and entropy sums written together
+            res = _driver.cwt_multirate(sig, mr_bands, want_power=True, want_band_sum=True, rt=rt, out_power=out_power,
+                                        want_info=True, out_info=out_info, allreduce=allreduce)
+            return CwtEntropy(freq, (b0, b1), len(freq_all), res["power"], res["info"], res["band_sum"], res["total"],
+                              res["entropy_sum"], float(np.log2(deg_free) / deg_free))
+        res = _driver.cwt_multirate(sig, mr_bands, want_power=True, want_band_sum=True, rt=rt, out_power=out_power)
         if truncated_bands == "exact" and n_trunc:
             # the truncated atoms are the lowest-frequency rows [0, n_trunc)
             sub = _driver.cwt_fft(sig, bands[:n_trunc], frequency_sample_rate_hz, dt, want_complex=False,
@@ -94,7 +101,6 @@ def cwt_power_entropy(band_order_nth: float, sig_wf, frequency_sample_rate_hz: f
     total = band_power.sum(-1)                               # [C] fp64 (tiny)
     if allreduce is not None:
         allreduce(total)
-    deg_free = len(freq_all) * n_points
     info = ent = None
     if want_info:
         sh = _driver.shannon(power, dt, 0, total, deg_free, eps=_driver.EPS64, planes=("info",), entropy_sum=True,

@@ -60,3 +60,17 @@ def test_sharded_paths_gloo(tmp_path, world, golden):
             assert abs(d["chan_entropy"][i] - rc["entropy_bits"]) < 1e-10
     assert covered[0][0] == 0 and covered[-1][1] == ref["power"].shape[0]
     assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    # fp32 multirate, band-sharded: every rank normalised with the all-reduced total estimate
+    ref3 = None
+    for rank in range(world):
+        d = np.load(tmp_path / f"mr_rank{rank}.npz")
+        if ref3 is None:
+            ref3 = orc.cwt_power_entropy(3, d["x"], 800.0)
+        b0, b1 = d["band_slice"]
+        assert abs(d["total"][0] - ref3["total"]) / ref3["total"] < 2e-5
+        p_ref = ref3["power"][b0:b1]
+        assert np.linalg.norm(d["power"][0] - p_ref) / np.linalg.norm(p_ref) < 1e-4
+        strong = p_ref > 1e-2 * ref3["power"].max()
+        strong[:max(0, 2 - b0)] = False              # the record-long atoms of the two lowest bands
+        assert np.max(np.abs(d["info"][0] - ref3["info"][b0:b1])[strong]) < 1e-3
+        assert abs(d["entropy_all"][0] - ref3["entropy_bits"]) < 1e-3

@@ -227,7 +227,7 @@ def test_multirate_properties_north_star_size(torch_cuda):
     assert tuple(a.power.shape) == (1, 60, n)
     assert torch.allclose(a.power.double().sum(-1), a.band_power, rtol=1e-5)
     pdf_sum = (a.power.double() / a.total_power[:, None, None]).sum()
-    assert abs(float(pdf_sum) - 1.0) < 1e-6
+    assert abs(float(pdf_sum) - 1.0) < 2e-6
     pa = a.power[0].clone()
     ent_a = float(a.entropy_bits()[0])
     del a
@@ -271,7 +271,7 @@ def test_cwt_properties_large(torch_cuda):
     # band sums == sums of the plane; pdf sums to one; entropy bounded by log2(D)
     assert torch.allclose(r.power.double().sum(-1), r.band_power, rtol=1e-6)
     pdf_sum = (r.power.double() / r.total_power[:, None, None]).sum((1, 2))
-    assert torch.allclose(pdf_sum, torch.ones_like(pdf_sum), atol=1e-9)
+    assert torch.allclose(pdf_sum, torch.ones_like(pdf_sum), atol=2e-6)      # S is the pre-pass estimate (~1e-6)
     ent = r.entropy_bits()
     assert bool(((ent > 0) & (ent < np.log2(48 * n))).all())
     # info plane == -log2(P/S + eps) recomputed with torch in fp64
@@ -287,7 +287,7 @@ def test_cwt_properties_large(torch_cuda):
         part = cwt_entropy.cwt_power_entropy(3, x[:1], FS, dtype="float32", band_slice=sl, want_info=False)
         tot += part.total_power
         parts.append(part)
-    assert abs(float(tot[0]) - float(r.total_power[0])) / float(r.total_power[0]) < 1e-9
+    assert abs(float(tot[0]) - float(r.total_power[0])) / float(r.total_power[0]) < 2e-6
     # oracle on a slab: first band rows against the CPU restatement of one band
     from oracle import qi_oracle as orc
     xf = np.fft.fft(x[0].cpu().numpy(), 2 * n)
