@@ -31,29 +31,47 @@ QI_DEV void tc4_stage(cplx<float>* __restrict__ tile, const cplx<float>* __restr
         const int u = task >> 2;
         const int j = u & (H - 1);
         const int base = ((u >> LOGH) << LOGB) + j;
+        // slot of element i of this butterfly (row base + i*H), with the swizzle folded per stage geometry:
+        //   H >= 16 : i*H does not touch the 4 low row bits -> one swizzle, compile-time offsets
+        //   H == 1  : rows 4g + i share s = g & 3
+        //   else    : generic
+        int slot[Q];
+        if constexpr (H >= 16) {
+            const int s0 = sw4(base, c);
+#pragma unroll
+            for (int i = 0; i < Q; ++i) slot[i] = s0 + i * (H << 2);
+        } else if constexpr (H == 1 && Q == 4) {
+            const int s = (base >> 2) & 3;
+            const int b4 = ((base >> 2) << 4) | (c ^ s);
+#pragma unroll
+            for (int i = 0; i < Q; ++i) slot[i] = b4 + ((i ^ s) << 2);
+        } else {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) slot[i] = sw4(base + i * H, c);
+        }
         cplx<float> a[Q];
         if (DIR == FFT_FWD) {
 #pragma unroll
-            for (int i = 0; i < Q; ++i) a[i] = tile[sw4(base + i * H, c)];
+            for (int i = 0; i < Q; ++i) a[i] = tile[slot[i]];
             if (STEP == 3) dif8<float, DIR>(a); else if (STEP == 2) dif4<float, DIR>(a); else dif2<float, DIR>(a);
 #pragma unroll
             for (int s = 0; s < Q; ++s) {
                 const int f = STEP == 3 ? brev3(s) : (STEP == 2 ? brev2(s) : s);
                 cplx<float> v = a[s];
                 if (f != 0) v = v * tw[(j * f) << TWSHIFT];
-                tile[sw4(base + s * H, c)] = v;
+                tile[slot[s]] = v;
             }
         } else {
 #pragma unroll
             for (int s = 0; s < Q; ++s) {
                 const int f = STEP == 3 ? brev3(s) : (STEP == 2 ? brev2(s) : s);
-                cplx<float> v = tile[sw4(base + s * H, c)];
+                cplx<float> v = tile[slot[s]];
                 if (f != 0) v = mul_conj(v, tw[(j * f) << TWSHIFT]);
                 a[s] = v;
             }
             if (STEP == 3) dit8<float, DIR>(a); else if (STEP == 2) dit4<float, DIR>(a); else dit2<float, DIR>(a);
 #pragma unroll
-            for (int i = 0; i < Q; ++i) tile[sw4(base + i * H, c)] = a[i];
+            for (int i = 0; i < Q; ++i) tile[slot[i]] = a[i];
         }
     }
 }

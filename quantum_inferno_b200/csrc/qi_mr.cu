@@ -441,7 +441,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
                   double* band_sum_est, double* total_power, double eps, int phase, void* ws, size_t ws_bytes,
                   cudaStream_t st) {
     const bool fused = out_info != nullptr;
-    if (fused && (!out_power || !band_sum || !band_sum_est || !total_power)) return QI_ERR_ARG;
+    if (fused && (!out_power || !band_sum || !band_sum_est || !total_power || out_complex)) return QI_ERR_ARG;
     if (!fused && phase != QI_MR_PHASE_ALL) return QI_ERR_ARG;
     MrPlan pl;
     int rc = mr_plan(C, N, hb, B, pl);

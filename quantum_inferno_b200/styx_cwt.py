@@ -9,6 +9,8 @@ tensors out, left on the device.  Keyword-only extras that do not exist upstream
     dtype     'float64' (default) or 'float32' -- arithmetic and output precision
     spectrum  'auto' | 'analytic' | 'table'    -- how each band's frequency response is obtained
     outputs   'complex' (default) | 'power' | 'both'
+    method    'exact' (default: record FFT + per-band inverse FFT) | 'multirate' (float32 only, 2^m >= 8192 points:
+              the decimation-pyramid fast path, complex TFR within ~3e-6 of the plane maximum)
 
 2-D input [channels, points] is an extension: the reference applied to every row.
 """
@@ -90,7 +92,8 @@ def wavelet_centered_4cwt(band_order_nth: float, duration_points: int,
 
 def cwt_complex_any_scale_pow2(band_order_nth: float, sig_wf, frequency_sample_rate_hz: float,
                                cwt_type: str = "fft", dictionary_type: str = "norm", *,
-                               dtype=None, spectrum: str = "auto", outputs: str = "complex"):
+                               dtype=None, spectrum: str = "auto", outputs: str = "complex",
+                               method: str = "exact"):
     """CWT of ``sig_wf`` with the order-N Gabor dictionary (reference styx_cwt.py:147-198):
     linear 'same' convolution with every atom, band centres from
     ``scales_dyadic.log_frequency_hz_from_fft_points`` (base G3).
@@ -108,10 +111,20 @@ def cwt_complex_any_scale_pow2(band_order_nth: float, sig_wf, frequency_sample_r
     frequency_cwt_hz = scales.log_frequency_hz_from_fft_points(
         frequency_sample_hz=frequency_sample_rate_hz, fft_points=n_points, scale_order=band_order_nth)
     time_cwt_s = np.arange(n_points) / frequency_sample_rate_hz
-    bands, _, _, _ = _plan.gabor_bands(band_order_nth, n_points, frequency_cwt_hz, frequency_sample_rate_hz,
-                                       dictionary_type, dt, spectrum)
-    res = _driver.cwt_fft(sig, bands, frequency_sample_rate_hz, dt, want_complex=outputs in ("complex", "both"),
-                          want_power=outputs in ("power", "both"), rt=rt)
+    bands, scale, _, _ = _plan.gabor_bands(band_order_nth, n_points, frequency_cwt_hz, frequency_sample_rate_hz,
+                                           dictionary_type, dt, spectrum)
+    if method not in ("exact", "multirate"):
+        raise ValueError("method must be 'exact' or 'multirate'")
+    if method == "multirate":
+        if dt != "float32" or not _plan.multirate_supported(n_points, scale):
+            raise ValueError("method='multirate' needs dtype='float32' and a record of 2^m >= 8192 points")
+        mr_bands, _, _, _ = _plan.multirate_bands(band_order_nth, n_points, frequency_cwt_hz,
+                                                  frequency_sample_rate_hz, dictionary_type)
+        res = _driver.cwt_multirate(sig, mr_bands, want_power=outputs in ("power", "both"),
+                                    want_complex=outputs in ("complex", "both"), rt=rt)
+    else:
+        res = _driver.cwt_fft(sig, bands, frequency_sample_rate_hz, dt, want_complex=outputs in ("complex", "both"),
+                              want_power=outputs in ("power", "both"), rt=rt)
 
     def shape(buf):
         if buf is None:

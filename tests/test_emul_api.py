@@ -184,6 +184,21 @@ def test_multirate_fused_path(order, logn):
         assert per_band_x.max() < 1e-4                   # ...removed by truncated_bands='exact'
 
 
+def test_multirate_complex_output():
+    """styx_cwt(dtype=float32, method='multirate'): complex TFR from the fast path."""
+    from oracle import qi_oracle as orc
+    x = _synth(8192, 4)
+    fr, tr, cr = orc.cwt_complex_any_scale_pow2(3, x, FS)
+    f, t, c = styx_cwt.cwt_complex_any_scale_pow2(3, x, FS, dtype="float32", method="multirate")
+    assert c.dtype == np.complex64 and np.array_equal(f, fr)
+    assert np.max(np.abs(c - cr)) / np.max(np.abs(cr)) < 5e-5
+    assert np.linalg.norm(np.abs(c) ** 2 - np.abs(cr) ** 2) / np.linalg.norm(np.abs(cr) ** 2) < 2e-5
+    f, t, (c2, p2) = styx_cwt.cwt_complex_any_scale_pow2(3, x, FS, dtype="float32", method="multirate", outputs="both")
+    assert np.array_equal(c2, c) and np.allclose(p2, np.abs(c) ** 2, rtol=1e-5)
+    with pytest.raises(ValueError):
+        styx_cwt.cwt_complex_any_scale_pow2(3, x, FS, method="multirate")          # float64 default
+
+
 def test_multirate_method_selection():
     from quantum_inferno_b200 import cwt_entropy
     x = _synth(8192)
