@@ -40,11 +40,44 @@ class CwtEntropy:
         return self.band_entropy_bits.sum(-1)
 
 
+def _host_pipelined(rt, band_order_nth, sig_wf, fs, dictionary_type, dt, host_chunks, kwargs, out_power, out_info):
+    """Channel groups of a host-resident batch: H2D of group k+1 (copy stream) overlaps the kernels of group k."""
+    torch = rt.torch
+    x = sig_wf if isinstance(sig_wf, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(sig_wf))
+    n_chan, n_points = int(x.shape[0]), int(x.shape[1])
+    freq_all = scales.log_frequency_hz_from_fft_points(frequency_sample_hz=fs, fft_points=n_points,
+                                                       scale_order=band_order_nth)
+    bsl = kwargs["band_slice"]
+    n_bands = len(freq_all) if bsl is None else int(bsl[1]) - int(bsl[0])
+    if out_power is None:
+        out_power = rt.empty((n_chan, n_bands, n_points), dt)
+    if kwargs["want_info"] and out_info is None:
+        out_info = rt.empty((n_chan, n_bands, n_points), dt)
+    main = torch.cuda.current_stream(rt.device)
+    copy_stream = torch.cuda.Stream(device=rt.device)
+    bounds = np.linspace(0, n_chan, min(int(host_chunks), n_chan) + 1).astype(int)
+    parts = []
+    for c0, c1 in zip(bounds[:-1], bounds[1:]):
+        with torch.cuda.stream(copy_stream):
+            xd = x[c0:c1].to(device=rt.device, dtype=getattr(torch, dt), non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        main.wait_event(ready)
+        xd.record_stream(main)
+        parts.append(cwt_power_entropy(band_order_nth, xd, fs, dictionary_type, dtype=dt, out_power=out_power[c0:c1],
+                                       out_info=None if out_info is None else out_info[c0:c1], **kwargs))
+    first = parts[0]
+    ent = None if first.band_entropy_bits is None else torch.cat([p.band_entropy_bits for p in parts])
+    return CwtEntropy(first.frequency_hz, first.band_slice, first.n_bands_total, out_power, out_info,
+                      torch.cat([p.band_power for p in parts]), torch.cat([p.total_power for p in parts]), ent,
+                      first.ref_bits)
+
+
 def cwt_power_entropy(band_order_nth: float, sig_wf, frequency_sample_rate_hz: float, dictionary_type: str = "norm",
                       *, dtype="float32", spectrum: str = "auto", band_slice: Optional[tuple] = None,
                       allreduce: Optional[Callable] = None, want_info: bool = True,
                       out_power=None, out_info=None, method: str = "auto",
-                      truncated_bands: str = "multirate") -> CwtEntropy:
+                      truncated_bands: str = "multirate", host_chunks: int = 1) -> CwtEntropy:
     """Power, information and entropy of the order-N Gabor CWT of ``sig_wf`` ([N] or [C, N]; numpy or CUDA tensor).
 
     band_slice : (b0, b1) computes only bands b0..b1-1 of the standard table (band sharding of one long record).
@@ -58,9 +91,17 @@ def cwt_power_entropy(band_order_nth: float, sig_wf, frequency_sample_rate_hz: f
                  (N/s < 10).  'multirate' keeps them on the fast path (whole-plane power L2 ~ 2e-6, but the
                  out-of-band leakage the reference's hard truncation lets into those 2-4 bands, ~1e-3 of their
                  peak, is not reproduced); 'exact' recomputes exactly those bands with the exact method.
+    host_chunks : for records that live in host memory ([C, N] numpy / CPU tensor, ideally pinned): process the
+                 channels in this many groups, copying group k+1 to the device on a second stream while group k is
+                 being transformed (channels are independent, so the result is identical).
     """
     rt = get_runtime()
     dt = dtype_name(dtype, default="float32")
+    if host_chunks > 1 and getattr(rt, "name", "") == "cuda" and not getattr(sig_wf, "is_cuda", False) \
+            and np.ndim(sig_wf) == 2 and np.shape(sig_wf)[0] > 1 and allreduce is None:
+        return _host_pipelined(rt, band_order_nth, sig_wf, frequency_sample_rate_hz, dictionary_type, dt, host_chunks,
+                               dict(spectrum=spectrum, band_slice=band_slice, want_info=want_info, method=method,
+                                    truncated_bands=truncated_bands), out_power, out_info)
     sig, _ = _driver._as_2d(rt, sig_wf, dt)
     n_points = int(sig.shape[1])
     freq_all = scales.log_frequency_hz_from_fft_points(
