@@ -138,6 +138,10 @@ def main():
                     ("fft_o6", dict(cwt_type="fft", band_order_nth=6))]:
         c, cb, t, f = cwt_atoms.cwt_chirp_from_sig(x1024, FS, **kw)
         d[f"{tag}_c"], d[f"{tag}_bits"], d[f"{tag}_f"] = c, cb, f
+    d["spec"], d["spec_f"] = cwt_atoms.chirp_spectrum(np.linspace(0.0, 400.0, 64), 0.1, 3, 50.0, FS, 1.0)
+    d["spec_c"], d["spec_c_f"] = cwt_atoms.chirp_spectrum_centered(6, 80.0, FS, -1.0, scales_dyadic.Slice.G3)
+    d["mqg"] = np.array([cwt_atoms.chirp_mqg_from_n(n_, s_, b_) for n_, s_, b_ in
+                         [(3, 0, 2.0), (12, 1.0, 2.0), (6, -1.0, scales_dyadic.Slice.G3), (1, 0, 2.0)]])
     np.savez_compressed(os.path.join(OUT, "atoms.npz"), **d)
 
     # ---------------------------------------------------------------- tfr_info

@@ -31,6 +31,38 @@ def chirp_mqg_from_n(band_order_nth: float, index_shift: float = 0, scale_base: 
     return 2 * quality_factor_q * gamma, quality_factor_q, gamma
 
 
+def chirp_spectrum(frequency_hz: np.ndarray, offset_time_s: float, band_order_nth: float, frequency_center_hz: float,
+                   frequency_sample_rate_hz: float, index_shift: float = 0, scale_base: float = scales.Slice.G2):
+    """Closed-form spectrum of the quantum chirp on a frequency axis (reference cwt_atoms.py:53-92; host float64).
+
+    :return: spectrum (complex), frequency shifted by the band centre [Hz]
+    """
+    cycles_m, _, gamma = chirp_mqg_from_n(band_order_nth, index_shift, scale_base)
+    scale_atom = chirp_scale(cycles_m, frequency_center_hz, frequency_sample_rate_hz)
+    p_complex = chirp_p_complex(scale_atom, gamma, index_shift)
+    omega_centre = 2 * np.pi * frequency_center_hz / frequency_sample_rate_hz
+    omega = 2 * np.pi * frequency_hz / frequency_sample_rate_hz
+    omega_shifted = omega - omega_centre
+    envelope = np.exp(-(1.0 / (4 * p_complex)) * (omega_shifted ** 2))
+    spectrum = np.sqrt(p_complex / np.abs(p_complex)) * envelope * np.exp(-1j * 2 * np.pi * frequency_hz * offset_time_s)
+    return spectrum, omega_shifted * frequency_sample_rate_hz / (2 * np.pi)
+
+
+def chirp_spectrum_centered(band_order_nth: float, scale_frequency_center_hz: float, frequency_sample_rate_hz: float,
+                            index_shift: float = 0, scale_base: float = scales.Slice.G2):
+    """Same spectrum on the fixed grid [-pi, pi) in steps of pi/128 about the band centre
+    (reference cwt_atoms.py:95-119).
+
+    :return: spectrum (complex), shifted frequency [Hz]
+    """
+    cycles_m, _, gamma = chirp_mqg_from_n(band_order_nth, index_shift, scale_base)
+    scale_atom = chirp_scale(cycles_m, scale_frequency_center_hz, frequency_sample_rate_hz)
+    p_complex = chirp_p_complex(scale_atom, gamma, index_shift)
+    omega_shifted = np.arange(-np.pi, np.pi, np.pi / 2 ** 7)
+    spectrum = np.sqrt(p_complex / np.abs(p_complex)) * np.exp(-(omega_shifted ** 2) / (4 * p_complex))
+    return spectrum, omega_shifted * frequency_sample_rate_hz / (2 * np.pi)
+
+
 def chirp_scale(cycles_m: float, scale_frequency_center_hz: Union[np.ndarray, float],
                 frequency_sample_rate_hz: float) -> float:
     """Non-dimensional atom scale M*fs/(2*pi*fc) (reference cwt_atoms.py:147-158)."""

@@ -95,6 +95,23 @@ def test_gabor_band_plan():
     assert np.array_equal(_plan.gabor_bands(3, 2 ** 16, f, 800.0, "anything")[3], a_norm)   # silent 'norm' fallback
 
 
+def test_chirp_host_helpers(golden):
+    """Scalar / closed-form helpers of cwt_atoms stay on the host and are bit-exact with the reference."""
+    from quantum_inferno_b200 import cwt_atoms
+    g = golden("atoms")
+    cases = [(3, 0, 2.0), (12, 1.0, 2.0), (6, -1.0, sc.Slice.G3), (1, 0, 2.0)]
+    assert np.array_equal(np.array([cwt_atoms.chirp_mqg_from_n(*c) for c in cases]), g["mqg"])
+    s, f = cwt_atoms.chirp_spectrum(np.linspace(0.0, 400.0, 64), 0.1, 3, 50.0, 800.0, 1.0)
+    assert np.array_equal(s, g["spec"]) and np.array_equal(f, g["spec_f"])
+    s, f = cwt_atoms.chirp_spectrum_centered(6, 80.0, 800.0, -1.0, sc.Slice.G3)
+    assert np.array_equal(s, g["spec_c"]) and np.array_equal(f, g["spec_c_f"])
+    m, q, gam = cwt_atoms.chirp_mqg_from_n(3)
+    assert abs(m - 7.1907) < 1e-4                       # SURVEY 3.5: M(3) = 7.1907, not 0.75*pi*3
+    assert cwt_atoms.chirp_scale(m, 10.0, 800.0) == m * 800.0 / 10.0 / (2.0 * np.pi)
+    t_s, f_hz = cwt_atoms.chirp_scales_from_duration(3, 10.24)
+    assert t_s == 10.24 / m and f_hz == 1 / t_s
+
+
 def test_utilities():
     assert rescaling.is_power_of_two(1024) and not rescaling.is_power_of_two(1000) and not rescaling.is_power_of_two(0)
     assert rescaling.to_log2_with_epsilon(1.0) == np.log2(1.0 + np.finfo(np.float64).eps)

@@ -1,0 +1,109 @@
+"""
+Secondary measurements for the other BASELINE.json configs (the headline line is bench.py).  One GPU, the per-GPU
+share of each config, CUDA-event timing, inputs resident in HBM, 3 warm-ups.  Prints one JSON object per config.
+
+    python tools/bench_configs.py [cfg1 cfg2 cfg3 cfg4 cfg5]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+from bench import FS, synth_batch_torch  # noqa: E402
+from quantum_inferno_b200 import cwt_entropy, styx_cwt, styx_fft, styx_stx  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+
+
+def timed(fn, reps=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+def cfg1():
+    """single channel 2^16 @ 800 Hz, order 3 CWT + power/entropy: the drop-in fp64 API and the fused fp32 path."""
+    x = synth_batch_torch(torch, 1 << 16, [0], DEV)[0]
+    x64 = x.double()
+    ms64, (f, t, c) = timed(lambda: styx_cwt.cwt_complex_any_scale_pow2(3, x64, FS))
+    ms32, r = timed(lambda: cwt_entropy.cwt_power_entropy(3, x, FS, dtype="float32"))
+    cells = c.shape[-2] * c.shape[-1]
+    return {"config": "cfg1: 1 x 2^16, N=3 CWT", "bands": int(c.shape[-2]),
+            "fp64_complex_tfr_ms": ms64, "fp64_cells_per_s": cells / ms64 * 1e3,
+            "fp32_fused_power_info_entropy_ms": ms32, "fp32_cells_per_s": cells / ms32 * 1e3}
+
+
+def cfg2():
+    """STFT Hann 1024 / 50 % on 64 x 2^20 (fp32 and fp64)."""
+    x = synth_batch_torch(torch, 1 << 20, list(range(64)), DEV)
+    out = {"config": "cfg2: STFT Hann 1024/512, 64 x 2^20"}
+    for dt, xx in (("float32", x), ("float64", x.double())):
+        ms, (f, t, z) = timed(lambda: styx_fft.stft_complex_pow2(xx, FS, 1024, alpha=1.0, dtype=dt))
+        cells = z.shape[0] * z.shape[1] * z.shape[2]
+        bytes_alg = cells * (8 if dt == "float32" else 16) + xx.numel() * xx.element_size()
+        out[dt] = {"ms": ms, "cells_per_s": cells / ms * 1e3, "samples_per_s": x.numel() / ms * 1e3,
+                   "alg_GBps": bytes_alg / ms / 1e6, "shape": list(z.shape)}
+    return out
+
+
+def cfg3():
+    """Stockwell on 16 x 2^18, orders 3/6/12, fp32 and fp64."""
+    x = synth_batch_torch(torch, 1 << 18, list(range(16)), DEV)
+    out = {"config": "cfg3: STX 16 x 2^18"}
+    for order in (3, 6, 12):
+        for dt, xx in (("float32", x), ("float64", x.double())):
+            if order == 12 and dt == "float64":
+                xx = xx[:8]                                   # 143 bands x 2^18 complex128 x 16 ch = 9.6 GB + workspace
+            ms, (f, t, z) = timed(lambda: styx_stx.stx_complex_any_scale_pow2(order, xx, FS, dtype=dt), reps=3)
+            cells = z.shape[0] * z.shape[1] * z.shape[2]
+            out[f"order{order}_{dt}"] = {"ms": ms, "cells_per_s": cells / ms * 1e3, "bands": int(z.shape[1]),
+                                          "channels": int(z.shape[0])}
+            del z
+            torch.cuda.empty_cache()
+    return out
+
+
+def cfg4():
+    """order 6 CWT + info/entropy, 256 ch x 2^22 over 8 GPUs -> the per-GPU share: 32 ch x 2^22 (102 bands), in 4 groups."""
+    n, ch = 1 << 22, 8
+    x = synth_batch_torch(torch, n, list(range(ch)), DEV)
+    ms, r = timed(lambda: cwt_entropy.cwt_power_entropy(6, x, FS, dtype="float32"), reps=3)
+    cells = ch * r.power.shape[1] * n
+    return {"config": "cfg4 share: N=6 CWT + info/entropy, 8 of the 32 ch/GPU x 2^22 per call", "bands": int(r.power.shape[1]),
+            "ms_per_8ch": ms, "cells_per_s": cells / ms * 1e3, "ms_per_gpu_share_32ch": 4 * ms}
+
+
+def cfg5():
+    """N=12 CWT of one 2^28 record, band-sharded over 8 GPUs -> this GPU's 33-band share (planes 8 x 2^28 x 33 B)."""
+    n = 1 << 28
+    x = synth_batch_torch(torch, n, [0], DEV)[0]
+    nb = 263
+    sl = (0, 33)
+    tot = torch.zeros(1, dtype=torch.float64, device=DEV)
+    ms, r = timed(lambda: cwt_entropy.cwt_power_entropy(12, x, FS, dtype="float32", band_slice=sl,
+                                                        allreduce=lambda t: t), reps=2, warm=1)
+    cells = (sl[1] - sl[0]) * n
+    return {"config": "cfg5 share: N=12 CWT, 1 x 2^28, bands 0..32 of 263 (lowest = deepest levels)", "ms": ms,
+            "cells_per_s": cells / ms * 1e3}
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["cfg1", "cfg2", "cfg3", "cfg4"]
+    for name in which:
+        t0 = time.time()
+        res = globals()[name]()
+        res["wall_s"] = time.time() - t0
+        print(json.dumps(res), flush=True)
+        torch.cuda.empty_cache()
