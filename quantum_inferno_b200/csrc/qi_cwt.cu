@@ -32,6 +32,17 @@ struct DevBand {
 
 // ---------------------------------------------------------------- on-the-fly Gabor response
 template <typename T>
+QI_DEV bool gabor_response_negligible(const DevBand& b, i64 k, int logL) {
+    // distance (in bins) to the nearest alias of the band centre; beyond ~9.5 sigma (fp32: 6.3) the response is
+    // below 3e-20 (2e-9) of its peak and the whole product is skipped -- spectrum load, exps and twiddle included
+    const T Lf = (T)(1ll << logL);
+    T dk = (T)(k - b.kappa_int) - (T)b.kappa_frac;
+    dk -= Lf * rint(dk / Lf);
+    const T u = (T)b.g * dk;
+    return (T)0.5 * u * u > (sizeof(T) == 8 ? (T)45.0 : (T)20.0);
+}
+
+template <typename T>
 QI_DEV cplx<T> gabor_response(const DevBand& b, i64 k, int logL, int half_shift) {
     const T g = (T)b.g;
     const T dk = (T)(k - b.kappa_int) - (T)b.kappa_frac;
@@ -97,6 +108,8 @@ template <typename T> struct SrcCwtSpec {
     QI_DEV cplx<T> load(i64 batch, i64 e) const {
         const i64 chan = batch % geo.n_channels;
         const DevBand& b = bands[band0 + (int)(batch / geo.n_channels)];
+        if (b.table_off < 0 && gabor_response_negligible<T>(b, (i64)brev_bits((unsigned)e, geo.logL), geo.logL))
+            return mk<T>((T)0, (T)0);
         const cplx<T> X = spec[(chan << geo.logL) + e];
         if (b.table_off >= 0) {
             cplx<T> H = tables[b.table_off + e];

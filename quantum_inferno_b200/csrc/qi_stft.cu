@@ -19,7 +19,7 @@ struct StftGeom {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g, cplx<T>* __restrict__ out,
             double* __restrict__ psd_acc) {
     QI_DYN_SMEM(smem_raw);
@@ -112,10 +112,12 @@ static int stft_impl(const void* sig, i64 C, i64 n_points, i64 stride, const voi
     int logF = 0;
     while ((1 << logF) < nfft) ++logF;
     if ((1 << logF) != nfft) return QI_ERR_ARG;
-    const size_t budget = 200 * 1024;
+    // <= ~100 KB per CTA so that two CTAs (2 x 512 threads) share an SM; fall back to one big CTA for long FFTs
+    size_t budget = 100 * 1024;
     int TC = 16;
     auto need = [&](int tc) { return ((size_t)nfft * (tc + 2)) * sizeof(cplx<T>) + 2 * tc * sizeof(T) + 64; };
-    while (TC > 1 && need(TC) > budget) TC >>= 1;
+    while (TC > 2 && need(TC) > budget) TC >>= 1;
+    if (need(TC) > budget) { budget = 200 * 1024; while (TC > 1 && need(TC) > budget) TC >>= 1; }
     if (need(TC) > budget) return QI_ERR_UNSUPPORTED;
     // the psd reduction uses shuffles across the TC lanes of one k: needs TC | 32 (true: power of two <= 16)
     StftGeom g;
@@ -130,7 +132,7 @@ static int stft_impl(const void* sig, i64 C, i64 n_points, i64 stride, const voi
 #endif
     if (psd_acc) cudaMemsetAsync(psd_acc, 0, sizeof(double) * (size_t)C * (nfft / 2 + 1), st);
     prof_set_category(QI_CAT_STFT);
-    QI_LAUNCH((stft_kernel<T>), grid, dim3(256), smem, st, static_cast<const T*>(sig), static_cast<const T*>(window),
+    QI_LAUNCH((stft_kernel<T>), grid, dim3(512), smem, st, static_cast<const T*>(sig), static_cast<const T*>(window),
               g, static_cast<cplx<T>*>(out), psd_acc);
     return check_cuda("qi_stft");
 }

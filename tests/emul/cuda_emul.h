@@ -195,7 +195,7 @@ static inline double __longlong_as_double(long long v) { double d; std::memcpy(&
 static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
-using std::exp; using std::log2; using std::hypot; using std::sqrt; using std::fabs; using std::fma; using std::floor;
+using std::exp; using std::log2; using std::hypot; using std::rint; using std::sqrt; using std::fabs; using std::fma; using std::floor;
 using std::min; using std::max;
 
 #define QI_EMUL_DYN_SMEM (qi_emul::cur->blk->smem)
