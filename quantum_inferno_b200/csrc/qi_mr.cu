@@ -25,7 +25,7 @@
 #include "qi_tfr.cuh"
 #include "qi_halfband_coeffs.h"
 #include "qi_mr_expand.cuh"
-#include "qi_fft_tc4.cuh"
+#include "qi_mr_level2k.cuh"
 
 #include <vector>
 #include <math.h>
@@ -87,20 +87,9 @@ mr_table_kernel(const MrDevBand* __restrict__ bands, i64 n_points, int half_w_ca
     for (int p = threadIdx.x; p < F; p += blockDim.x) tables[b.table_off + p] = tile[p * 2] * inv;
 }
 
-// ---------------------------------------------------------------- A: overlap-save level convolution
-struct MrLevelGeom {
-    int level, logF, TC;
-    int band_first, band_count, n_bands;
-    int wk;                 // two-sided kernel support reserved per block (even); valid outputs per block V = F - wk
-    i64 n_points;           // N
-    i64 n_level;            // N >> level
-    i64 q_first;            // first output index (level rate): -MR_HALO for level >= 1, 0 for level 0
-    i64 n_out;              // outputs per channel at this level
-    i64 n_blocks;
-    i64 x_stride, x_len;    // level signal: per-channel stride, stored length
-    int x_halo;             // halo of the stored level signal (0 for level 0)
-};
-
+// ---------------------------------------------------------------- A: overlap-save level convolution (generic)
+// Any block length / one block per column; used for the deepest level (one 4096-point block holds the whole level)
+// and for levels whose kernels need 4096-point blocks.  The 2048-point fast path is qi_mr_level2k.cuh.
 __global__ void __launch_bounds__(1024)
 mr_level_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __restrict__ bands,
                 const cplx<float>* __restrict__ tables, cplx<float>* __restrict__ wbuf,
@@ -177,83 +166,6 @@ mr_level_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __r
     }
 }
 
-// ---------------------------------------------------------------- A': the same for 2048-point blocks, 4 per CTA
-// Compile-time geometry + XOR-swizzled tile (qi_fft_tc4.cuh): every shared-memory access of the kernel is bank
-// conflict free.  Used for every level except the deepest (whose single 4096-point block goes through the
-// generic kernel above).
-__global__ void __launch_bounds__(1024)
-mr_level4_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __restrict__ bands,
-                 const cplx<float>* __restrict__ tables, cplx<float>* __restrict__ wbuf,
-                 float* __restrict__ out_power, cplx<float>* __restrict__ out_complex, double* __restrict__ band_sum) {
-    constexpr int LOGF = 11, F = 1 << LOGF, TC = 4;
-    QI_DYN_SMEM(smem_raw);
-    cplx<float>* tile_x = reinterpret_cast<cplx<float>*>(smem_raw);
-    cplx<float>* tile_y = tile_x + F * TC;
-    cplx<float>* tw = tile_y + F * TC;
-    double* scratch = reinterpret_cast<double*>(tw + F);
-    const i64 chan = blockIdx.y;
-    const i64 blk0 = (i64)blockIdx.x * TC;
-    const int V = F - g.wk;
-    const int half = g.wk / 2;
-    const float* xs = x + chan * g.x_stride;
-
-    fill_twiddles<float>(tw, LOGF);
-    for (int idx = threadIdx.x; idx < F * TC; idx += blockDim.x) {
-        const int p = idx & (F - 1);                 // lanes along the samples -> coalesced global loads
-        const int c = idx >> LOGF;
-        const i64 blk = blk0 + c;
-        float v = 0.0f;
-        if (blk < g.n_blocks) {
-            const i64 k = g.q_first + blk * V - half + p + g.x_halo;
-            if (k >= 0 && k < g.x_len) v = xs[k];
-        }
-        tile_x[sw4(p, c)] = mk<float>(v, 0.0f);
-    }
-    __syncthreads();
-    tc4_fft_fwd<LOGF>(tile_x, tw);
-
-    for (int bi = 0; bi < g.band_count; ++bi) {
-        const int b = g.band_first + bi;
-        const MrDevBand band = bands[b];
-        const cplx<float>* K = tables + band.table_off;
-        // slots are visited linearly: slot -> (row, column) is only needed for the table index
-        for (int slot = threadIdx.x; slot < F * TC; slot += blockDim.x) {
-            const int rs = slot >> 2;                                  // r ^ s with s = (r >> 2) & 3 = (rs >> 2) & 3
-            const int r = rs ^ ((rs >> 2) & 3);
-            tile_y[slot] = tile_x[slot] * K[r];
-        }
-        __syncthreads();
-        tc4_fft_inv<LOGF>(tile_y, tw);
-        float acc_f = 0.0f;
-        for (int c = 0; c < TC; ++c) {
-            const i64 blk = blk0 + c;
-            if (blk >= g.n_blocks) break;
-            const i64 o0 = blk * V;
-            if (g.level == 0) {
-                const i64 cell0 = (chan * g.n_bands + b) * g.n_points + o0;
-                for (int pv = threadIdx.x; pv < V; pv += blockDim.x) {
-                    if (o0 + pv < g.n_out) {
-                        const cplx<float> y = tile_y[sw4(pv + half, c)];
-                        const float pw = norm2(y);
-                        if (out_power) out_power[cell0 + pv] = pw;
-                        if (out_complex) out_complex[cell0 + pv] = y;
-                        acc_f += pw;
-                    }
-                }
-            } else {
-                cplx<float>* wdst = wbuf + band.w_off + chan * band.w_stride + o0;
-                for (int pv = threadIdx.x; pv < V; pv += blockDim.x)
-                    if (o0 + pv < g.n_out) wdst[pv] = tile_y[sw4(pv + half, c)];
-            }
-        }
-        if (g.level == 0 && band_sum) {
-            const double acc = block_sum((double)acc_f, scratch);
-            if (threadIdx.x == 0) atomicAdd(&band_sum[chan * g.n_bands + b], acc);
-        }
-        __syncthreads();
-    }
-}
-
 // ---------------------------------------------------------------- host driver
 struct MrPlan {
     int cap;                         // deepest level
@@ -262,7 +174,7 @@ struct MrPlan {
     std::vector<int> expand_list;       // bands with level >= 1 (final expand launch)
     std::vector<int> deep_list;         // bands with level > MR_LMID (first brought to level MR_LMID)
     std::vector<MrLevelGeom> levels;
-    size_t off_bands, off_list, off_deep, off_pyr, off_tables, off_w, off_mid, total;
+    size_t off_bands, off_list, off_deep, off_tw, off_pyr, off_tables, off_w, off_mid, total;
     i64 pyr_per_chan, w_total, mid_total;
 };
 
@@ -321,12 +233,13 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl) {
             g.logF = 12;
             if ((1 << g.logF) - g.wk < g.n_out) return QI_ERR_UNSUPPORTED;
         } else {
-            int half = (int)ceil(5.2 * smax) + 1;
+            // half a multiple of 16 -> V a multiple of 32: every plane store of the 2048-point kernel is sector aligned
+            const int half = ((int)ceil(5.2 * smax) + 1 + 15) & ~15;
             g.wk = 2 * half;
             g.logF = g.wk <= 768 ? 11 : 12;
             if (g.wk > 3072) return QI_ERR_UNSUPPORTED;
         }
-        g.TC = g.logF == 11 ? 4 : 1;
+        g.TC = 1;
         const int V = (1 << g.logF) - g.wk;
         g.n_blocks = (g.n_out + V - 1) / V;
         pl.levels.push_back(g);
@@ -354,6 +267,7 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl) {
     pl.off_bands = o; o = align_up(o + sizeof(MrDevBand) * (size_t)B, 256);
     pl.off_list = o; o = align_up(o + sizeof(int) * (size_t)(B + 1), 256);
     pl.off_deep = o; o = align_up(o + sizeof(int) * (size_t)(B + 1), 256);
+    pl.off_tw = o; o = align_up(o + sizeof(float4) * (size_t)(4 * L2K_TWJ), 256);
     pl.off_pyr = o; o = align_up(o + sizeof(float) * (size_t)pl.pyr_per_chan * C, 256);
     pl.off_tables = o; o = align_up(o + sizeof(cplx<float>) * (size_t)toff, 256);
     pl.off_w = o; o = align_up(o + sizeof(cplx<float>) * (size_t)woff, 256);
@@ -453,6 +367,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     int* d_list = reinterpret_cast<int*>(base + pl.off_list);
     int* d_deep = reinterpret_cast<int*>(base + pl.off_deep);
     cplx<float>* midbuf = reinterpret_cast<cplx<float>*>(base + pl.off_mid);
+    float4* tw2k = reinterpret_cast<float4*>(base + pl.off_tw);
     float* pyr = reinterpret_cast<float*>(base + pl.off_pyr);
     cplx<float>* tables = reinterpret_cast<cplx<float>*>(base + pl.off_tables);
     cplx<float>* wbuf = reinterpret_cast<cplx<float>*>(base + pl.off_w);
@@ -482,6 +397,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
         cudaFuncSetAttribute(mr_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
         QI_LAUNCH(mr_table_kernel, dim3((unsigned)B), dim3(256), smem, st, (const MrDevBand*)d_bands, N, 2047, tables);
+        QI_LAUNCH(mr_twiddle2k_kernel, dim3((4 * L2K_TWJ + 255) / 256), dim3(256), 0, st, tw2k);
     }
     // P: pyramid
     for (int l = 1; do_front && l <= pl.cap; ++l) {
@@ -502,16 +418,20 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
         g.x_stride = g.level ? pl.pyr_per_chan : stride;
         const int F = 1 << g.logF;
         prof_set_category(g.level ? QI_CAT_INV_FIRST : QI_CAT_INV_MID);
-        dim3 grid((unsigned)((g.n_blocks + g.TC - 1) / g.TC), (unsigned)C);
-        if (g.logF == 11 && g.TC == 4) {
-            const size_t smem = ((size_t)F * 4 * 2 + F) * sizeof(cplx<float>) + 256;
+        if (g.logF == L2K_LOGF && g.band_count <= L2K_MAXB) {
+            // 2048-point blocks: pairs of blocks per CTA, a few pairs in sequence so the twiddle copy is amortised
+            const i64 pairs = (g.n_blocks + 1) / 2;
+            i64 ppc = pairs * C / (148 * 2 * 8);
+            ppc = ppc < 1 ? 1 : (ppc > 4 ? 4 : ppc);
+            dim3 grid2((unsigned)((pairs + ppc - 1) / ppc), (unsigned)C);
 #ifndef QI_EMUL
-            cudaFuncSetAttribute(mr_level4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(mr_level2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2K_SMEM);
 #endif
-            QI_LAUNCH(mr_level4_kernel, grid, dim3(1024), smem, st, x, g, (const MrDevBand*)d_bands,
-                      (const cplx<float>*)tables, wbuf, out_power, out_complex, band_sum);
+            QI_LAUNCH(mr_level2k_kernel, grid2, dim3(L2K_THREADS), L2K_SMEM, st, x, g, (const MrDevBand*)d_bands,
+                      (const cplx<float>*)tables, (const float4*)tw2k, wbuf, out_power, out_complex, band_sum, (int)ppc);
             continue;
         }
+        dim3 grid((unsigned)((g.n_blocks + g.TC - 1) / g.TC), (unsigned)C);
         const size_t smem = ((size_t)F * (g.TC + 1) * 2 + F) * sizeof(cplx<float>) + 256;
 #ifndef QI_EMUL
         cudaFuncSetAttribute(mr_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -9,6 +9,11 @@ QI_DEV double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     return v;
 }
+QI_DEV float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
 QI_DEV double warp_max(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { double t = __shfl_down_sync(0xffffffffu, v, o); v = t > v ? t : v; }
