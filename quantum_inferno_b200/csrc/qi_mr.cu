@@ -462,7 +462,6 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
             dim3 grid((unsigned)((n_dst + tile - 1) / tile), (unsigned)(end - pos), (unsigned)C);
             if (mode == MR_MODE_MID) QI_LAUNCH((mr_expand_kernel<MR_MODE_MID>), grid, dim3(256), 0, st, ea, taps);
             else if (mode == MR_MODE_POWER) QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER>), grid, dim3(256), 0, st, ea, taps);
-            else if (mode == MR_MODE_SUMS) QI_LAUNCH((mr_expand_kernel<MR_MODE_SUMS>), grid, dim3(256), 0, st, ea, taps);
             else QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER_INFO>), grid, dim3(256), 0, st, ea, taps);
             pos = end;
         }
