@@ -33,6 +33,7 @@ ORDER = 3
 LOG2_N = int(os.environ.get("QI_BENCH_LOG2N", "24"))
 CH_PER_GPU = int(os.environ.get("QI_BENCH_CHANNELS", "8"))
 ALG_BYTES_PER_CELL_F32 = 2 * 4 + 4.0 / 60.0       # power + info planes + input share
+HOST_CHUNKS = int(os.environ.get("QI_BENCH_HOST_CHUNKS", "4"))
 METHOD = os.environ.get("QI_BENCH_METHOD", "multirate")     # 'multirate' (default fast path) or 'exact'
 ALGORITHMS = {
     "multirate": "multirate fp32 path: half-band pyramid, per-level overlap-save FFT in shared memory, half-band "
@@ -255,10 +256,18 @@ def run_gpu_arm(args):
     def step_host(src):
         # the call a user makes for host-resident records: channel groups, H2D of group k+1 under the kernels of group k
         return cwt_entropy.cwt_power_entropy(ORDER, src, FS, dtype="float32", out_power=power, out_info=info,
-                                             method=METHOD, host_chunks=4)
+                                             method=METHOD, host_chunks=HOST_CHUNKS)
 
     step_host(x_host)
     sync_all()
+    # the box's plain pinned-host -> HBM bandwidth for the same buffer: the floor of any end-to-end number
+    xd_probe = torch.empty_like(x)
+    e0.record()
+    xd_probe.copy_(x_host, non_blocking=True)
+    e1.record()
+    sync_all()
+    h2d_gbps = x_host.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    del xd_probe
     e0.record()
     d2h = 0
     for _ in range(e2e_steps):
@@ -313,8 +322,9 @@ def run_gpu_arm(args):
             "cpu_baseline": cpu_baseline_single() if world == 1 else None,
             "e2e": {"value": world * cells_per_step_gpu / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms,
-                    "note": "public API cwt_entropy.cwt_power_entropy(host_chunks=4) on pinned host records (H2D of the "
+                    "ms_per_step": e2e_ms, "h2d_gbps_measured": h2d_gbps,
+                    "h2d_floor_ms": x_host.numel() * 4 / (h2d_gbps * 1e9) * 1e3,
+                    "note": f"public API cwt_entropy.cwt_power_entropy(host_chunks={HOST_CHUNKS}) on pinned host records (H2D of the "
                             "next channel group overlaps the kernels of the current one); planes stay in HBM, "
                             "entropy/power summaries are read back"},
             "gpu_launches": int(launches),

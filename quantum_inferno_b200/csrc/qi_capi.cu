@@ -2,6 +2,7 @@
 #include "qi_fft.cuh"
 #include "qi_host.h"
 
+#include <string.h>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -37,6 +38,32 @@ void prof_end(cudaStream_t st) {
     cudaEventRecord(r.b, st);
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_recs.push_back(r);
+}
+#endif
+
+#ifdef QI_EMUL
+void stage_to_device(void* dst, const void* src, size_t bytes, cudaStream_t) { memcpy(dst, src, bytes); }
+#else
+// The table travels in the kernel's parameter space and a few threads write it out: no copy engine is involved, so the
+// transfer can never queue behind a bulk host->device copy that another stream has in flight (measured: with
+// cudaMemcpyAsync the first kernel of a call waited for the WHOLE 128 MB record copy of the next channel group).
+namespace {
+struct StageBlob { unsigned q[768]; };                // 3 KB per launch, inside the 4 KB parameter space
+__global__ void stage_blob_kernel(StageBlob blob, unsigned* __restrict__ dst, int n4) {
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = blob.q[i];
+}
+}  // namespace
+void stage_to_device(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    // every table of this library is an array of 4- or 8-byte fields: whole 32-bit words
+    const unsigned char* s = static_cast<const unsigned char*>(src);
+    unsigned char* d = static_cast<unsigned char*>(dst);
+    while (bytes > 0) {
+        const size_t chunk = bytes < sizeof(StageBlob) ? bytes : sizeof(StageBlob);
+        StageBlob blob;
+        memcpy(&blob, s, chunk);
+        stage_blob_kernel<<<1, 256, 0, st>>>(blob, reinterpret_cast<unsigned*>(d), (int)((chunk + 3) / 4));
+        s += chunk; d += chunk; bytes -= chunk;
+    }
 }
 #endif
 

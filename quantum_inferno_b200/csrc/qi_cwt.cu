@@ -212,11 +212,8 @@ static int cwt_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiAtomB
 
     std::vector<DevBand> db; std::vector<int> tab;
     fill_dev_bands(hb, B, lo.logL, (conv_mode == QI_CONV_LINEAR_SAME && (N % 2 == 0)) ? 1 : 0, db, tab);
-    cudaMemcpyAsync(d_bands, db.data(), sizeof(DevBand) * (size_t)B, cudaMemcpyHostToDevice, st);
-    if (n_tab) cudaMemcpyAsync(d_tab, tab.data(), sizeof(int) * (size_t)n_tab, cudaMemcpyHostToDevice, st);
-#ifndef QI_EMUL
-    cudaStreamSynchronize(st);   // host vectors go out of scope; pageable copies are staged but be explicit
-#endif
+    stage_to_device(d_bands, db.data(), sizeof(DevBand) * (size_t)B, st);
+    if (n_tab) stage_to_device(d_tab, tab.data(), sizeof(int) * (size_t)n_tab, st);
 
     CwtGeom geo;
     geo.n_points = N; geo.n_channels = C; geo.n_bands = B; geo.logL = lo.logL;
@@ -286,10 +283,7 @@ static int atoms_time_impl(const QiAtomBand* hb, int B, i64 N, double fs, const 
     for (auto& t : tmp) t.analytic = 0;
     fill_dev_bands(tmp.data(), B, 0, 0, db, tab);
     DevBand* d_bands = static_cast<DevBand*>(ws);
-    cudaMemcpyAsync(d_bands, db.data(), sizeof(DevBand) * (size_t)B, cudaMemcpyHostToDevice, st);
-#ifndef QI_EMUL
-    cudaStreamSynchronize(st);
-#endif
+    stage_to_device(d_bands, db.data(), sizeof(DevBand) * (size_t)B, st);
     dim3 grid((unsigned)((N + 255) / 256), (unsigned)B);
     QI_LAUNCH((atoms_time_kernel<T>), grid, dim3(256), 0, st, (const DevBand*)d_bands, B, N, fs, xtime, static_cast<cplx<T>*>(out));
     return check_cuda("qi_atoms_time");

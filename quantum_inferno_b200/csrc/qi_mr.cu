@@ -373,14 +373,9 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     cplx<float>* wbuf = reinterpret_cast<cplx<float>*>(base + pl.off_w);
     const HbTaps taps = make_taps();
 
-    cudaMemcpyAsync(d_bands, pl.bands.data(), sizeof(MrDevBand) * (size_t)B, cudaMemcpyHostToDevice, st);
-    if (!pl.expand_list.empty())
-        cudaMemcpyAsync(d_list, pl.expand_list.data(), sizeof(int) * pl.expand_list.size(), cudaMemcpyHostToDevice, st);
-    if (!pl.deep_list.empty())
-        cudaMemcpyAsync(d_deep, pl.deep_list.data(), sizeof(int) * pl.deep_list.size(), cudaMemcpyHostToDevice, st);
-#ifndef QI_EMUL
-    cudaStreamSynchronize(st);
-#endif
+    stage_to_device(d_bands, pl.bands.data(), sizeof(MrDevBand) * (size_t)B, st);
+    if (!pl.expand_list.empty()) stage_to_device(d_list, pl.expand_list.data(), sizeof(int) * pl.expand_list.size(), st);
+    if (!pl.deep_list.empty()) stage_to_device(d_deep, pl.deep_list.data(), sizeof(int) * pl.deep_list.size(), st);
     const bool do_front = phase != QI_MR_PHASE_EXPAND;      // tables, pyramid, level convolutions, estimates
     const bool do_back = phase != QI_MR_PHASE_ESTIMATE;     // expansion to the full rate
     if (do_front) {

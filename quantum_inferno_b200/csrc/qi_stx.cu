@@ -64,10 +64,7 @@ static void upload_stx_bands(const QiStxBand* hb, int B, i64 N, DevStxBand* d_ba
         db[b].q = hb[b].sigma * 2.0 * M_PI / (double)N;
         db[b].shift = ((hb[b].shift % N) + N) % N;
     }
-    cudaMemcpyAsync(d_bands, db.data(), sizeof(DevStxBand) * (size_t)B, cudaMemcpyHostToDevice, st);
-#ifndef QI_EMUL
-    cudaStreamSynchronize(st);
-#endif
+    stage_to_device(d_bands, db.data(), sizeof(DevStxBand) * (size_t)B, st);
 }
 
 template <typename T>

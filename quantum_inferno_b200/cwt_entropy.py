@@ -56,16 +56,27 @@ def _host_pipelined(rt, band_order_nth, sig_wf, fs, dictionary_type, dt, host_ch
     main = torch.cuda.current_stream(rt.device)
     copy_stream = torch.cuda.Stream(device=rt.device)
     bounds = np.linspace(0, n_chan, min(int(host_chunks), n_chan) + 1).astype(int)
+    # two staging buffers owned by this call (allocated on the compute stream, so the caching allocator never has to
+    # reason about the copy stream); buffer k % 2 is refilled only after the kernels of group k - 2 have consumed it
+    gmax = int(np.max(np.diff(bounds)))
+    stage = [torch.empty((gmax, n_points), dtype=x.dtype, device=rt.device) for _ in range(2)]
+    consumed = [None, None]
+    copy_stream.wait_stream(main)
     parts = []
-    for c0, c1 in zip(bounds[:-1], bounds[1:]):
+    for k, (c0, c1) in enumerate(zip(bounds[:-1], bounds[1:])):
+        buf = stage[k % 2][: c1 - c0]
         with torch.cuda.stream(copy_stream):
-            xd = x[c0:c1].to(device=rt.device, dtype=getattr(torch, dt), non_blocking=True)
+            if consumed[k % 2] is not None:
+                copy_stream.wait_event(consumed[k % 2])
+            buf.copy_(x[c0:c1], non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(copy_stream)
         main.wait_event(ready)
-        xd.record_stream(main)
-        parts.append(cwt_power_entropy(band_order_nth, xd, fs, dictionary_type, dtype=dt, out_power=out_power[c0:c1],
+        parts.append(cwt_power_entropy(band_order_nth, buf, fs, dictionary_type, dtype=dt, out_power=out_power[c0:c1],
                                        out_info=None if out_info is None else out_info[c0:c1], **kwargs))
+        consumed[k % 2] = torch.cuda.Event()
+        consumed[k % 2].record(main)
+    copy_stream.wait_stream(main)
     first = parts[0]
     ent = None if first.band_entropy_bits is None else torch.cat([p.band_entropy_bits for p in parts])
     return CwtEntropy(first.frequency_hz, first.band_slice, first.n_bands_total, out_power, out_info,
