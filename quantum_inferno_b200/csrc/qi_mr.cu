@@ -34,22 +34,54 @@ namespace qi {
 
 // ---------------------------------------------------------------- P: half-band decimation by 2
 // src: level l (with halo `src_halo`, length src_len incl. halo; level 0: halo 0), dst: level l+1 with MR_HALO.
+// A CTA makes 1024 outputs: the source tile is split on the way into shared memory into its even samples (the
+// centre taps) and its odd samples (all other taps), so a thread's four consecutive outputs need six 128-bit loads
+//     out[q] = 0.5 * even[q] + sum_t c_t * (odd[q + t] + odd[q - t - 1])
+// src rows must be 8-byte aligned, dst rows 16-byte aligned, dst_len a multiple of 4 (true for every level array).
+constexpr int DEC_TILE = 1024, DEC_PAD = 8;
+static_assert(QI_HB_MAX_TAPS <= DEC_PAD - 1, "decimator window");
 __global__ void __launch_bounds__(256)
 mr_decimate_kernel(const float* __restrict__ src, i64 src_stride, i64 src_len, int src_halo,
                    float* __restrict__ dst, i64 dst_stride, i64 dst_len, HbTaps taps) {
-    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;      // dst index, q = i - MR_HALO
-    if (i >= dst_len) return;
+    __shared__ __align__(16) float s_even[DEC_TILE + 2 * DEC_PAD];
+    __shared__ __align__(16) float s_odd[DEC_TILE + 2 * DEC_PAD + 4];
     const i64 c = blockIdx.y;
     const float* s = src + c * src_stride;
-    const i64 centre = 2 * (i - MR_HALO) + src_halo;               // src index of sample 2q
-    auto at = [&](i64 k) -> float { return (k >= 0 && k < src_len) ? s[k] : 0.0f; };
-    float acc = 0.5f * at(centre);
-    const int nt = taps.n[0];
-#pragma unroll
-    for (int t = 0; t < QI_HB_MAX_TAPS; ++t) {
-        if (t < nt) acc += taps.c[0][t] * (at(centre + 2 * t + 1) + at(centre - 2 * t - 1));
+    const i64 i_base = (i64)blockIdx.x * DEC_TILE;                 // dst index of the tile's first output, q = i - MR_HALO
+    const i64 k_base = 2 * (i_base - MR_HALO - DEC_PAD) + src_halo; // src index of slot 0 (even by construction)
+    for (int j = threadIdx.x; j < DEC_TILE + 2 * DEC_PAD; j += blockDim.x) {
+        const i64 k = k_base + 2 * j;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (k >= 0 && k + 1 < src_len) v = *reinterpret_cast<const float2*>(s + k);
+        else {
+            if (k >= 0 && k < src_len) v.x = s[k];
+            if (k + 1 >= 0 && k + 1 < src_len) v.y = s[k + 1];
+        }
+        s_even[j] = v.x;
+        s_odd[j] = v.y;
     }
-    dst[c * dst_stride + i] = acc;
+    if (threadIdx.x < 4) s_odd[DEC_TILE + 2 * DEC_PAD + threadIdx.x] = 0.0f;
+    __syncthreads();
+    const int j0 = 4 * threadIdx.x;                                // outputs j0 .. j0+3 of the tile; slot = j + DEC_PAD
+    if (i_base + j0 >= dst_len) return;
+    float od[20];                                                  // odd[j0 - 8 .. j0 + 11] <-> slots j0 .. j0 + 19
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(s_odd + j0 + 4 * m);
+        od[4 * m] = v.x; od[4 * m + 1] = v.y; od[4 * m + 2] = v.z; od[4 * m + 3] = v.w;
+    }
+    const float4 ev = *reinterpret_cast<const float4*>(s_even + j0 + DEC_PAD);
+    const float e[4] = {ev.x, ev.y, ev.z, ev.w};
+    float o[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float acc = 0.5f * e[r];
+#pragma unroll
+        for (int t = 0; t < QI_HB_MAX_TAPS; ++t)                   // taps beyond n[0] are stored as zeros
+            acc += taps.c[0][t] * (od[8 + r + t] + od[8 + r - t - 1]);
+        o[r] = acc;
+    }
+    *reinterpret_cast<float4*>(dst + c * dst_stride + i_base + j0) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // ---------------------------------------------------------------- T: kernel tables
@@ -153,12 +185,18 @@ mr_level_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __r
                 }
             } else {
                 cplx<float>* wdst = wbuf + band.w_off + chan * band.w_stride + o0;
-                for (int pv = threadIdx.x; pv < V; pv += blockDim.x)
-                    if (o0 + pv < g.n_out) wdst[pv] = ycol[pv * TP];
+                for (int pv = threadIdx.x; pv < V; pv += blockDim.x) {
+                    if (o0 + pv < g.n_out) {
+                        const cplx<float> y = ycol[pv * TP];
+                        wdst[pv] = y;
+                        const i64 q = g.q_first + o0 + pv;             // raw sum over the record proper, see mr_total_kernel
+                        if (q >= 0 && q < g.n_level) acc_f += norm2(y);
+                    }
+                }
             }
         }
         double acc = (double)acc_f;
-        if (g.level == 0 && band_sum) {
+        if (band_sum) {
             acc = block_sum(acc, scratch);
             if (threadIdx.x == 0) atomicAdd(&band_sum[chan * g.n_bands + b], acc);
         }
@@ -276,53 +314,41 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl) {
     return QI_OK;
 }
 
-// total[c] = sum of the level-0 bands' exact sums + the deeper bands' estimates; the estimate table is completed
-// with the exact level-0 entries so the caller sees one [C, B] table.
-__global__ void mr_total_kernel(const MrDevBand* __restrict__ bands, int B, const double* __restrict__ band_sum,
-                                double* __restrict__ band_sum_est, double* __restrict__ total) {
+// Band-power estimates and the per-record total that normalises the pdf, needed before the planes are written.
+// band_sum_est arrives holding the RAW sums  sum_{q < N/h} |w(q)|^2  of every band with level >= 1, accumulated by
+// the kernel that produced its decimated output w at level min(L, MR_LMID) (h = 2^that level).  With P = |w|^2
+// band-limited below that level's Nyquist rate,
+//     sum_{n<N} P(n) ~= h * sum_q P(h q) + (h-1)/2 (P(N) - P(0)) - (h^2-1)/12 (P'(N) - P'(0))      (Euler-Maclaurin,
+// P' by central differences; deep bands use their level-MR_LMID copy: smaller h => smaller remainder).
+// Level-0 bands enter with their exact sums.  total[c] = sum over bands.
+__global__ void mr_total_kernel(const MrDevBand* __restrict__ bands, int B, i64 n_points,
+                                const cplx<float>* __restrict__ wbuf, const cplx<float>* __restrict__ midbuf,
+                                const double* __restrict__ band_sum, double* __restrict__ band_sum_est,
+                                double* __restrict__ total) {
     __shared__ double scratch[32];
     const i64 c = blockIdx.x;
     double s = 0.0;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        if (bands[b].level == 0) band_sum_est[c * B + b] = band_sum[c * B + b];
-        s += band_sum_est[c * B + b];
+        const MrDevBand band = bands[b];
+        double est;
+        if (band.level == 0) {
+            est = band_sum[c * B + b];
+        } else {
+            const int lvl = band.level > MR_LMID ? MR_LMID : band.level;
+            const i64 m = n_points >> lvl;
+            const cplx<float>* w = (band.level > MR_LMID ? midbuf + band.mid_off + c * band.mid_stride
+                                                          : wbuf + band.w_off + c * band.w_stride) + MR_HALO;
+            const double h = (double)(1ll << lvl);
+            const double p0 = norm2(w[0]), pn = norm2(w[m]);
+            const double d0 = ((double)norm2(w[1]) - (double)norm2(w[-1])) / (2.0 * h);
+            const double dn = ((double)norm2(w[m + 1]) - (double)norm2(w[m - 1])) / (2.0 * h);
+            est = h * band_sum_est[c * B + b] + 0.5 * (h - 1.0) * (pn - p0) - (h * h - 1.0) / 12.0 * (dn - d0);
+        }
+        band_sum_est[c * B + b] = est;
+        s += est;
     }
     s = block_sum(s, scratch);
     if (threadIdx.x == 0) total[c] = s;
-}
-
-// Band-sum estimate straight from a band's decimated output w (level L, h = 2^L), needed before the planes are
-// written:  sum_{n<N} P(n) ~= h * sum_{q<N/h} P(h q) + (h - 1)/2 * (P(N) - P(0))   (Euler-Maclaurin; |w|^2 is
-// band-limited below the level's Nyquist rate, the next term is O(h/(12 s)) smaller than the correction).
-__global__ void __launch_bounds__(256)
-mr_sums_kernel(const MrDevBand* __restrict__ bands, const int* __restrict__ band_list, int B, i64 n_points,
-               const cplx<float>* __restrict__ wbuf, const cplx<float>* __restrict__ midbuf,
-               double* __restrict__ band_sum_est) {
-    __shared__ double scratch[32];
-    const int b = band_list[blockIdx.y];
-    const MrDevBand band = bands[b];
-    const i64 c = blockIdx.z;
-    // deep bands are summed on their level-MR_LMID copy (smaller h => smaller Euler-Maclaurin remainder)
-    const int lvl = band.level > MR_LMID ? MR_LMID : band.level;
-    const i64 m = n_points >> lvl;
-    const cplx<float>* w = (band.level > MR_LMID ? midbuf + band.mid_off + c * band.mid_stride
-                                                  : wbuf + band.w_off + c * band.w_stride) + MR_HALO;
-    const i64 chunk = (m + gridDim.x - 1) / gridDim.x;
-    const i64 q0 = (i64)blockIdx.x * chunk;
-    const i64 q1 = q0 + chunk < m ? q0 + chunk : m;
-    double s = 0.0;
-    for (i64 q = q0 + threadIdx.x; q < q1; q += blockDim.x) s += (double)norm2(w[q]);
-    const double h = (double)(1ll << lvl);
-    s *= h;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        // Euler-Maclaurin end corrections: + (h-1)/2 (P(N) - P(0)) - (h^2-1)/12 (P'(N) - P'(0)), P' by central differences
-        const double p0 = norm2(w[0]), pn = norm2(w[m]);
-        const double d0 = ((double)norm2(w[1]) - (double)norm2(w[-1])) / (2.0 * h);
-        const double dn = ((double)norm2(w[m + 1]) - (double)norm2(w[m - 1])) / (2.0 * h);
-        s += 0.5 * (h - 1.0) * (pn - p0) - (h * h - 1.0) / 12.0 * (dn - d0);
-    }
-    s = block_sum(s, scratch);
-    if (threadIdx.x == 0) atomicAdd(&band_sum_est[c * B + b], s);
 }
 
 // information plane + entropy sums of the rows the level-0 kernel wrote (their power is already in HBM)
@@ -399,7 +425,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
         const float* src = l == 1 ? sig : pyr + pl.lvl_off[l - 1];
         const i64 src_stride = l == 1 ? stride : pl.pyr_per_chan;
         const i64 src_len = l == 1 ? N : pl.lvl_len[l - 1];
-        dim3 grid((unsigned)((pl.lvl_len[l] + 255) / 256), (unsigned)C);
+        dim3 grid((unsigned)((pl.lvl_len[l] + DEC_TILE - 1) / DEC_TILE), (unsigned)C);
         QI_LAUNCH(mr_decimate_kernel, grid, dim3(256), 0, st, src, src_stride, src_len, l == 1 ? 0 : MR_HALO,
                   pyr + pl.lvl_off[l], pl.pyr_per_chan, pl.lvl_len[l], taps);
     }
@@ -413,6 +439,8 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
         g.x_stride = g.level ? pl.pyr_per_chan : stride;
         const int F = 1 << g.logF;
         prof_set_category(g.level ? QI_CAT_INV_FIRST : QI_CAT_INV_MID);
+        // level 0: exact band sums; levels 1..MR_LMID in the fused mode: raw sums for the power estimate
+        double* sum_dst = g.level == 0 ? band_sum : ((fused && g.level <= MR_LMID) ? band_sum_est : nullptr);
         if (g.logF == L2K_LOGF && g.band_count <= L2K_MAXB) {
             // 2048-point blocks: pairs of blocks per CTA, a few pairs in sequence so the twiddle copy is amortised
             const i64 pairs = (g.n_blocks + 1) / 2;
@@ -423,7 +451,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
             cudaFuncSetAttribute(mr_level2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2K_SMEM);
 #endif
             QI_LAUNCH(mr_level2k_kernel, grid2, dim3(L2K_THREADS), L2K_SMEM, st, x, g, (const MrDevBand*)d_bands,
-                      (const cplx<float>*)tables, (const float4*)tw2k, wbuf, out_power, out_complex, band_sum, (int)ppc);
+                      (const cplx<float>*)tables, (const float4*)tw2k, wbuf, out_power, out_complex, sum_dst, (int)ppc);
             continue;
         }
         dim3 grid((unsigned)((g.n_blocks + g.TC - 1) / g.TC), (unsigned)C);
@@ -432,7 +460,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
         cudaFuncSetAttribute(mr_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
         QI_LAUNCH(mr_level_kernel, grid, dim3(1024), smem, st, x, g, (const MrDevBand*)d_bands,
-                  (const cplx<float>*)tables, wbuf, out_power, out_complex, band_sum);
+                  (const cplx<float>*)tables, wbuf, out_power, out_complex, sum_dst);
     }
     // E: expand -- deep bands first to level MR_LMID (1/32 of the cells), then everything to the full rate
     MrExpandArgs ea;
@@ -465,16 +493,10 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
         prof_set_category(QI_CAT_INV_FIRST);
         if (!pl.deep_list.empty()) launch_groups(pl.deep_list, d_deep, MR_LMID, (N >> MR_LMID) + 2 * MR_HALO, MR_MODE_MID);
         if (fused) {
-            // band-sum estimates from the level-k samples, then the per-record total that normalises the pdf
-            if (!pl.expand_list.empty()) {
-                i64 chunks = ((N >> 1) + 16383) / 16384;
-                if (chunks > 256) chunks = 256;
-                dim3 grid((unsigned)chunks, (unsigned)pl.expand_list.size(), (unsigned)C);
-                QI_LAUNCH(mr_sums_kernel, grid, dim3(256), 0, st, (const MrDevBand*)d_bands, (const int*)d_list, B, N,
-                          (const cplx<float>*)wbuf, (const cplx<float>*)midbuf, band_sum_est);
-            }
-            QI_LAUNCH(mr_total_kernel, dim3((unsigned)C), dim3(128), 0, st, (const MrDevBand*)d_bands, B,
-                      (const double*)band_sum, band_sum_est, total_power);
+            // raw sums are in band_sum_est (level kernels / the MID pass); finish the estimates and the totals
+            QI_LAUNCH(mr_total_kernel, dim3((unsigned)C), dim3(128), 0, st, (const MrDevBand*)d_bands, B, N,
+                      (const cplx<float>*)wbuf, (const cplx<float>*)midbuf, (const double*)band_sum, band_sum_est,
+                      total_power);
         }
     }
     if (do_back) {
@@ -513,6 +535,10 @@ int qi_cwt_multirate(const void* sig, int64_t C, int64_t N, int64_t stride, cons
                      double* band_sum_est, double* total_power, double eps, int phase, void* ws, size_t ws_bytes,
                      void* stream) {
     if (!sig || !bands || !ws || C <= 0 || N <= 0 || B <= 0 || stride < N) return QI_ERR_ARG;
+    // vector loads / 256-bit plane stores: records 8-byte aligned with an even stride, planes 32-byte aligned
+    if (((uintptr_t)sig & 7) || (stride & 1) || ((uintptr_t)out_power & 31) || ((uintptr_t)out_info & 31) ||
+        ((uintptr_t)out_complex & 15))
+        return QI_ERR_ARG;
     if (!out_power && !out_complex && !band_sum) return QI_ERR_ARG;
     if (phase < QI_MR_PHASE_ALL || phase > QI_MR_PHASE_EXPAND) return QI_ERR_ARG;
     return qi::mr_run(static_cast<const float*>(sig), C, N, stride, bands, B, static_cast<float*>(out_power),

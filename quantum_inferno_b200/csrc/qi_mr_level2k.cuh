@@ -14,6 +14,8 @@
 //     four rows, L1/L2 resident) and runs its radix-4 butterfly before anything touches shared memory; the last
 //     inverse stage hands its natural-order outputs from registers to HBM (level 0: |.|^2 -> power plane; deeper
 //     levels: the decimated complex output w_b).  Two tile buffers alternate between bands -> 3 barriers per band.
+//     band_sum (optional) receives sum |y|^2 over the record's own samples: the exact band power at level 0, the raw
+//     sum that mr_total_kernel turns into the band-power estimate at deeper levels.
 //   * twiddles come from a per-stage table laid out [slot pair][j] (built once per call by mr_twiddle2k_kernel with
 //     the exact sincospi roots, copied to shared memory per CTA): 4 conflict-free 128-bit loads per butterfly.
 #pragma once
@@ -286,17 +288,22 @@ mr_level2k_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* _
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int pv = t + 256 * i - half;
-                        if (pv >= 0 && pv < V && o0 + pv < g.n_out) wdst[t + 256 * i] = y[i];
+                        if (pv >= 0 && pv < V && o0 + pv < g.n_out) {
+                            wdst[t + 256 * i] = y[i];
+                            // sum over the record proper (q in [0, N >> level), not the halo) for the power estimate
+                            const i64 q = g.q_first + o0 + pv;
+                            if (q >= 0 && q < g.n_level) acc += norm2(y[i]);
+                        }
                     }
                 }
             }
-            if (g.level == 0 && band_sum) {
+            if (band_sum) {
                 acc = warp_sum(acc);
                 if (lane == 0) wsum[warp * L2K_MAXB + bi] += acc;
             }
         }
     }
-    if (g.level == 0 && band_sum) {
+    if (band_sum) {
         __syncthreads();
         if (t < g.band_count) {
             double s = 0.0;

@@ -13,17 +13,31 @@ class EmulRuntime:
     def __init__(self):
         self.lib = emul_lib.load()
 
+    @staticmethod
+    def _aligned(shape, dtype, align=256):
+        """Like a device allocation: the first byte sits on a 256-byte boundary (the C ABI checks plane alignment)."""
+        shape = tuple(int(s) for s in shape)
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+        raw = np.empty(nbytes + align, dtype=np.uint8)
+        off = (-raw.ctypes.data) % align
+        return raw[off:off + nbytes].view(dt).reshape(shape)
+
     def empty(self, shape, dtype):
-        return np.empty(tuple(int(s) for s in shape), dtype=dtype)
+        return self._aligned(shape, dtype)
 
     def zeros(self, shape, dtype):
-        return np.zeros(tuple(int(s) for s in shape), dtype=dtype)
+        out = self._aligned(shape, dtype)
+        out[...] = 0
+        return out
 
     def is_device_array(self, x):
         return False
 
     def asarray(self, x, dtype):
-        return np.ascontiguousarray(np.asarray(x), dtype=dtype)
+        out = self._aligned(np.shape(x), dtype)
+        out[...] = np.asarray(x)
+        return out
 
     def ptr(self, buf):
         return None if buf is None else buf.ctypes.data
