@@ -481,11 +481,17 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
                 ++end;
             }
             ea.band_list = d_idx + pos;
-            const i64 tile = (i64)MR_SEGQ << k;
+            const i64 tile = (i64)MR_SEGQ << 3;          // per CTA, for every k (see mr_expand_kernel)
             dim3 grid((unsigned)((n_dst + tile - 1) / tile), (unsigned)(end - pos), (unsigned)C);
-            if (mode == MR_MODE_MID) QI_LAUNCH((mr_expand_kernel<MR_MODE_MID>), grid, dim3(256), 0, st, ea, taps);
-            else if (mode == MR_MODE_POWER) QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER>), grid, dim3(256), 0, st, ea, taps);
-            else QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER_INFO>), grid, dim3(256), 0, st, ea, taps);
+            if (k < 3) {
+                if (mode == MR_MODE_MID) QI_LAUNCH((mr_expand_kernel<MR_MODE_MID, true>), grid, dim3(256), 0, st, ea, taps);
+                else if (mode == MR_MODE_POWER) QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER, true>), grid, dim3(256), 0, st, ea, taps);
+                else QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER_INFO, true>), grid, dim3(256), 0, st, ea, taps);
+            } else {
+                if (mode == MR_MODE_MID) QI_LAUNCH((mr_expand_kernel<MR_MODE_MID, false>), grid, dim3(256), 0, st, ea, taps);
+                else if (mode == MR_MODE_POWER) QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER, false>), grid, dim3(256), 0, st, ea, taps);
+                else QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER_INFO, false>), grid, dim3(256), 0, st, ea, taps);
+            }
             pos = end;
         }
     };
