@@ -364,14 +364,19 @@ mr_info_rows_kernel(const float4* __restrict__ p, const double* __restrict__ tot
     const i64 t0 = (i64)blockIdx.x * chunk;
     const i64 t1 = t0 + chunk < T4 ? t0 + chunk : T4;
     double acc = 0.0;
-    for (i64 t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
-        const float4 v = p[row + t];
-        const float d0 = v.x * inv, d1 = v.y * inv, d2 = v.z * inv, d3 = v.w * inv;
-        const float i0 = -mr_fast_log2f(d0 + eps), i1 = -mr_fast_log2f(d1 + eps);
-        const float i2 = -mr_fast_log2f(d2 + eps), i3 = -mr_fast_log2f(d3 + eps);
+    auto one = [&](const float4 v, i64 t) {
+        const float d0 = fmaf(v.x, inv, eps), d1 = fmaf(v.y, inv, eps), d2 = fmaf(v.z, inv, eps), d3 = fmaf(v.w, inv, eps);
+        const float i0 = -mr_fast_log2f(d0), i1 = -mr_fast_log2f(d1), i2 = -mr_fast_log2f(d2), i3 = -mr_fast_log2f(d3);
         o_info[row + t] = make_float4(i0, i1, i2, i3);
-        acc += (double)((d0 * i0 + d1 * i1) + (d2 * i2 + d3 * i3));
+        acc += (double)((d0 * i0 + d1 * i1) + (d2 * i2 + d3 * i3));   // eps inside the weight, as in the fused expand pass
+    };
+    i64 t = t0 + threadIdx.x;
+    for (; t + 3 * (i64)blockDim.x < t1; t += 4 * (i64)blockDim.x) {       // four independent 128-bit loads in flight
+        const float4 v0 = p[row + t], v1 = p[row + t + blockDim.x];
+        const float4 v2 = p[row + t + 2 * blockDim.x], v3 = p[row + t + 3 * blockDim.x];
+        one(v0, t); one(v1, t + blockDim.x); one(v2, t + 2 * blockDim.x); one(v3, t + 3 * blockDim.x);
     }
+    for (; t < t1; t += blockDim.x) one(p[row + t], t);
     acc = block_sum(acc, scratch);
     if (threadIdx.x == 0 && ent_sum) atomicAdd(&ent_sum[c * B + b], acc);
 }
@@ -543,7 +548,7 @@ int qi_cwt_multirate(const void* sig, int64_t C, int64_t N, int64_t stride, cons
     if (!sig || !bands || !ws || C <= 0 || N <= 0 || B <= 0 || stride < N) return QI_ERR_ARG;
     // vector loads / 256-bit plane stores: records 8-byte aligned with an even stride, planes 32-byte aligned
     if (((uintptr_t)sig & 7) || (stride & 1) || ((uintptr_t)out_power & 31) || ((uintptr_t)out_info & 31) ||
-        ((uintptr_t)out_complex & 15))
+        ((uintptr_t)out_complex & 31))
         return QI_ERR_ARG;
     if (!out_power && !out_complex && !band_sum) return QI_ERR_ARG;
     if (phase < QI_MR_PHASE_ALL || phase > QI_MR_PHASE_EXPAND) return QI_ERR_ARG;
