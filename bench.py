@@ -36,12 +36,15 @@ ALG_BYTES_PER_CELL_F32 = 2 * 4 + 4.0 / 60.0       # power + info pl
 HOST_CHUNKS = int(os.environ.get("QI_BENCH_HOST_CHUNKS", "4"))
 METHOD = os.environ.get("QI_BENCH_METHOD", "multirate")     # 'multirate' (default fast path) or 'exact'
 ALGORITHMS = {
-    "multirate": "multirate fp32 path: half-band pyramid, per-level overlap-save FFT in shared memory, half-band "
-                 "interpolation fused with |.|^2 and band sums, then one streaming information pass",
+    "multirate": "multirate fp32 path: half-band pyramid, per-level overlap-save FFT convolution in shared memory "
+                 "(level 0 -> power rows), polyphase interpolation fused with |.|^2, -log2(P/S+eps), both plane stores "
+                 "and the band/entropy sums; one streaming information pass for the level-0 rows",
     "exact": "exact path: record FFT + per-band 3-pass inverse FFT through HBM"}
 KERNEL_OF = {
-    "multirate": {"fft_fwd": "mr_table_kernel+mr_decimate_kernel", "inv_first": "mr_level_kernel[level>=1]",
-                  "inv_mid": "mr_level_kernel[level 0]", "inv_last": "mr_expand_kernel", "info": "shannon_kernel"},
+    "multirate": {"fft_fwd": "mr_table_kernel+mr_decimate_kernel",
+                  "inv_first": "mr_level2k_kernel[levels>=1]+mr_expand_kernel<MID>",
+                  "inv_mid": "mr_level2k_kernel[level 0]", "inv_last": "mr_expand_kernel<POWER_INFO>",
+                  "info": "mr_info_rows_kernel"},
     "exact": {"fft_fwd": "fft_pass_kernel[forward]", "inv_first": "fft_pass_kernel[spectrum x response]",
               "inv_mid": "fft_pass_kernel[middle]", "inv_last": "fft_pass_kernel[slice + power]",
               "info": "shannon_kernel"}}
@@ -205,7 +208,10 @@ def run_gpu_arm(args):
     n = 1 << LOG2_N
     chans = [rank * CH_PER_GPU + i for i in range(CH_PER_GPU)]
     x = synth_batch_torch(torch, n, chans, dev)                       # resident input, 4*C*N bytes (> L2)
-    n_bands = len(cwt_entropy.scales.log_frequency_hz_from_fft_points(FS, n, ORDER))
+    freq = cwt_entropy.scales.log_frequency_hz_from_fft_points(FS, n, ORDER)
+    n_bands = len(freq)
+    from quantum_inferno_b200 import _plan
+    n_level0 = int(np.count_nonzero(_plan.multirate_bands(ORDER, n, freq, FS, "norm")[0]["level"] == 0))
     cells_per_step_gpu = CH_PER_GPU * n_bands * n
     power = torch.empty(CH_PER_GPU, n_bands, n, dtype=torch.float32, device=dev)
     info = torch.empty_like(power)
@@ -295,12 +301,16 @@ def run_gpu_arm(args):
         dom = int(np.argmax(cat_ms[0]))
         dom_launches = int(cat_ms[1][dom])
         dom_avg_ms = float(cat_ms[0][dom] / max(1, dom_launches))
-        # one launch of an inverse pass / info kernel processes (bands in the launch) x C x N cells
-        cells_per_launch = cells_per_step_gpu * args.steps / max(1, dom_launches)
+        # cells the dominant category's launches process per step: the expand launches of the multirate path write the
+        # bands of level >= 1 only (the level-0 rows are written by the level-0 convolution + the information pass)
+        dom_cells_step = cells_per_step_gpu
+        if METHOD == "multirate" and _lib.CATEGORY_NAMES[dom] == "inv_last":
+            dom_cells_step = CH_PER_GPU * (n_bands - n_level0) * n
+        cells_per_launch = dom_cells_step * args.steps / max(1, dom_launches)
         achieved = ALG_BYTES_PER_CELL_F32 * cells_per_launch / (dom_avg_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(_lib.CATEGORY_NAMES[dom])
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[METHOD].get(_lib.CATEGORY_NAMES[dom])
         except (OSError, ValueError):
             pass
         line = {
@@ -316,6 +326,7 @@ def run_gpu_arm(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "avg_launch_ms": dom_avg_ms, "launches": dom_launches,
+                         "cells_per_launch": cells_per_launch,
                          "alg_bytes_per_cell": ALG_BYTES_PER_CELL_F32,
                          "step_frac": ALG_BYTES_PER_CELL_F32 * cells_per_step_gpu / (ms_per_step * 1e-3) / 1e9 / peak,
                          "category_ms_per_step": {nm: float(ms) / args.steps for nm, ms in zip(_lib.CATEGORY_NAMES, cat_ms[0])}},

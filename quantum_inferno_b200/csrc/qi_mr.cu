@@ -8,14 +8,19 @@
 //                   Gaussian response (|theta - omega| <= 4.8/s).  Its kernel at that rate,
 //                   2^l * psi(2^l d - 1/2) truncated like the reference's N-sample atom, is sampled in fp64,
 //                   transformed once in shared memory and kept (bit-reversed order, L2 resident) for all channels.
-//   A  level conv   overlap-save convolution of x_l with all bands of level l: one forward FFT of a 2048/4096-point
-//                   block in shared memory, then per band multiply + inverse FFT in shared memory.  Level-0 bands
-//                   go straight to |.|^2 -> power plane (+ fp64 band sums); deeper bands leave their decimated
-//                   complex output w_b (8 B per 2^l cells) in HBM.
-//   E  expand       per (channel, band, 2048-cell tile): the tile's w_b samples are read once, interpolated by 2 l
-//                   times in shared memory with minimax half-band interpolators whose length shrinks as the signal
-//                   gets more oversampled (7,4,3,3,2,2,... taps per side), and the last stage feeds |.|^2, the power
-//                   plane store and the band sums from registers.
+//   A  level conv   overlap-save convolution of x_l with all bands of level l in 2048-point blocks
+//                   (qi_mr_level2k.cuh): block spectra in registers, per band multiply + inverse FFT in shared
+//                   memory.  Level-0 bands go straight to |.|^2 -> power rows (+ exact fp64 band sums); deeper bands
+//                   leave their decimated complex output w_b (8 B per 2^l cells) in HBM, together with the raw sum
+//                   of |w_b|^2 that the band-power estimate needs.
+//   S  total power  mr_total_kernel: S per record from those sums (Euler-Maclaurin corrected), BEFORE any plane of
+//                   the deeper bands is written, so that the information plane can be fused into E.
+//   E  expand       qi_mr_expand.cuh: per (channel, band, 16384-cell span) the band's decimated samples are read
+//                   once, brought to level k = min(l, 3) by half-band stages in shared memory and to the full rate
+//                   by one merged polyphase interpolator x2^k from registers, fused with |.|^2, -log2(P/S + eps),
+//                   both plane stores (256-bit) and the band / entropy sums.  Bands deeper than level 5 first get a
+//                   level-5 copy (MID mode, 1/32 of the cells).
+//   I  info rows    the level-0 rows' information plane (their power was written before S was known).
 //
 // Replaces (fp32 tolerance of the north star: power rel. L2 <= 1e-4) quantum_inferno/styx_cwt.py:147-198 + np.abs()**2.
 // The numpy model of exactly this algorithm is tools/multirate_prototype.py.
