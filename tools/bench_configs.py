@@ -20,9 +20,21 @@ from quantum_inferno_b200 import cwt_entropy, styx_cwt, styx_fft, styx_stx  # no
 DEV = torch.device("cuda", 0)
 
 
-def timed(fn, reps=5, warm=3):
+def spin(ms=300.0):
+    """Keep the GPU busy for a while so that the short measurements below run at the loaded clock."""
+    a = torch.randn(4096, 4096, device=DEV)
+    t0 = time.time()
+    while (time.time() - t0) * 1e3 < ms:
+        for _ in range(10):
+            a = (a @ a).tanh_()
+        torch.cuda.synchronize()
+
+
+def timed(fn, reps=10, warm=3):
     for _ in range(warm):
         fn()
+    spin()
+    fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
