@@ -62,7 +62,29 @@ def cwt_power_entropy_band_sharded(band_order_nth, sig_wf, frequency_sample_rate
     rank = dist.get_rank(group) if rank is None else rank
     world = dist.get_world_size(group) if world is None else world
     n_points = int(sig_wf.shape[-1])
-    n_bands = len(scales.log_frequency_hz_from_fft_points(frequency_sample_rate_hz, n_points, band_order_nth))
+    freq = scales.log_frequency_hz_from_fft_points(frequency_sample_rate_hz, n_points, band_order_nth)
     return cwt_entropy.cwt_power_entropy(band_order_nth, sig_wf, frequency_sample_rate_hz,
-                                         band_slice=band_shard(n_bands, rank, world),
+                                         band_slice=band_shard(len(freq), rank, world,
+                                                               band_cost(band_order_nth, n_points, freq,
+                                                                         frequency_sample_rate_hz, kwargs)),
                                          allreduce=sum_allreduce(group), **kwargs)
+
+
+# measured cost of one band of the fused fp32 multirate path relative to a deep band (B200, 2^24 samples): the full
+# rate convolution + separate information pass of a level-0 band, the larger input share of the x2 / x4 interpolators
+_MULTIRATE_LEVEL_COST = {0: 3.6, 1: 3.8, 2: 2.5, 3: 1.5, 4: 1.25}
+
+
+def band_cost(band_order_nth, n_points, frequency_hz, frequency_sample_rate_hz, kwargs=None):
+    """Per-band cost estimate for ``band_shard``: equal for the exact method (one full-length inverse FFT per band),
+    level dependent for the multirate method."""
+    from . import _plan
+    kwargs = kwargs or {}
+    dt = str(kwargs.get("dtype", "float32")).replace("torch.", "")
+    if dt != "float32" or kwargs.get("method", "auto") == "exact":
+        return None
+    bands, scale, _, _ = _plan.multirate_bands(band_order_nth, n_points, frequency_hz, frequency_sample_rate_hz,
+                                               kwargs.get("dictionary_type", "norm"))
+    if not _plan.multirate_supported(n_points, scale):
+        return None
+    return [_MULTIRATE_LEVEL_COST.get(int(lv), 1.05) for lv in bands["level"]]
