@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define QI_ABI_VERSION 1
+#define QI_ABI_VERSION 2
 
 /* dtype of the arithmetic and of every real/complex buffer in a call */
 #define QI_F32 0
@@ -171,10 +171,25 @@ int qi_stx_windows(const QiStxBand* bands, int n_bands, int64_t n_points, int dt
  * removed (detrend != 0), is multiplied by window[nperseg] (device pointer), zero-padded to nfft = 2^m,
  * transformed, and the one-sided bins multiplied by `scale`.
  *   out     : complex [n_channels, nfft/2+1, n_frames] (time fastest, scipy's layout) or NULL
- *   psd_acc : double  [n_channels, nfft/2+1] receives sum over frames of |X_k|^2 (unscaled) or NULL */
+ *   psd_acc : double  [n_channels, nfft/2+1] receives sum over frames of |X_k|^2 (unscaled) or NULL
+ *   roll    : the windowed, zero-padded segment is rotated left by `roll` samples before the transform, i.e. bin k is
+ *             multiplied by exp(+2*pi*i*k*roll/nfft) (scipy.signal.ShortTimeFFT phase_shift, used through
+ *             quantum_inferno/utilities/short_time_fft.py:54-58); 0 for scipy.signal.stft */
 int qi_stft(const void* sig, int64_t n_channels, int64_t n_points, int64_t sig_stride, const void* window,
-            int nperseg, int hop, int nfft, int64_t n_frames, int pad_left, double scale, int detrend, int dtype,
-            void* out, double* psd_acc, void* stream);
+            int nperseg, int hop, int nfft, int64_t n_frames, int pad_left, double scale, int detrend, int roll,
+            int dtype, void* out, double* psd_acc, void* stream);
+
+/* Inverse STFT by overlap-add (scipy.signal.ShortTimeFFT.istft as called by
+ * quantum_inferno/utilities/short_time_fft.py:106-134).
+ *   S        : complex [n_channels, nfft/2+1, n_frames] (time fastest), one-sided spectra made with the same `roll`
+ *   dual_win : real [nperseg] device pointer (canonical dual window; any scaling folded in)
+ *   frame p covers output samples [first_start + p*hop, ... + nperseg); frames [frame_lo, frame_hi) are summed
+ *   out      : real [n_channels, n_out] = samples k0 .. k0 + n_out - 1
+ *   workspace: >= qi_istft_workspace_bytes (the windowed inverse transforms of all frames) */
+size_t qi_istft_workspace_bytes(int64_t n_channels, int64_t n_frames, int nperseg, int dtype);
+int qi_istft(const void* S, int64_t n_channels, int64_t n_frames, const void* dual_win, int nperseg, int hop, int nfft,
+             int roll, int64_t first_start, int64_t frame_lo, int64_t frame_hi, int64_t k0, int64_t n_out, int dtype,
+             void* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- power / information / entropy (tfr_info) -------------------------------------------------
  * `power` is real [M, F, T] (M independent matrices: channels).  All reductions accumulate in fp64. */
@@ -207,7 +222,8 @@ int qi_tdr_marginal(const void* sig, int64_t M, int64_t n, int64_t sig_stride, i
 /* Elementwise on n values of a real (is_complex=0), complex (is_complex=1) or signed-real (is_complex=2: no
  * modulus, log2(x + eps) as in tfr_info.py:65-70) buffer:
  * square=0: out = log2(|x| + eps)  (quantum_inferno/utilities/rescaling.py:13-20 to_log2_with_epsilon, used at
- *           cwt_atoms.py:442 and styx_fft.py:55);  square=1: out = |x|^2 + eps (styx_stx.py:188-190). out is real. */
+ *           cwt_atoms.py:442 and styx_fft.py:55);  square=1: out = |x|^2 + eps (styx_stx.py:188-190);
+ *           square=2: out = |x| + eps (np.abs of utilities/short_time_fft.py:95).  out is real. */
 int qi_abs_log2(const void* in, int64_t n, int dtype, int is_complex, int square, double eps, void* out, void* stream);
 
 /* Replaces scipy.fft.rfft in ShannonFFT.__init__ (tfr_info.py:177): real [M, n=2^m] -> complex [M, n/2+1]

@@ -164,6 +164,26 @@ def main():
     d["x1024"] = x1024
     np.savez_compressed(os.path.join(OUT, "info.npz"), **d)
 
+    # ---------------------------------------------------------------- utilities/short_time_fft
+    from quantum_inferno.utilities import short_time_fft
+    tone, _, fft_nd, fs_t, _, _ = benchmark_signals.well_tempered_tone()
+    xs = tone + np.random.default_rng(77).standard_normal(len(tone)) / 8.0
+    d = {"x": xs, "fft_nd": np.array(fft_nd)}
+    cases = [(fft_nd, fft_nd // 2, "magnitude", "zeros", 0.25), (200, 150, "psd", "even", 0.5),
+             (256, 192, "none", "odd", 1.0), (128, 64, "magnitude", "edge", 0.0), (100, 20, "magnitude", "zeros", 0.25)]
+    d["cases"] = np.array([(m, ov, al) for m, ov, _, _, al in cases])
+    d["case_scaling"] = np.array([c[2] for c in cases])
+    d["case_padding"] = np.array([c[3] for c in cases])
+    for i, (m, ov, scal, pad, al) in enumerate(cases):
+        scal = None if scal == "none" else scal
+        f, t, mag = short_time_fft.stft_tukey(xs, fs_t, al, m, ov, scal, pad)
+        _, _, sp = short_time_fft.spectrogram_tukey(xs, fs_t, al, m, ov, scal, pad)
+        spec = short_time_fft.get_stft_object_tukey(fs_t, al, m, ov, scal).stft(xs)
+        ts, xr = short_time_fft.istft_tukey(spec, fs_t, al, m, ov, scal)
+        d[f"c{i}_f"], d[f"c{i}_t"], d[f"c{i}_mag"], d[f"c{i}_sp"] = f, t, mag, sp
+        d[f"c{i}_spec"], d[f"c{i}_ts"], d[f"c{i}_xr"] = spec, ts, xr
+    np.savez_compressed(os.path.join(OUT, "stft_tukey.npz"), **d)
+
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)) // 1024, "KiB")
 

@@ -486,3 +486,125 @@ def cwt_power_entropy(order, sig, fs, dictionary_type="norm"):
     pf = shannon_stft_per_freq(p)
     return dict(freq=freqs, power=p, info=g.info, band_sum=p.sum(axis=1), total=float(p.sum()),
                 entropy_bits=float(g.shannon_bits.sum()), band_entropy_bits=pf.shannon_bits.sum(axis=1))
+
+
+# ---------------------------------------------------------------- utilities/short_time_fft.py
+# The reference delegates to scipy.signal.ShortTimeFFT (scipy >= 1.15, pyproject.toml:20); its published algorithm
+# (scipy/signal/_short_time_fft.py: _pre_padding, _post_padding, _x_slices, stft_detrend, _fft_func, _ifft_func,
+# istft, _calc_dual_canonical_window) is restated here with numpy only.
+def tukey_symmetric(m, alpha):
+    """scipy.signal.windows.tukey(m, alpha, sym=True) as called at utilities/short_time_fft.py:51."""
+    if m == 1 or alpha <= 0:
+        return np.ones(m)
+    if alpha >= 1.0:
+        return 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(m) / (m - 1))
+    n = np.arange(m)
+    width = int(np.floor(alpha * (m - 1) / 2.0))
+    n1, n2, n3 = n[0:width + 1], n[width + 1:m - width - 1], n[m - width - 1:]
+    w1 = 0.5 * (1 + np.cos(np.pi * (-1 + 2.0 * n1 / alpha / (m - 1))))
+    w3 = 0.5 * (1 + np.cos(np.pi * (-2.0 / alpha + 1 + 2.0 * n3 / alpha / (m - 1))))
+    return np.concatenate((w1, np.ones(n2.shape), w3))
+
+
+class StftTukeyPlan:
+    """Bookkeeping of get_stft_object_tukey (utilities/short_time_fft.py:19-60) + ShortTimeFFT's slice ranges."""
+
+    def __init__(self, fs, alpha, segment_length, overlap_length, scaling="magnitude"):
+        if segment_length < overlap_length:
+            overlap_length = segment_length // 2
+        if alpha < 0 or alpha > 1:
+            alpha = 0.25
+        if scaling not in ("magnitude", "psd", None):
+            scaling = "magnitude"
+        self.fs, self.m, self.hop = float(fs), int(segment_length), int(segment_length - overlap_length)
+        self.mfft = 2 ** int(np.ceil(np.log2(segment_length)))        # round_value(..., "ceil_power_of_two")
+        self.mid = self.m // 2
+        win = tukey_symmetric(self.m, alpha)
+        if scaling == "magnitude":                                    # ShortTimeFFT.scale_to: the window itself is scaled
+            win = win / abs(win.sum())
+        elif scaling == "psd":
+            win = win / np.sqrt((win ** 2).sum() / (1.0 / self.fs))
+        self.win = win
+        w2 = win ** 2
+        dd = w2.copy()                                                # canonical dual window
+        for k in range(self.hop, self.m, self.hop):
+            dd[k:] += w2[:-k]
+            dd[:-k] += w2[k:]
+        self.dual = win / dd
+        self.roll = self.mid % self.m                                 # phase_shift = 0
+        self.f = np.fft.rfftfreq(self.mfft, 1.0 / self.fs)
+        self.delta_t = self.hop / self.fs
+        # _pre_padding: move the window left until it no longer overlaps t >= 0
+        n0 = -self.mid
+        for p_, n_ in enumerate(range(n0, n0 - self.m - 1, -self.hop)):
+            n_next = n_ - self.hop
+            if n_next + self.m <= 0 or np.all(w2[n_next:] == 0):
+                self.k_min, self.p_min = n_, -p_
+                break
+
+    def p_max(self, n):
+        w2 = self.win ** 2
+        q1 = n // self.hop
+        k1 = q1 * self.hop - self.mid
+        for q_, k_ in enumerate(range(k1, n + self.m, self.hop), start=q1):
+            n_next = k_ + self.hop
+            if n_next >= n or np.all(w2[:n - n_next] == 0):
+                return q_ + 1
+        raise RuntimeError("unreachable")
+
+    def slices(self, x, padding):
+        n = len(x)
+        p0, p1 = self.p_min, self.p_max(n)
+        k0 = p0 * self.hop - self.mid
+        k1 = k0 + (p1 - p0) * self.hop + self.m
+        kw = {"zeros": dict(mode="constant"), "edge": dict(mode="edge"), "even": dict(mode="reflect", reflect_type="even"),
+              "odd": dict(mode="reflect", reflect_type="odd")}[padding]
+        x1 = np.pad(x[max(k0, 0):min(k1, n)], (-min(k0, 0), max(k1 - n, 0)), **kw)
+        return [x1[k:k + self.m] for k in range(0, (p1 - p0) * self.hop, self.hop)]
+
+    def stft(self, x, detrend_constant=False, padding="zeros"):
+        cols = []
+        for s in self.slices(np.asarray(x, dtype=np.float64), padding):
+            if detrend_constant:
+                s = s - s.mean()
+            z = np.zeros(self.mfft)
+            z[:self.m] = s * self.win
+            cols.append(np.fft.rfft(np.roll(z, -self.roll)))
+        return np.array(cols).T
+
+    def istft(self, spec, k1):
+        q_max = spec.shape[-1] + self.p_min
+        q0, q1 = self.p_min, min(self.p_max(k1), q_max)
+        x = np.zeros(k1 + self.m)
+        for q in range(q0, q1):
+            xs = np.roll(np.fft.irfft(spec[:, q - self.p_min], n=self.mfft), self.roll)[:self.m] * self.dual
+            i0 = q * self.hop - self.mid
+            j0 = max(0, -i0)
+            x[i0 + j0:i0 + self.m] += xs[j0:]
+        return x[:k1]
+
+
+def stft_tukey(x, fs, alpha, segment_length, overlap_length, scaling="magnitude", padding="zeros"):
+    """utilities/short_time_fft.py:64-102 -> (frequency bins, time bins, |stft_detrend(x, 'constant')|)."""
+    if padding not in ("zeros", "edge", "even", "odd"):
+        padding = "zeros"
+    plan = StftTukeyPlan(fs, alpha, segment_length, overlap_length, scaling)
+    mag = np.abs(plan.stft(x, True, padding))
+    return plan.f, np.arange(0, plan.delta_t * mag.shape[1], plan.delta_t), mag
+
+
+def spectrogram_tukey(x, fs, alpha, segment_length, overlap_length, scaling="magnitude", padding="zeros"):
+    """utilities/short_time_fft.py:138-175."""
+    if padding not in ("zeros", "edge", "even", "odd"):
+        padding = "zeros"
+    plan = StftTukeyPlan(fs, alpha, segment_length, overlap_length, scaling)
+    s = plan.stft(x, False, padding)
+    sp = s.real ** 2 + s.imag ** 2
+    return plan.f, np.arange(0, plan.delta_t * sp.shape[1], plan.delta_t), sp
+
+
+def istft_tukey(spec, fs, alpha, segment_length, overlap_length, scaling="magnitude"):
+    """utilities/short_time_fft.py:106-134."""
+    plan = StftTukeyPlan(fs, alpha, segment_length, overlap_length, scaling)
+    last = int((spec.shape[1] - 1) * plan.hop)
+    return np.arange(0, last / fs, 1 / fs), plan.istft(spec, last)

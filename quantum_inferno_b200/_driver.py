@@ -116,9 +116,9 @@ def stx_windows(bands, n_points, dt, rt=None):
     return out
 
 
-def stft(sig, window, nperseg, hop, nfft, n_frames, pad_left, scale, dt, detrend=True, psd=False, rt=None):
+def stft(sig, window, nperseg, hop, nfft, n_frames, pad_left, scale, dt, detrend=True, psd=False, rt=None, roll=0):
     """sig: device [C, N]; window: numpy float64 [nperseg].  Returns complex [C, nfft/2+1, n_frames]
-    (psd=False) or the fp64 accumulator [C, nfft/2+1] of sum_frames |X|^2 (psd=True)."""
+    (psd=False) or the fp64 accumulator [C, nfft/2+1] of sum_frames |X|^2 (psd=True).  roll: see qi_stft."""
     rt = rt or get_runtime()
     lib = rt.lib
     C, N = int(sig.shape[0]), int(sig.shape[1])
@@ -127,10 +127,27 @@ def stft(sig, window, nperseg, hop, nfft, n_frames, pad_left, scale, dt, detrend
     out = None if psd else rt.empty((C, K, n_frames), COMPLEX_OF[dt])
     acc = rt.empty((C, K), "float64") if psd else None
     rc = lib.qi_stft(rt.ptr(sig), C, N, N, rt.ptr(win), int(nperseg), int(hop), int(nfft), int(n_frames),
-                     int(pad_left), float(scale), 1 if detrend else 0, DTYPE_CODE[dt], rt.ptr(out), rt.ptr(acc),
-                     rt.stream())
+                     int(pad_left), float(scale), 1 if detrend else 0, int(roll), DTYPE_CODE[dt], rt.ptr(out),
+                     rt.ptr(acc), rt.stream())
     _lib.check(lib, rc, "qi_stft")
     return acc if psd else out
+
+
+def istft(spec, dual_win, nperseg, hop, nfft, roll, first_start, frame_lo, frame_hi, k0, n_out, dt, rt=None):
+    """spec: device complex [C, nfft/2+1, P]; dual_win: numpy float64 [nperseg].  Returns real [C, n_out]: the
+    overlap-add of frames [frame_lo, frame_hi) restricted to samples k0 .. k0 + n_out - 1 (see qi_istft)."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    C, P = int(spec.shape[0]), int(spec.shape[2])
+    dwin = rt.asarray(np.asarray(dual_win, dtype=np.float64), dt)
+    out = rt.empty((C, int(n_out)), dt)
+    nbytes = lib.qi_istft_workspace_bytes(C, P, int(nperseg), DTYPE_CODE[dt])
+    ws = rt.workspace(nbytes)
+    rc = lib.qi_istft(rt.ptr(spec), C, P, rt.ptr(dwin), int(nperseg), int(hop), int(nfft), int(roll), int(first_start),
+                      int(frame_lo), int(frame_hi), int(k0), int(n_out), DTYPE_CODE[dt], rt.ptr(out), rt.ptr(ws), nbytes,
+                      rt.stream())
+    _lib.check(lib, rc, "qi_istft")
+    return out
 
 
 def power_reduce(power, dt, rows=False, cols=False, total=False, maximum=False, rt=None):
@@ -202,12 +219,13 @@ def rfft(sig, dt, rt=None):
 
 
 def abs_log2(buf, dt, is_complex, eps=EPS64, square=False, rt=None, signed=False):
-    """log2(|x| + eps) (utilities/rescaling.py:13-20) or |x|^2 when square=True, elementwise on the device."""
+    """log2(|x| + eps) (utilities/rescaling.py:13-20), |x|^2 + eps when square=True (1) or |x| + eps when square=2,
+    elementwise on the device."""
     rt = rt or get_runtime()
     lib = rt.lib
     n = int(np.prod(buf.shape))
     out = rt.empty(buf.shape, dt)
-    rc = lib.qi_abs_log2(rt.ptr(buf), n, DTYPE_CODE[dt], 2 if signed else (1 if is_complex else 0), 1 if square else 0, float(eps),
+    rc = lib.qi_abs_log2(rt.ptr(buf), n, DTYPE_CODE[dt], 2 if signed else (1 if is_complex else 0), int(square), float(eps),
                          rt.ptr(out), rt.stream())
     _lib.check(lib, rc, "qi_abs_log2")
     return out

@@ -12,7 +12,7 @@ import numpy as np
 
 QI_F32, QI_F64 = 0, 1
 QI_CONV_LINEAR_SAME, QI_CONV_CIRC_CORR = 0, 1
-QI_ABI_VERSION = 1
+QI_ABI_VERSION = 2
 QI_N_CATEGORIES = 7
 CATEGORY_NAMES = ("fft_fwd", "inv_first", "inv_mid", "inv_last", "info", "stft", "other")
 
@@ -50,7 +50,10 @@ SIGNATURES = {
     "qi_stx_fft": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int,
                             _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int, _c_vp]),
     "qi_stft": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_int, _c_dbl, _c_int,
-                         _c_int, _c_vp, _c_vp, _c_vp]),
+                         _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
+    "qi_istft_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int, _c_int]),
+    "qi_istft": (_c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_i64,
+                          _c_i64, _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
     "qi_power_reduce": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "qi_shannon": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_vp, _c_dbl, _c_dbl,
                             _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),

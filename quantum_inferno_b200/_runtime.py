@@ -57,7 +57,10 @@ class CudaRuntime:
 
     def asarray(self, x, dtype):
         """numpy / torch (any device) -> contiguous tensor of `dtype` on this device."""
-        t = x if isinstance(x, self.torch.Tensor) else self.torch.from_numpy(np.ascontiguousarray(x))
+        if not isinstance(x, self.torch.Tensor):
+            x = np.ascontiguousarray(x)
+            x = self.torch.from_numpy(x if x.flags.writeable else x.copy())    # read-only arrays (npz, scipy windows)
+        t = x
         return t.to(device=self.device, dtype=self._tdtype(dtype), non_blocking=True).contiguous()
 
     def ptr(self, buf):

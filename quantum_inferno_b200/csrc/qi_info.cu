@@ -183,13 +183,13 @@ abs_log2_kernel(const T* __restrict__ in, i64 n, int is_complex, int square, dou
     } else if (is_complex) {
         const cplx<T> v = reinterpret_cast<const cplx<T>*>(in)[i];
         mag2 = v.re * v.re + v.im * v.im;
-        mag = square ? (T)0 : (T)hypot(v.re, v.im);
+        mag = square == 1 ? (T)0 : (T)hypot(v.re, v.im);
     } else {
         const T v = in[i];
         mag2 = v * v;
         mag = v < (T)0 ? -v : v;
     }
-    out[i] = square ? mag2 + (T)eps : log2(mag + (T)eps);
+    out[i] = square == 1 ? mag2 + (T)eps : (square == 2 ? mag + (T)eps : log2(mag + (T)eps));
 }
 
 static unsigned splits_for(i64 Tn, i64 rows) {

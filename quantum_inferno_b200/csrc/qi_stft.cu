@@ -5,7 +5,8 @@
 // the per-frame mean removed, the periodic window applied, one radix-8 tile FFT run, the two spectra
 // separated with the Hermitian split and the one-sided bins stored with time as the fastest axis (the
 // layout scipy returns).  Replaces scipy.signal.stft / welch as called by
-// quantum_inferno/styx_fft.py:175-187, :215-227, :254-266.
+// quantum_inferno/styx_fft.py:175-187, :215-227, :254-266, and scipy.signal.ShortTimeFFT.stft_detrend / spectrogram /
+// istft as called by quantum_inferno/utilities/short_time_fft.py:64-175.
 #include "qi_fft.cuh"
 #include "qi_host.h"
 #include "qi_reduce.cuh"
@@ -14,7 +15,7 @@ namespace qi {
 
 struct StftGeom {
     i64 n_points, sig_stride, n_frames;
-    int nperseg, hop, logF, pad_left, TC, detrend;
+    int nperseg, hop, logF, pad_left, TC, detrend, roll;
     double scale;
 };
 
@@ -86,8 +87,12 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
         const int k = active ? idx / TC : 0;
         const cplx<T> z1 = tile[(int)brev_bits((unsigned)k, g.logF) * TP + c];
         const cplx<T> z2 = tile[(int)brev_bits((unsigned)((R - k) & (R - 1)), g.logF) * TP + c];
-        const cplx<T> xa = mk<T>((T)0.5 * (z1.re + z2.re), (T)0.5 * (z1.im - z2.im));
-        const cplx<T> xb = mk<T>((T)0.5 * (z1.im + z2.im), (T)-0.5 * (z1.re - z2.re));
+        cplx<T> xa = mk<T>((T)0.5 * (z1.re + z2.re), (T)0.5 * (z1.im - z2.im));
+        cplx<T> xb = mk<T>((T)0.5 * (z1.im + z2.im), (T)-0.5 * (z1.re - z2.re));
+        if (g.roll) {               // segment rotated left by roll samples: bin k times exp(+2 pi i k roll / nfft)
+            const cplx<T> ph = unit_root<T>((unsigned long long)(((i64)k * g.roll) & (R - 1)), g.logF);
+            xa = xa * ph; xb = xb * ph;
+        }
         const i64 fa = frame0 + 2 * c;
         if (out && active) {
             cplx<T>* o = out + (chan * K + k) * g.n_frames + fa;
@@ -107,8 +112,8 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
 
 template <typename T>
 static int stft_impl(const void* sig, i64 C, i64 n_points, i64 stride, const void* window, int nperseg, int hop,
-                     int nfft, i64 n_frames, int pad_left, double scale, int detrend, void* out, double* psd_acc,
-                     cudaStream_t st) {
+                     int nfft, i64 n_frames, int pad_left, double scale, int detrend, int roll, void* out,
+                     double* psd_acc, cudaStream_t st) {
     int logF = 0;
     while ((1 << logF) < nfft) ++logF;
     if ((1 << logF) != nfft) return QI_ERR_ARG;
@@ -123,6 +128,7 @@ static int stft_impl(const void* sig, i64 C, i64 n_points, i64 stride, const voi
     StftGeom g;
     g.n_points = n_points; g.sig_stride = stride; g.n_frames = n_frames;
     g.nperseg = nperseg; g.hop = hop; g.logF = logF; g.pad_left = pad_left; g.TC = TC; g.detrend = detrend;
+    g.roll = ((roll % nfft) + nfft) % nfft;
     g.scale = scale;
     if (C > 65535) return QI_ERR_UNSUPPORTED;
     dim3 grid((unsigned)((n_frames + 2 * TC - 1) / (2 * TC)), (unsigned)C);
@@ -137,10 +143,137 @@ static int stft_impl(const void* sig, i64 C, i64 n_points, i64 stride, const voi
     return check_cuda("qi_stft");
 }
 
+// ---------------------------------------------------------------- inverse STFT
+// (1) per CTA 2*TC frames of one channel: the one-sided spectra of two frames are combined into one Hermitian-
+//     completed complex spectrum Z = Xa + i Xb (rows in bit-reversed order), one inverse tile FFT gives frame a in the
+//     real and frame b in the imaginary part; times the dual window -> slices[chan][frame][nperseg].
+// (2) overlap-add as a gather: every output sample sums the <= ceil(nperseg/hop) slices that cover it, in ascending
+//     frame order (the order of scipy's loop).
+struct IstftGeom {
+    i64 n_frames, first_start, frame_lo, frame_hi, k0, n_out;
+    int nperseg, hop, logF, TC, roll;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(512)
+istft_frames_kernel(const cplx<T>* __restrict__ S, const T* __restrict__ dual_win, IstftGeom g, T* __restrict__ slices) {
+    QI_DYN_SMEM(smem_raw);
+    const int R = 1 << g.logF;
+    const int TC = g.TC, TP = TC + 1;
+    cplx<T>* tile = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* tw = tile + (size_t)R * TP;
+    const i64 chan = blockIdx.y;
+    const i64 frame0 = (i64)blockIdx.x * (2 * TC);
+    const int K = (R >> 1) + 1;
+    fill_twiddles<T>(tw, g.logF);
+    for (int idx = threadIdx.x; idx < K * TC; idx += blockDim.x) {        // lanes along the frames (fastest axis of S)
+        const int c = idx % TC;
+        const int k = idx / TC;
+        const i64 fa = frame0 + 2 * c, fb = fa + 1;
+        cplx<T> xa = mk<T>((T)0, (T)0), xb = xa;
+        if (fa < g.n_frames) xa = S[(chan * K + k) * g.n_frames + fa];
+        if (fb < g.n_frames) xb = S[(chan * K + k) * g.n_frames + fb];
+        if (g.roll) {               // undo the rotation of the forward transform: bin k times exp(-2 pi i k roll / nfft)
+            const cplx<T> ph = conj(unit_root<T>((unsigned long long)(((i64)k * g.roll) & (R - 1)), g.logF));
+            xa = xa * ph; xb = xb * ph;
+        }
+        if (k == 0 || k == R / 2) {                                        // irfft ignores these imaginary parts
+            tile[(int)brev_bits((unsigned)k, g.logF) * TP + c] = mk<T>(xa.re, xb.re);
+        } else {
+            tile[(int)brev_bits((unsigned)k, g.logF) * TP + c] = mk<T>(xa.re - xb.im, xa.im + xb.re);
+            tile[(int)brev_bits((unsigned)(R - k), g.logF) * TP + c] = mk<T>(xa.re + xb.im, xb.re - xa.im);
+        }
+    }
+    __syncthreads();
+    tile_fft<T, FFT_INV>(tile, tw, g.logF, TC, TP);
+    const T inv = (T)(1.0 / (double)R);
+    for (int idx = threadIdx.x; idx < g.nperseg * TC; idx += blockDim.x) {  // lanes along the samples of a slice
+        const int n = idx % g.nperseg;
+        const int c = idx / g.nperseg;
+        const i64 fa = frame0 + 2 * c;
+        const cplx<T> v = tile[n * TP + c];
+        const T w = dual_win[n] * inv;
+        if (fa < g.n_frames) slices[(chan * g.n_frames + fa) * g.nperseg + n] = v.re * w;
+        if (fa + 1 < g.n_frames) slices[(chan * g.n_frames + fa + 1) * g.nperseg + n] = v.im * w;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+istft_ola_kernel(const T* __restrict__ slices, IstftGeom g, T* __restrict__ out) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n_out) return;
+    const i64 chan = blockIdx.y;
+    const i64 k = g.k0 + i;
+    // frames p with first_start + p*hop <= k < first_start + p*hop + nperseg
+    const i64 d = k - g.first_start;
+    i64 p_hi = d >= 0 ? d / g.hop : -((-d + g.hop - 1) / g.hop);                       // floor(d / hop)
+    const i64 e = d - (g.nperseg - 1);
+    i64 p_lo = e > 0 ? (e + g.hop - 1) / g.hop : -((-e) / g.hop);                      // ceil(e / hop)
+    if (p_lo < g.frame_lo) p_lo = g.frame_lo;
+    if (p_hi > g.frame_hi - 1) p_hi = g.frame_hi - 1;
+    T acc = (T)0;
+    for (i64 p = p_lo; p <= p_hi; ++p)
+        acc += slices[(chan * g.n_frames + p) * g.nperseg + (d - p * g.hop)];
+    out[chan * g.n_out + i] = acc;
+}
+
+template <typename T>
+static int istft_impl(const void* S, i64 C, i64 P, const void* dual_win, int nperseg, int hop, int nfft, int roll,
+                      i64 first_start, i64 frame_lo, i64 frame_hi, i64 k0, i64 n_out, void* out, void* ws,
+                      cudaStream_t st) {
+    int logF = 0;
+    while ((1 << logF) < nfft) ++logF;
+    if ((1 << logF) != nfft) return QI_ERR_ARG;
+    size_t budget = 100 * 1024;
+    int TC = 16;
+    auto need = [&](int tc) { return ((size_t)nfft * (tc + 2)) * sizeof(cplx<T>) + 64; };
+    while (TC > 2 && need(TC) > budget) TC >>= 1;
+    if (need(TC) > budget) { budget = 200 * 1024; while (TC > 1 && need(TC) > budget) TC >>= 1; }
+    if (need(TC) > budget) return QI_ERR_UNSUPPORTED;
+    if (C > 65535) return QI_ERR_UNSUPPORTED;
+    IstftGeom g;
+    g.n_frames = P; g.first_start = first_start; g.frame_lo = frame_lo; g.frame_hi = frame_hi; g.k0 = k0; g.n_out = n_out;
+    g.nperseg = nperseg; g.hop = hop; g.logF = logF; g.TC = TC; g.roll = ((roll % nfft) + nfft) % nfft;
+    const size_t smem = need(TC);
+#ifndef QI_EMUL
+    cudaFuncSetAttribute(istft_frames_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    prof_set_category(QI_CAT_STFT);
+    dim3 grid((unsigned)((P + 2 * TC - 1) / (2 * TC)), (unsigned)C);
+    QI_LAUNCH((istft_frames_kernel<T>), grid, dim3(512), smem, st, static_cast<const cplx<T>*>(S),
+              static_cast<const T*>(dual_win), g, static_cast<T*>(ws));
+    dim3 grid2((unsigned)((n_out + 255) / 256), (unsigned)C);
+    QI_LAUNCH((istft_ola_kernel<T>), grid2, dim3(256), 0, st, static_cast<const T*>(ws), g, static_cast<T*>(out));
+    return check_cuda("qi_istft");
+}
+
 }  // namespace qi
 
+extern "C" size_t qi_istft_workspace_bytes(int64_t C, int64_t n_frames, int nperseg, int dtype) {
+    if (C <= 0 || n_frames <= 0 || nperseg <= 0) return 0;
+    return (size_t)C * (size_t)n_frames * (size_t)nperseg * (dtype == QI_F64 ? 8 : 4);
+}
+
+extern "C" int qi_istft(const void* S, int64_t C, int64_t n_frames, const void* dual_win, int nperseg, int hop, int nfft,
+                        int roll, int64_t first_start, int64_t frame_lo, int64_t frame_hi, int64_t k0, int64_t n_out,
+                        int dtype, void* out, void* ws, size_t ws_bytes, void* stream) {
+    if (!S || !dual_win || !out || !ws || C <= 0 || n_frames <= 0 || nperseg <= 0 || hop <= 0 || nfft < nperseg ||
+        n_out <= 0 || frame_lo < 0 || frame_hi > n_frames || frame_lo >= frame_hi)
+        return QI_ERR_ARG;
+    if (ws_bytes < qi_istft_workspace_bytes(C, n_frames, nperseg, dtype)) return QI_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == QI_F32)
+        return qi::istft_impl<float>(S, C, n_frames, dual_win, nperseg, hop, nfft, roll, first_start, frame_lo, frame_hi,
+                                     k0, n_out, out, ws, st);
+    if (dtype == QI_F64)
+        return qi::istft_impl<double>(S, C, n_frames, dual_win, nperseg, hop, nfft, roll, first_start, frame_lo,
+                                      frame_hi, k0, n_out, out, ws, st);
+    return QI_ERR_ARG;
+}
+
 extern "C" int qi_stft(const void* sig, int64_t C, int64_t n_points, int64_t stride, const void* window, int nperseg,
-                       int hop, int nfft, int64_t n_frames, int pad_left, double scale, int detrend, int dtype,
+                       int hop, int nfft, int64_t n_frames, int pad_left, double scale, int detrend, int roll, int dtype,
                        void* out, double* psd_acc, void* stream) {
     if (!sig || !window || C <= 0 || n_points <= 0 || nperseg <= 0 || hop <= 0 || nfft < nperseg || n_frames <= 0)
         return QI_ERR_ARG;
@@ -148,9 +281,9 @@ extern "C" int qi_stft(const void* sig, int64_t C, int64_t n_points, int64_t str
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == QI_F32)
         return qi::stft_impl<float>(sig, C, n_points, stride, window, nperseg, hop, nfft, n_frames, pad_left, scale,
-                                    detrend, out, psd_acc, st);
+                                    detrend, roll, out, psd_acc, st);
     if (dtype == QI_F64)
         return qi::stft_impl<double>(sig, C, n_points, stride, window, nperseg, hop, nfft, n_frames, pad_left, scale,
-                                     detrend, out, psd_acc, st);
+                                     detrend, roll, out, psd_acc, st);
     return QI_ERR_ARG;
 }

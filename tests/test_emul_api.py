@@ -213,3 +213,37 @@ def test_multirate_method_selection():
     # non power-of-two records silently use the exact method under 'auto'
     c = cwt_entropy.cwt_power_entropy(3, x[:3000], FS, dtype="float32")
     assert c.power.shape == (1, len(c.frequency_hz), 3000)
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 2e-5)])
+def test_short_time_fft_tukey(golden, dtype, tol):
+    """Drop-in utilities/short_time_fft: kernels (gather, detrend, window, FFT, phase rotation; inverse FFT pairs, dual
+    window, overlap-add) against the reference's outputs."""
+    from scipy.signal import ShortTimeFFT as ScipyShortTimeFFT
+    from quantum_inferno_b200.utilities import short_time_fft as stf
+    g = golden("stft_tukey")
+    x = g["x"]
+    for i, (m, ov, alpha) in enumerate(g["cases"]):
+        scal = None if str(g["case_scaling"][i]) == "none" else str(g["case_scaling"][i])
+        pad = str(g["case_padding"][i])
+        f, t, mag = stf.stft_tukey(x, FS, alpha, int(m), int(ov), scal, pad, dtype=dtype)
+        assert np.array_equal(f, g[f"c{i}_f"]) and np.array_equal(t, g[f"c{i}_t"])
+        assert mag.shape == g[f"c{i}_mag"].shape and rel(mag, g[f"c{i}_mag"]) < tol
+        _, _, sp = stf.spectrogram_tukey(x, FS, alpha, int(m), int(ov), scal, pad, dtype=dtype)
+        assert rel(sp, g[f"c{i}_sp"]) < tol
+        obj = stf.get_stft_object_tukey(FS, alpha, int(m), int(ov), scal, dtype=dtype)
+        assert isinstance(obj, ScipyShortTimeFFT) and obj.invertible and obj.fft_mode == "onesided"
+        assert rel(obj.stft(x), g[f"c{i}_spec"]) < tol
+        ts, xr = stf.istft_tukey(g[f"c{i}_spec"], FS, alpha, int(m), int(ov), scal, dtype=dtype)
+        assert np.array_equal(ts, g[f"c{i}_ts"]) and xr.shape == g[f"c{i}_xr"].shape
+        assert np.max(np.abs(xr - g[f"c{i}_xr"])) < (1e-14 if dtype == "float64" else 2e-5)
+    # the reference's own tests (quantum_inferno/tests/utilities/test_short_time_fft.py:17-66)
+    nd = int(g["fft_nd"])
+    obj = stf.get_stft_object_tukey(FS, 0.25, nd, nd // 2, "magnitude")
+    assert (obj.scaling, obj.m_num, obj.mfft, obj.hop) == ("magnitude", nd, nd, nd // 2) and obj.delta_f == FS / nd
+    ts, xr = stf.istft_tukey(obj.stft(x), FS, 0.25, nd, nd // 2, "magnitude")
+    assert len(xr) == len(x) and np.allclose(x, xr, atol=1e-14) and np.allclose(ts, np.arange(len(x)) / FS, atol=1e-14)
+    batch = np.stack([x, x[::-1]])
+    assert rel(obj.stft(batch)[1], obj.stft(x[::-1].copy())) < 1e-15
+    with pytest.raises(NotImplementedError):
+        obj.stft_detrend(x, "linear")

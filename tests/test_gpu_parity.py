@@ -351,3 +351,40 @@ def test_fft_roundtrip_large(torch_cuda):
         back = torch.empty_like(xc)
         _lib.check(rt.lib, rt.lib.qi_fft_c2c(spec.data_ptr(), back.data_ptr(), 2, log2n, 1, code, rt.stream()), "ifft")
         assert float((back - xc).abs().max() / xc.abs().max()) < tol * 10
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 2e-5)])
+def test_short_time_fft_tukey(torch_cuda, golden, dtype, tol):
+    """utilities/short_time_fft drop-in against the reference's outputs + the reference's own
+    round-trip test (quantum_inferno/tests/utilities/test_short_time_fft.py:47-66)."""
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200.utilities import short_time_fft as stf
+    g = golden("stft_tukey")
+    x = g["x"]
+    for i, (m, ov, alpha) in enumerate(g["cases"]):
+        scal = None if str(g["case_scaling"][i]) == "none" else str(g["case_scaling"][i])
+        pad = str(g["case_padding"][i])
+        f, t, mag = stf.stft_tukey(x, FS, alpha, int(m), int(ov), scal, pad, dtype=dtype)
+        assert np.array_equal(f, g[f"c{i}_f"]) and np.array_equal(t, g[f"c{i}_t"])
+        assert mag.shape == g[f"c{i}_mag"].shape and rel(mag, g[f"c{i}_mag"]) < tol
+        _, _, sp = stf.spectrogram_tukey(x, FS, alpha, int(m), int(ov), scal, pad, dtype=dtype)
+        assert rel(sp, g[f"c{i}_sp"]) < tol
+        obj = stf.get_stft_object_tukey(FS, alpha, int(m), int(ov), scal, dtype=dtype)
+        assert rel(obj.stft(x), g[f"c{i}_spec"]) < tol
+        ts, xr = stf.istft_tukey(g[f"c{i}_spec"], FS, alpha, int(m), int(ov), scal, dtype=dtype)
+        assert np.array_equal(ts, g[f"c{i}_ts"]) and xr.shape == g[f"c{i}_xr"].shape
+        assert np.max(np.abs(xr - g[f"c{i}_xr"])) < (1e-14 if dtype == "float64" else 2e-5)
+    nd = int(g["fft_nd"])
+    obj = stf.get_stft_object_tukey(FS, 0.25, nd, nd // 2, "magnitude")
+    ts, xr = stf.istft_tukey(obj.stft(x), FS, 0.25, nd, nd // 2, "magnitude")
+    assert len(xr) == len(x) and np.allclose(x, xr, atol=1e-14)
+    # a larger batch against the oracle: 4 channels x 2^18 samples, CUDA tensors in -> CUDA tensors out
+    torch = torch_cuda
+    xb = np.stack([synth(1 << 18, chan=c) for c in range(4)])
+    f, t, mag = stf.stft_tukey(torch.from_numpy(xb).cuda(), FS, 0.25, 1024, 512, dtype=dtype)
+    assert mag.is_cuda and tuple(mag.shape) == (4, 513, (1 << 18) // 512 + 1)
+    for c in (0, 3):
+        assert rel(mag[c].double().cpu().numpy(), orc.stft_tukey(xb[c], FS, 0.25, 1024, 512)[2]) < tol
+    spec = stf.get_stft_object_tukey(FS, 0.25, 1024, 512, dtype=dtype).stft(torch.from_numpy(xb).cuda())
+    ts, xr = stf.istft_tukey(spec, FS, 0.25, 1024, 512, dtype=dtype)
+    assert np.max(np.abs(xr.double().cpu().numpy() - xb[:, :xr.shape[-1]])) < (1e-13 if dtype == "float64" else 2e-5)

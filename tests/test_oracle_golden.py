@@ -140,3 +140,26 @@ def test_tfr_info(golden):
     assert rel(ff.sig, g["fft_sig"]) < 1e-14 and rel(ff.marginal, g["fft_marg"]) < 1e-13
     assert np.max(np.abs(ff.info - g["fft_info"])) < 1e-10
     assert np.max(np.abs(ff.angle_rads - g["fft_angle"])) < 1e-9
+
+
+def test_short_time_fft_tukey(golden):
+    """utilities/short_time_fft.py: restatement of scipy's ShortTimeFFT vs the reference's outputs,
+    all four padding modes, the three scalings, odd hop/window combinations, and the reference's own round-trip test
+    (quantum_inferno/tests/utilities/test_short_time_fft.py:47-66, atol 1e-14)."""
+    g = golden("stft_tukey")
+    x = g["x"]
+    for i, (m, ov, alpha) in enumerate(g["cases"]):
+        scal = None if str(g["case_scaling"][i]) == "none" else str(g["case_scaling"][i])
+        pad = str(g["case_padding"][i])
+        f, t, mag = orc.stft_tukey(x, FS, alpha, int(m), int(ov), scal, pad)
+        assert np.array_equal(f, g[f"c{i}_f"]) and np.array_equal(t, g[f"c{i}_t"])
+        assert mag.shape == g[f"c{i}_mag"].shape and rel(mag, g[f"c{i}_mag"]) < 1e-13
+        _, _, sp = orc.spectrogram_tukey(x, FS, alpha, int(m), int(ov), scal, pad)
+        assert rel(sp, g[f"c{i}_sp"]) < 1e-13
+        ts, xr = orc.istft_tukey(g[f"c{i}_spec"], FS, alpha, int(m), int(ov), scal)
+        assert np.array_equal(ts, g[f"c{i}_ts"]) and xr.shape == g[f"c{i}_xr"].shape
+        assert np.max(np.abs(xr - g[f"c{i}_xr"])) < 1e-14
+    # the reference's shape assertions (test_short_time_fft.py:35-45) and round trip on the first case
+    nd = int(g["fft_nd"])
+    assert g["c0_mag"].shape == (nd // 2 + 1, len(x) // (nd // 2) + 1)
+    assert np.allclose(x[:len(g["c0_xr"])], g["c0_xr"], atol=1e-14)

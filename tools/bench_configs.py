@@ -111,6 +111,27 @@ def cfg5():
             "cells_per_s": cells / ms * 1e3}
 
 
+def cfg6():
+    """utilities/short_time_fft on the config-2 shape (64 x 2^20, Tukey 1024/512): |STFT| of the
+    detrended slices, and the complex STFT -> inverse STFT round trip."""
+    from quantum_inferno_b200.utilities import short_time_fft as stf
+    x = synth_batch_torch(torch, 1 << 20, list(range(64)), DEV)
+    out = {"config": "cfg6: stft_tukey / istft_tukey 1024/512, 64 x 2^20"}
+    for dt, xx in (("float32", x), ("float64", x.double())):
+        es = 4 if dt == "float32" else 8
+        ms, (f, t, mag) = timed(lambda: stf.stft_tukey(xx, FS, 0.25, 1024, 512, dtype=dt))
+        cells = mag.numel()
+        obj = stf.get_stft_object_tukey(FS, 0.25, 1024, 512, dtype=dt)
+        spec = obj.stft(xx)
+        ms_i, (ts, xr) = timed(lambda: stf.istft_tukey(spec, FS, 0.25, 1024, 512, dtype=dt))
+        err = float((xr - xx[:, :xr.shape[-1]]).abs().max())
+        out[dt] = {"stft_tukey_ms": ms, "cells_per_s": cells / ms * 1e3,
+                   "stft_alg_GBps": (cells * es + xx.numel() * es) / ms / 1e6,
+                   "istft_ms": ms_i, "istft_alg_GBps": (spec.numel() * 2 * es + xr.numel() * es) / ms_i / 1e6,
+                   "round_trip_max_abs_err": err}
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg1", "cfg2", "cfg3", "cfg4"]
     for name in which:
