@@ -160,7 +160,11 @@ mr_level_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __r
     __syncthreads();
     tile_fft<float, FFT_FWD>(tile_x, tw, g.logF, TC, TP);
 
-    for (int bi = 0; bi < g.band_count; ++bi) {
+    // grid.z splits the level's bands over CTAs (each repeats the cheap forward transform): the deepest level is one
+    // block per channel with a dozen bands, which would otherwise be a dozen serial inverse FFTs on 8 SMs
+    const int per_z = (g.band_count + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int bi_end = min(g.band_count, ((int)blockIdx.z + 1) * per_z);
+    for (int bi = (int)blockIdx.z * per_z; bi < bi_end; ++bi) {
         const int b = g.band_first + bi;
         const MrDevBand band = bands[b];
         const cplx<float>* K = tables + band.table_off;
@@ -464,7 +468,9 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
                       (const cplx<float>*)tables, (const float4*)tw2k, wbuf, out_power, out_complex, sum_dst, (int)ppc);
             continue;
         }
-        dim3 grid((unsigned)((g.n_blocks + g.TC - 1) / g.TC), (unsigned)C);
+        const i64 gx = (g.n_blocks + g.TC - 1) / g.TC;
+        const int gz = gx * C < 148 ? g.band_count : 1;           // few blocks: spread the bands instead
+        dim3 grid((unsigned)gx, (unsigned)C, (unsigned)gz);
         const size_t smem = ((size_t)F * (g.TC + 1) * 2 + F) * sizeof(cplx<float>) + 256;
 #ifndef QI_EMUL
         cudaFuncSetAttribute(mr_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
