@@ -443,8 +443,21 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
         QI_LAUNCH(mr_decimate_kernel, grid, dim3(256), 0, st, src, src_stride, src_len, l == 1 ? 0 : MR_HALO,
                   pyr + pl.lvl_off[l], pl.pyr_per_chan, pl.lvl_len[l], taps);
     }
-    // A: level convolutions (deepest first; level 0 last so its epilogue traffic is contiguous in time)
+    // A: level convolutions (deepest first; level 0 last so its epilogue traffic is contiguous in time).  Levels >= 1
+    // whose grids are only a few CTAs are collected into merged launches.
     int level0_first = 0, level0_count = 0;
+    MrMultiLevel multi;
+    multi.n = 0;
+    auto flush_multi = [&]() {
+        if (!multi.n) return;
+        prof_set_category(QI_CAT_INV_FIRST);
+#ifndef QI_EMUL
+        cudaFuncSetAttribute(mr_level2k_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2K_SMEM);
+#endif
+        QI_LAUNCH(mr_level2k_multi_kernel, dim3((unsigned)multi.cta_end[multi.n - 1], (unsigned)C), dim3(L2K_THREADS),
+                  L2K_SMEM, st, multi, (const MrDevBand*)d_bands, (const cplx<float>*)tables, (const float4*)tw2k, wbuf);
+        multi.n = 0;
+    };
     for (const MrLevelGeom& g0 : pl.levels) {
         if (g0.level == 0) { level0_first = g0.band_first; level0_count = g0.band_count; }
         if (!do_front) continue;
@@ -460,7 +473,16 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
             const i64 pairs = (g.n_blocks + 1) / 2;
             i64 ppc = pairs * C / (148 * 2 * 8);
             ppc = ppc < 1 ? 1 : (ppc > 4 ? 4 : ppc);
-            dim3 grid2((unsigned)((pairs + ppc - 1) / ppc), (unsigned)C);
+            const i64 ctas = (pairs + ppc - 1) / ppc;
+            if (g.level > 0 && ctas * C <= 148 * 2) {            // less than one wave: goes into a merged launch
+                const int i = multi.n++;
+                multi.g[i] = g; multi.x[i] = x; multi.sum[i] = sum_dst; multi.ppc[i] = (int)ppc;
+                multi.cta_end[i] = (i ? multi.cta_end[i - 1] : 0) + (int)ctas;
+                if (multi.n == L2K_MULTI) flush_multi();
+                continue;
+            }
+            flush_multi();
+            dim3 grid2((unsigned)ctas, (unsigned)C);
 #ifndef QI_EMUL
             cudaFuncSetAttribute(mr_level2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2K_SMEM);
 #endif
@@ -478,6 +500,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
         QI_LAUNCH(mr_level_kernel, grid, dim3(1024), smem, st, x, g, (const MrDevBand*)d_bands,
                   (const cplx<float>*)tables, wbuf, out_power, out_complex, sum_dst);
     }
+    if (do_front) flush_multi();
     // E: expand -- deep bands first to level MR_LMID (1/32 of the cells), then everything to the full rate
     MrExpandArgs ea;
     ea.bands = d_bands; ea.n_bands = B; ea.n_points = N; ea.wbuf = wbuf; ea.midbuf = midbuf;

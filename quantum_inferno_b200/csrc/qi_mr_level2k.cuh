@@ -103,11 +103,11 @@ QI_DEV void l2k_stage8(float4* __restrict__ tile, int p0, const float4* __restri
     }
 }
 
-__global__ void __launch_bounds__(L2K_THREADS, 2)
-mr_level2k_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __restrict__ bands,
-                  const cplx<float>* __restrict__ tables, const float4* __restrict__ tw_g,
-                  cplx<float>* __restrict__ wbuf, float* __restrict__ out_power, cplx<float>* __restrict__ out_complex,
-                  double* __restrict__ band_sum, int pairs_per_cta) {
+// bx: index of this CTA among the CTAs of its level (blockIdx.x, or the offset inside a merged multi-level launch)
+QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const MrDevBand* __restrict__ bands,
+                     const cplx<float>* __restrict__ tables, const float4* __restrict__ tw_g,
+                     cplx<float>* __restrict__ wbuf, float* __restrict__ out_power, cplx<float>* __restrict__ out_complex,
+                     double* __restrict__ band_sum, int pairs_per_cta, int bx) {
     QI_DYN_SMEM(smem_raw);
     float4* tile0 = reinterpret_cast<float4*>(smem_raw);
     float4* tile1 = tile0 + L2K_TILE;
@@ -132,7 +132,7 @@ mr_level2k_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* _
     const int pD1 = 4 * (t + 256) + ((t + 256) >> 1);                      //               g = t + 256
 
     for (int pp = 0; pp < pairs_per_cta; ++pp) {
-        const i64 blk0 = 2 * ((i64)blockIdx.x * pairs_per_cta + pp);
+        const i64 blk0 = 2 * ((i64)bx * pairs_per_cta + pp);
         if (blk0 >= g.n_blocks) break;                                     // uniform over the CTA
         __syncthreads();                                                   // previous pair's last stage has left the tiles
         // ---- forward, stage B=2048 straight from HBM (real input, two blocks)
@@ -311,6 +311,36 @@ mr_level2k_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* _
             atomicAdd(&band_sum[chan * g.n_bands + g.band_first + t], s);
         }
     }
+}
+
+__global__ void __launch_bounds__(L2K_THREADS, 2)
+mr_level2k_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __restrict__ bands,
+                  const cplx<float>* __restrict__ tables, const float4* __restrict__ tw_g,
+                  cplx<float>* __restrict__ wbuf, float* __restrict__ out_power, cplx<float>* __restrict__ out_complex,
+                  double* __restrict__ band_sum, int pairs_per_cta) {
+    l2k_body(x, g, bands, tables, tw_g, wbuf, out_power, out_complex, band_sum, pairs_per_cta, (int)blockIdx.x);
+}
+
+// The deep levels are a few CTAs each and independent of one another: one launch runs up to L2K_MULTI of them side by
+// side instead of a chain of latency-bound launches.
+constexpr int L2K_MULTI = 8;
+struct MrMultiLevel {
+    int n;
+    int cta_end[L2K_MULTI];          // exclusive prefix sums of CTAs per level (grid.x = cta_end[n-1])
+    int ppc[L2K_MULTI];
+    MrLevelGeom g[L2K_MULTI];
+    const float* x[L2K_MULTI];
+    double* sum[L2K_MULTI];
+};
+
+__global__ void __launch_bounds__(L2K_THREADS, 2)
+mr_level2k_multi_kernel(MrMultiLevel m, const MrDevBand* __restrict__ bands, const cplx<float>* __restrict__ tables,
+                        const float4* __restrict__ tw_g, cplx<float>* __restrict__ wbuf) {
+    int li = 0;
+    while (li + 1 < m.n && (int)blockIdx.x >= m.cta_end[li]) ++li;
+    const int bx = (int)blockIdx.x - (li ? m.cta_end[li - 1] : 0);
+    const MrLevelGeom g = m.g[li];
+    l2k_body(m.x[li], g, bands, tables, tw_g, wbuf, nullptr, nullptr, m.sum[li], m.ppc[li], bx);
 }
 
 }  // namespace qi
