@@ -44,8 +44,10 @@ def launches(src, dst):
         for n, (cnt, ms) in sorted(per.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{n}` | {cnt} | {ms:.3f} | {100 * ms / tot:.1f} % |\n")
         if len(starts) >= 2:
-            s, e = starts[-2], starts[-1]
-            # one resident step = the launches between two table kernels with the largest grid
+            # one resident step = the run of launches between two table kernels with the largest total time
+            # (the end-to-end leg of the bench re-runs the step per channel group with smaller grids)
+            spans = list(zip(starts[:-1], starts[1:]))
+            s, e = max(spans, key=lambda se: sum(m[2] for m in mine[se[0]:se[1]]))
             f.write("\n## one step (launch order)\n\n| kernel | grid | ms |\n|---|---|---|\n")
             step_tot = 0.0
             for n, g, ms in mine[s:e]:
