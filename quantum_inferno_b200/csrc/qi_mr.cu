@@ -100,7 +100,7 @@ mr_table_kernel(const MrDevBand* __restrict__ bands, i64 n_points, int half_w_ca
     cplx<float>* tile = reinterpret_cast<cplx<float>*>(smem_raw);       // [F][2]
     cplx<float>* tw = tile + (size_t)F * 2;
     fill_twiddles<float>(tw, b.logF);
-    const double step = (double)(1ll << b.level);
+    const double step = (double)(1ll << b.conv_level);
     const double tmax = 0.5 * (double)(n_points - 1);
     // time support kept: 5.2 sigma (3e-6 of the peak) or the whole block half for record-long atoms
     int half_w = (int)ceil(5.2 * b.scale / step) + 1;
@@ -234,7 +234,9 @@ static HbTaps make_taps() {
     return t;
 }
 
-static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl) {
+// allow_env: bands of the levels 1 .. cap-1 may be stored as demodulated envelopes one level deeper (power / information
+// outputs only; the complex TFR needs the carrier).  The workspace query plans without it (an upper bound).
+static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl, bool allow_env = false) {
     int logN = 0;
     while ((1ll << logN) < N) ++logN;
     if ((1ll << logN) != N || logN < 13 || logN > 30) return QI_ERR_UNSUPPORTED;
@@ -287,20 +289,41 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl) {
             if (g.wk > 3072) return QI_ERR_UNSUPPORTED;
         }
         g.TC = 1;
+        // Envelope decimation.  The band output y_b at level l is analytic with support |theta - omega_l| <= 4.8/s_l, so
+        // its even samples are alias free, and times exp(-i omega_d q) they form a LOW-PASS signal at level l + 1 that
+        // the real-coefficient interpolators of E handle like any other level-(l+1) band: half the inverse FFT, half the
+        // decimated traffic, one octave less for the x2/x4 interpolators.  |.|^2 does not see the demodulation.
+        // omega_d is a multiple of 2 pi / 64 (exact phases from a 64-entry table).
+        g.env = 0;
+        std::vector<int> demod(count, 0);
+        if (allow_env && l >= 1 && l < pl.cap && g.logF == L2K_LOGF && count <= L2K_MAXB) {
+            g.env = 1;
+            for (int b = first; b < first + count; ++b) {
+                const double wc = hb[b].omega * (double)(1ll << (l + 1));             // centre at level l + 1
+                const int kd = (int)llround(wc * 64.0 / (2.0 * M_PI));
+                const double dev = fabs(wc - 2.0 * M_PI * kd / 64.0);
+                const double halfbw = 4.8 / (hb[b].scale / (double)(1ll << (l + 1)));
+                if (halfbw + dev > 0.98 * M_PI / 2.0 || wc + halfbw >= 2.0 * M_PI) g.env = 0;
+                demod[b - first] = kd & 63;
+            }
+        }
+        if (g.env) { g.q_first = -2 * MR_HALO; g.n_out = (N >> l) + 4 * MR_HALO; }
         const int V = (1 << g.logF) - g.wk;
         g.n_blocks = (g.n_out + V - 1) / V;
         pl.levels.push_back(g);
+        const int lout = l + g.env;
         for (int b = first; b < first + count; ++b) {
             MrDevBand d;
-            d.omega = hb[b].omega; d.scale = hb[b].scale; d.amp = hb[b].amp; d.level = l; d.logF = g.logF;
+            d.omega = hb[b].omega; d.scale = hb[b].scale; d.amp = hb[b].amp; d.logF = g.logF;
+            d.level = lout; d.conv_level = l; d.demod = g.env ? demod[b - first] : 0;
             d.table_off = toff; toff += (1ll << g.logF);
             d.w_off = 0; d.w_stride = 0; d.mid_off = 0; d.mid_stride = 0;
             if (l) {
-                d.w_stride = (g.n_out + 63) / 64 * 64;
+                d.w_stride = ((N >> lout) + 2 * MR_HALO + 63) / 64 * 64;
                 d.w_off = woff; woff += d.w_stride * C;
                 pl.expand_list.push_back(b);
             }
-            if (l > MR_LMID) {
+            if (lout > MR_LMID) {
                 d.mid_stride = ((N >> MR_LMID) + 2 * MR_HALO + 63) / 64 * 64;
                 d.mid_off = moff; moff += d.mid_stride * C;
                 pl.deep_list.push_back(b);
@@ -314,7 +337,7 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl) {
     pl.off_bands = o; o = align_up(o + sizeof(MrDevBand) * (size_t)B, 256);
     pl.off_list = o; o = align_up(o + sizeof(int) * (size_t)(B + 1), 256);
     pl.off_deep = o; o = align_up(o + sizeof(int) * (size_t)(B + 1), 256);
-    pl.off_tw = o; o = align_up(o + sizeof(float4) * (size_t)(4 * L2K_TWJ), 256);
+    pl.off_tw = o; o = align_up(o + sizeof(float4) * (size_t)L2K_TW_TOTAL, 256);
     pl.off_pyr = o; o = align_up(o + sizeof(float) * (size_t)pl.pyr_per_chan * C, 256);
     pl.off_tables = o; o = align_up(o + sizeof(cplx<float>) * (size_t)toff, 256);
     pl.off_w = o; o = align_up(o + sizeof(cplx<float>) * (size_t)woff, 256);
@@ -398,7 +421,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     if (fused && (!out_power || !band_sum || !band_sum_est || !total_power || out_complex)) return QI_ERR_ARG;
     if (!fused && phase != QI_MR_PHASE_ALL) return QI_ERR_ARG;
     MrPlan pl;
-    int rc = mr_plan(C, N, hb, B, pl);
+    int rc = mr_plan(C, N, hb, B, pl, /*allow_env=*/out_complex == nullptr);
     if (rc != QI_OK) return rc;
     if (ws_bytes < pl.total) return QI_ERR_WORKSPACE;
     if (C > 65535 || B > 65535) return QI_ERR_UNSUPPORTED;
@@ -432,7 +455,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
         cudaFuncSetAttribute(mr_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
         QI_LAUNCH(mr_table_kernel, dim3((unsigned)B), dim3(256), smem, st, (const MrDevBand*)d_bands, N, 2047, tables);
-        QI_LAUNCH(mr_twiddle2k_kernel, dim3((4 * L2K_TWJ + 255) / 256), dim3(256), 0, st, tw2k);
+        QI_LAUNCH(mr_twiddle2k_kernel, dim3((L2K_TW_TOTAL + 255) / 256), dim3(256), 0, st, tw2k);
     }
     // P: pyramid
     for (int l = 1; do_front && l <= pl.cap; ++l) {
@@ -467,7 +490,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
         const int F = 1 << g.logF;
         prof_set_category(g.level ? QI_CAT_INV_FIRST : QI_CAT_INV_MID);
         // level 0: exact band sums; levels 1..MR_LMID in the fused mode: raw sums for the power estimate
-        double* sum_dst = g.level == 0 ? band_sum : ((fused && g.level <= MR_LMID) ? band_sum_est : nullptr);
+        double* sum_dst = g.level == 0 ? band_sum : ((fused && g.level + g.env <= MR_LMID) ? band_sum_est : nullptr);
         if (g.logF == L2K_LOGF && g.band_count <= L2K_MAXB) {
             // 2048-point blocks: pairs of blocks per CTA, a few pairs in sequence so the twiddle copy is amortised
             const i64 pairs = (g.n_blocks + 1) / 2;
@@ -571,8 +594,10 @@ extern "C" {
 size_t qi_cwt_multirate_workspace_bytes(int64_t C, int64_t N, const QiMrBand* bands, int B) {
     if (C <= 0 || N <= 0 || B <= 0 || !bands) return 0;
     qi::MrPlan pl;
-    if (qi::mr_plan(C, N, bands, B, pl) != QI_OK) return 0;
-    return pl.total;
+    if (qi::mr_plan(C, N, bands, B, pl, false) != QI_OK) return 0;
+    qi::MrPlan pe;
+    if (qi::mr_plan(C, N, bands, B, pe, true) != QI_OK) return 0;
+    return pl.total > pe.total ? pl.total : pe.total;
 }
 
 int qi_cwt_multirate(const void* sig, int64_t C, int64_t N, int64_t stride, const QiMrBand* bands, int B,

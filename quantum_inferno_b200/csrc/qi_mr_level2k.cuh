@@ -28,21 +28,36 @@ namespace qi {
 constexpr int L2K_LOGF = 11;
 constexpr int L2K_F = 1 << L2K_LOGF;
 constexpr int L2K_TILE = L2K_F + L2K_F / 8;          // padded rows per tile buffer
-constexpr int L2K_TWJ = 256 + 32 + 4;                // twiddle rows: stage B=2048 (j<256), B=256 (j<32), B=32 (j<4)
+// twiddle rows: 2048-point stages B=2048 (j<256), B=256 (j<32), B=32 (j<4); 1024-point stages of the envelope bands
+// B=1024 (j<128), B=128 (j<16), B=16 (j<2); then 16 rows holding the 64 demodulation phases exp(-2 pi i m / 64)
 constexpr int L2K_TW0 = 0, L2K_TW1 = 256, L2K_TW2 = 288;
+constexpr int L2K_TWE0 = 292, L2K_TWE1 = 420, L2K_TWE2 = 436;
+constexpr int L2K_TWJ = 438;
+constexpr int L2K_DEMOD = 4 * L2K_TWJ;               // float4 index of the demodulation table (16 float4 = 64 phases / 2 ... see kernel)
+constexpr int L2K_TW_TOTAL = 4 * L2K_TWJ + 32;       // float4 elements in the whole table
 constexpr int L2K_MAXB = 64;                         // bands per level handled by this kernel
 constexpr int L2K_THREADS = 256;
-constexpr size_t L2K_SMEM = (size_t)(2 * L2K_TILE + 4 * L2K_TWJ) * 16 + (size_t)(L2K_THREADS / 32) * L2K_MAXB * 4;
+constexpr size_t L2K_SMEM = (size_t)(2 * L2K_TILE + L2K_TW_TOTAL) * 16 + (size_t)(L2K_THREADS / 32) * L2K_MAXB * 4;
 
 // tw[m * L2K_TWJ + row] = ( w_B^(j * brev3(2m)), w_B^(j * brev3(2m+1)) ),  w_B = exp(-2 pi i / B)
 __global__ void mr_twiddle2k_kernel(float4* __restrict__ tw) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 4 * L2K_TWJ) return;
+    if (idx >= L2K_TW_TOTAL) return;
+    if (idx >= L2K_DEMOD) {                                    // two consecutive phases per float4
+        const int m = 2 * (idx - L2K_DEMOD);
+        const cplx<float> w0 = conj(unit_root<float>((unsigned long long)m, 6));
+        const cplx<float> w1 = conj(unit_root<float>((unsigned long long)(m + 1), 6));
+        tw[idx] = make_float4(w0.re, w0.im, w1.re, w1.im);
+        return;
+    }
     const int m = idx / L2K_TWJ, row = idx % L2K_TWJ;
     int logB, j;
     if (row < L2K_TW1) { logB = 11; j = row; }
     else if (row < L2K_TW2) { logB = 8; j = row - L2K_TW1; }
-    else { logB = 5; j = row - L2K_TW2; }
+    else if (row < L2K_TWE0) { logB = 5; j = row - L2K_TW2; }
+    else if (row < L2K_TWE1) { logB = 10; j = row - L2K_TWE0; }
+    else if (row < L2K_TWE2) { logB = 7; j = row - L2K_TWE1; }
+    else { logB = 4; j = row - L2K_TWE2; }
     const cplx<float> w0 = conj(unit_root<float>((unsigned long long)(j * brev3(2 * m)), logB));
     const cplx<float> w1 = conj(unit_root<float>((unsigned long long)(j * brev3(2 * m + 1)), logB));
     tw[idx] = make_float4(w0.re, w0.im, w1.re, w1.im);
@@ -59,6 +74,7 @@ struct MrLevelGeom {
     i64 n_blocks;
     i64 x_stride, x_len;    // level signal: per-channel stride, stored length
     int x_halo;             // halo of the stored level signal (0 for level 0)
+    int env;                // every band of this level is stored as a demodulated envelope at level + 1
 };
 
 // radix-8 stage on the two columns of a float4 tile; rows base + i*H live at tile[p0 + i*STRIDE]
@@ -112,7 +128,7 @@ QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const Mr
     float4* tile0 = reinterpret_cast<float4*>(smem_raw);
     float4* tile1 = tile0 + L2K_TILE;
     float4* tw = tile1 + L2K_TILE;
-    float* wsum = reinterpret_cast<float*>(tw + 4 * L2K_TWJ);          // [warps][L2K_MAXB]
+    float* wsum = reinterpret_cast<float*>(tw + L2K_TW_TOTAL);         // [warps][L2K_MAXB]
     const int t = threadIdx.x;
     const int warp = t >> 5, lane = t & 31;
     const i64 chan = blockIdx.y;
@@ -120,7 +136,7 @@ QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const Mr
     const int half = g.wk / 2;
     const float* xs = x + chan * g.x_stride;
 
-    for (int i = t; i < 4 * L2K_TWJ; i += L2K_THREADS) tw[i] = tw_g[i];
+    for (int i = t; i < L2K_TW_TOTAL; i += L2K_THREADS) tw[i] = tw_g[i];
     for (int i = t; i < (L2K_THREADS / 32) * L2K_MAXB; i += L2K_THREADS) wsum[i] = 0.0f;
 
     // per-thread tile addresses (padded rows), fixed for the whole kernel
@@ -200,8 +216,114 @@ QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const Mr
             dif4<float, FFT_FWD>(X0[task]); dif4<float, FFT_FWD>(X1[task]);
         }
 
+        // ---- envelope bands: two bands per pass, half-size inverse transforms (see mr_plan)
+        //   fold   Z[k'] = Y[k'] + Y[k' + 1024]  <->  rows (2q, 2q+1) of the bit-reversed 2048-row spectrum add up to
+        //          row q of the bit-reversed 1024-row one: y(2m) = IFFT_1024(Z)(m)
+        //   the first (radix-2) stage of that transform joins rows (2g, 2g+1): still inside the thread that holds rows
+        //   4g .. 4g+3 of Y; then radix 8-8-8 with 128 butterflies per band, i.e. 256 = both bands of the pass
+        for (int pi = 0; g.env && pi < g.band_count; pi += 2) {
+            const int nbp = g.band_count - pi < 2 ? g.band_count - pi : 2;
+            float4* tile = ((pi >> 1) & 1) ? tile0 : tile1;
+#pragma unroll
+            for (int task = 0; task < 2; ++task) {
+                const int gq = t + 256 * task;
+                const int p = 2 * gq + (gq >> 2);                          // padded row of 2 gq in a 1024-row tile
+                for (int bb = 0; bb < nbp; ++bb) {
+                    const float4* K = reinterpret_cast<const float4*>(tables + bands[g.band_first + pi + bb].table_off);
+                    const float4 k01 = K[2 * gq], k23 = K[2 * gq + 1];
+                    const cplx<float> kk[4] = {mk<float>(k01.x, k01.y), mk<float>(k01.z, k01.w), mk<float>(k23.x, k23.y),
+                                               mk<float>(k23.z, k23.w)};
+                    const cplx<float> za0 = X0[task][0] * kk[0] + X0[task][1] * kk[1];
+                    const cplx<float> za1 = X0[task][2] * kk[2] + X0[task][3] * kk[3];
+                    const cplx<float> zc0 = X1[task][0] * kk[0] + X1[task][1] * kk[1];
+                    const cplx<float> zc1 = X1[task][2] * kk[2] + X1[task][3] * kk[3];
+                    const cplx<float> a0 = za0 + za1, a1 = za0 - za1, c0 = zc0 + zc1, c1 = zc0 - zc1;
+                    tile[bb * (L2K_TILE / 2) + p] = make_float4(a0.re, a0.im, c0.re, c0.im);
+                    tile[bb * (L2K_TILE / 2) + p + 1] = make_float4(a1.re, a1.im, c1.re, c1.im);
+                }
+            }
+            __syncthreads();
+            const int bb = t >> 7, u = t & 127;                            // band of the pass / butterfly of that band
+            const bool live = bb < nbp;
+            float4* tb = tile + bb * (L2K_TILE / 2);
+            if (live) {   // stage B=16: rows 16G + j + 2i -> 18G + j + 2i + (i >> 2)
+                const int p0 = (u >> 1) * 18 + (u & 1);
+                cplx<float> a[8], c[8];
+                float4 w[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) w[m] = tw[m * L2K_TWJ + L2K_TWE2 + (u & 1)];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const float4 v = tb[p0 + 2 * s + (s >> 2)];
+                    cplx<float> va = mk<float>(v.x, v.y), vb = mk<float>(v.z, v.w);
+                    if (s) {
+                        const float4 ww = w[s >> 1];
+                        const cplx<float> tt = (s & 1) ? mk<float>(ww.z, ww.w) : mk<float>(ww.x, ww.y);
+                        va = mul_conj(va, tt); vb = mul_conj(vb, tt);
+                    }
+                    a[s] = va; c[s] = vb;
+                }
+                dit8<float, FFT_INV>(a); dit8<float, FFT_INV>(c);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) tb[p0 + 2 * i + (i >> 2)] = make_float4(a[i].re, a[i].im, c[i].re, c[i].im);
+            }
+            __syncthreads();
+            if (live) {   // stage B=128: rows 128G + j + 16i -> 144G + j + (j >> 3) + 18i
+                const int j = u & 15;
+                l2k_stage8<FFT_INV, 18>(tb, (u >> 4) * 144 + j + (j >> 3), tw, L2K_TWE1 + j);
+            }
+            __syncthreads();
+            if (live) {   // stage B=1024: rows j + 128i -> j + (j >> 3) + 144i; outputs m = u + 128 i leave from registers
+                cplx<float> a[8], c[8];
+                float4 w[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) w[m] = tw[m * L2K_TWJ + L2K_TWE0 + u];
+                const int p0 = u + (u >> 3);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const float4 v = tb[p0 + 144 * s];
+                    cplx<float> va = mk<float>(v.x, v.y), vb = mk<float>(v.z, v.w);
+                    if (s) {
+                        const float4 ww = w[s >> 1];
+                        const cplx<float> tt = (s & 1) ? mk<float>(ww.z, ww.w) : mk<float>(ww.x, ww.y);
+                        va = mul_conj(va, tt); vb = mul_conj(vb, tt);
+                    }
+                    a[s] = va; c[s] = vb;
+                }
+                dit8<float, FFT_INV>(a); dit8<float, FFT_INV>(c);
+                const int b = g.band_first + pi + bb;
+                const MrDevBand band = bands[b];
+                const cplx<float>* dm = reinterpret_cast<const cplx<float>*>(tw + L2K_DEMOD);   // exp(-2 pi i m / 64)
+                const int Vh = V >> 1, hh = half >> 1;
+                const i64 n_w = (g.n_level >> 1) + 2 * MR_HALO;              // stored samples of w at level + 1
+                float acc = 0.0f;
+#pragma unroll
+                for (int col = 0; col < 2; ++col) {
+                    const i64 blk = blk0 + col;
+                    if (blk >= g.n_blocks) break;
+                    const cplx<float>* y = col ? c : a;
+                    cplx<float>* wdst = wbuf + band.w_off + chan * band.w_stride;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int mm = u + 128 * i - hh;
+                        const i64 wi = blk * Vh + mm;                       // index into w (halo included): q' = wi - HALO
+                        if (mm >= 0 && mm < Vh && wi < n_w) {
+                            const i64 q = wi - MR_HALO;
+                            const cplx<float> e = y[i] * dm[(int)((band.demod * q) & 63)];
+                            wdst[wi] = e;
+                            if (q >= 0 && q < (g.n_level >> 1)) acc += norm2(e);
+                        }
+                    }
+                }
+                if (band_sum) {
+                    acc = warp_sum(acc);
+                    if (lane == 0) wsum[warp * L2K_MAXB + pi + bb] += acc;
+                }
+            }
+        }
+
         // ---- bands
-        for (int bi = 0; bi < g.band_count; ++bi) {
+        for (int bi = 0; !g.env && bi < g.band_count; ++bi) {
             const int b = g.band_first + bi;
             const MrDevBand band = bands[b];
             const float4* K = reinterpret_cast<const float4*>(tables + band.table_off);
