@@ -13,6 +13,8 @@
 //                   memory.  Level-0 bands go straight to |.|^2 -> power rows (+ exact fp64 band sums); deeper bands
 //                   leave their decimated complex output w_b (8 B per 2^l cells) in HBM, together with the raw sum
 //                   of |w_b|^2 that the band-power estimate needs.
+//                   With power / information outputs the bands of levels 1 .. cap-1 are stored as demodulated
+//                   ENVELOPES one level deeper (half-size inverse transforms, see mr_plan).
 //   S  total power  mr_total_kernel: S per record from those sums (Euler-Maclaurin corrected), BEFORE any plane of
 //                   the deeper bands is written, so that the information plane can be fused into E.
 //   E  expand       qi_mr_expand.cuh: per (channel, band, 16384-cell span) the band's decimated samples are read
