@@ -509,10 +509,15 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
             flush_multi();
             dim3 grid2((unsigned)ctas, (unsigned)C);
 #ifndef QI_EMUL
-            cudaFuncSetAttribute(mr_level2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2K_SMEM);
+            cudaFuncSetAttribute(mr_level2k_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2K_SMEM);
+            cudaFuncSetAttribute(mr_level2k_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2K_SMEM);
 #endif
-            QI_LAUNCH(mr_level2k_kernel, grid2, dim3(L2K_THREADS), L2K_SMEM, st, x, g, (const MrDevBand*)d_bands,
-                      (const cplx<float>*)tables, (const float4*)tw2k, wbuf, out_power, out_complex, sum_dst, (int)ppc);
+            if (g.env)
+                QI_LAUNCH((mr_level2k_kernel<true>), grid2, dim3(L2K_THREADS), L2K_SMEM, st, x, g, (const MrDevBand*)d_bands,
+                          (const cplx<float>*)tables, (const float4*)tw2k, wbuf, out_power, out_complex, sum_dst, (int)ppc);
+            else
+                QI_LAUNCH((mr_level2k_kernel<false>), grid2, dim3(L2K_THREADS), L2K_SMEM, st, x, g, (const MrDevBand*)d_bands,
+                          (const cplx<float>*)tables, (const float4*)tw2k, wbuf, out_power, out_complex, sum_dst, (int)ppc);
             continue;
         }
         const i64 gx = (g.n_blocks + g.TC - 1) / g.TC;

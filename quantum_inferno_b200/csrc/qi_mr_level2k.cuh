@@ -120,6 +120,8 @@ QI_DEV void l2k_stage8(float4* __restrict__ tile, int p0, const float4* __restri
 }
 
 // bx: index of this CTA among the CTAs of its level (blockIdx.x, or the offset inside a merged multi-level launch)
+// ENV = false compiles the envelope path out (the level-0 launch: fewer registers)
+template <bool ENV>
 QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const MrDevBand* __restrict__ bands,
                      const cplx<float>* __restrict__ tables, const float4* __restrict__ tw_g,
                      cplx<float>* __restrict__ wbuf, float* __restrict__ out_power, cplx<float>* __restrict__ out_complex,
@@ -221,7 +223,7 @@ QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const Mr
         //          row q of the bit-reversed 1024-row one: y(2m) = IFFT_1024(Z)(m)
         //   the first (radix-2) stage of that transform joins rows (2g, 2g+1): still inside the thread that holds rows
         //   4g .. 4g+3 of Y; then radix 8-8-8 with 128 butterflies per band, i.e. 256 = both bands of the pass
-        for (int pi = 0; g.env && pi < g.band_count; pi += 2) {
+        for (int pi = 0; ENV && g.env && pi < g.band_count; pi += 2) {
             const int nbp = g.band_count - pi < 2 ? g.band_count - pi : 2;
             float4* tile = ((pi >> 1) & 1) ? tile0 : tile1;
 #pragma unroll
@@ -323,7 +325,7 @@ QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const Mr
         }
 
         // ---- bands
-        for (int bi = 0; !g.env && bi < g.band_count; ++bi) {
+        for (int bi = 0; !(ENV && g.env) && bi < g.band_count; ++bi) {
             const int b = g.band_first + bi;
             const MrDevBand band = bands[b];
             const float4* K = reinterpret_cast<const float4*>(tables + band.table_off);
@@ -435,12 +437,13 @@ QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const Mr
     }
 }
 
+template <bool ENV>
 __global__ void __launch_bounds__(L2K_THREADS, 2)
 mr_level2k_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __restrict__ bands,
                   const cplx<float>* __restrict__ tables, const float4* __restrict__ tw_g,
                   cplx<float>* __restrict__ wbuf, float* __restrict__ out_power, cplx<float>* __restrict__ out_complex,
                   double* __restrict__ band_sum, int pairs_per_cta) {
-    l2k_body(x, g, bands, tables, tw_g, wbuf, out_power, out_complex, band_sum, pairs_per_cta, (int)blockIdx.x);
+    l2k_body<ENV>(x, g, bands, tables, tw_g, wbuf, out_power, out_complex, band_sum, pairs_per_cta, (int)blockIdx.x);
 }
 
 // The deep levels are a few CTAs each and independent of one another: one launch runs up to L2K_MULTI of them side by
@@ -462,7 +465,7 @@ mr_level2k_multi_kernel(MrMultiLevel m, const MrDevBand* __restrict__ bands, con
     while (li + 1 < m.n && (int)blockIdx.x >= m.cta_end[li]) ++li;
     const int bx = (int)blockIdx.x - (li ? m.cta_end[li - 1] : 0);
     const MrLevelGeom g = m.g[li];
-    l2k_body(m.x[li], g, bands, tables, tw_g, wbuf, nullptr, nullptr, m.sum[li], m.ppc[li], bx);
+    l2k_body<true>(m.x[li], g, bands, tables, tw_g, wbuf, nullptr, nullptr, m.sum[li], m.ppc[li], bx);
 }
 
 }  // namespace qi
