@@ -10,7 +10,11 @@ _lib = None
 def load():
     global _lib
     if _lib is None:
-        subprocess.run([os.path.join(HERE, "build_emul.sh")], check=True, capture_output=True)
         from quantum_inferno_b200._lib import bind
+        override = os.environ.get("QI_EMUL_LIB")                # e.g. the AddressSanitizer build of asan_check.sh
+        if override:
+            _lib = bind(ctypes.CDLL(override))
+            return _lib
+        subprocess.run([os.path.join(HERE, "build_emul.sh")], check=True, capture_output=True)
         _lib = bind(ctypes.CDLL(os.path.join(HERE, "libqi_emul.so")))
     return _lib
