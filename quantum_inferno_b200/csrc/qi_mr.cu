@@ -25,7 +25,7 @@
 //   I  info rows    the level-0 rows' information plane (their power was written before S was known).
 //
 // Replaces (fp32 tolerance of the north star: power rel. L2 <= 1e-4) quantum_inferno/styx_cwt.py:147-198 + np.abs()**2.
-// The numpy model of exactly this algorithm is tools/multirate_prototype.py.
+// tools/multirate_prototype.py is the numpy model the first version of this algorithm was validated with.
 #include "qi_fft.cuh"
 #include "qi_host.h"
 #include "qi_reduce.cuh"
