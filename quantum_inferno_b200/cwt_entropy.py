@@ -56,6 +56,11 @@ def _host_pipelined(rt, band_order_nth, sig_wf, fs, dictionary_type, dt, host_ch
     main = torch.cuda.current_stream(rt.device)
     copy_stream = torch.cuda.Stream(device=rt.device)
     bounds = np.linspace(0, n_chan, min(int(host_chunks), n_chan) + 1).astype(int)
+    if len(bounds) > 2 and bounds[1] - bounds[0] >= 2:
+        # the first group's upload is the only one that nothing overlaps: make it half a group (the rest shifts down,
+        # the last group grows) -- e.g. 8 channels in 4 groups go as 1 + 2 + 2 + 3
+        shift = (bounds[1] - bounds[0]) // 2
+        bounds[1:-1] -= shift
     # two staging buffers owned by this call (allocated on the compute stream, so the caching allocator never has to
     # reason about the copy stream); buffer k % 2 is refilled only after the kernels of group k - 2 have consumed it
     gmax = int(np.max(np.diff(bounds)))

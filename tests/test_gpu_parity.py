@@ -412,3 +412,20 @@ def test_multirate_vs_exact_other_orders(torch_cuda, order, logn):
     for band in (n_trunc + 1, len(a.frequency_hz) // 2, len(a.frequency_hz) - 2):
         row = np.abs(orc.cwt_band(xf, order, n, a.frequency_hz[band], FS)) ** 2
         assert l2(pa[0, band].cpu().numpy(), row) < TOL32_L2
+
+
+@pytest.mark.parametrize("n_chan,chunks", [(8, 4), (5, 3), (2, 2), (3, 8)])
+def test_host_pipelined_equals_resident(torch_cuda, n_chan, chunks):
+    """cwt_power_entropy(host_chunks=k) on host-resident records (pinned tensor or numpy): channel groups are uploaded
+    under the kernels of the previous group; channels are independent, so every output equals the resident call's."""
+    torch = torch_cuda
+    from quantum_inferno_b200 import cwt_entropy
+    n = 1 << 15
+    x = np.stack([synth(n, chan=c) for c in range(n_chan)]).astype(np.float32)
+    ref = cwt_entropy.cwt_power_entropy(3, torch.from_numpy(x).cuda(), FS, dtype="float32")
+    for src in (torch.from_numpy(x).pin_memory(), x):
+        r = cwt_entropy.cwt_power_entropy(3, src, FS, dtype="float32", host_chunks=chunks)
+        assert torch.equal(r.power, ref.power) and torch.allclose(r.info, ref.info, rtol=0, atol=1e-5)
+        # the fp64 sums are accumulated with atomics: equal up to the order of the additions
+        assert torch.allclose(r.band_power, ref.band_power, rtol=1e-12) and torch.allclose(r.total_power, ref.total_power, rtol=1e-12)
+        assert torch.allclose(r.band_entropy_bits, ref.band_entropy_bits, rtol=0, atol=1e-9)
