@@ -26,6 +26,7 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
     QI_DYN_SMEM(smem_raw);
     const int R = 1 << g.logF;
     const int TC = g.TC, TP = TC + 1;
+    const int logTC = 31 - __clz(TC);
     cplx<T>* tile = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* tw = tile + (size_t)R * TP;
     T* means = reinterpret_cast<T*>(tw + R);              // 2*TC means
@@ -66,8 +67,8 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < g.nperseg * TC; idx += blockDim.x) {
-        const int c = idx % TC;
-        const int r = idx / TC;
+        const int c = idx & (TC - 1);                   // TC is a power of two
+        const int r = idx >> logTC;
         const T w = window[r];
         cplx<T> v = tile[r * TP + c];
         v.re = (v.re - means[2 * c]) * w;
@@ -83,8 +84,8 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
     const int padded = (total + (int)blockDim.x - 1) / (int)blockDim.x * (int)blockDim.x;   // whole warps stay converged
     for (int idx = threadIdx.x; idx < padded; idx += blockDim.x) {
         const bool active = idx < total;
-        const int c = idx % TC;
-        const int k = active ? idx / TC : 0;
+        const int c = idx & (TC - 1);
+        const int k = active ? idx >> logTC : 0;
         const cplx<T> z1 = tile[(int)brev_bits((unsigned)k, g.logF) * TP + c];
         const cplx<T> z2 = tile[(int)brev_bits((unsigned)((R - k) & (R - 1)), g.logF) * TP + c];
         cplx<T> xa = mk<T>((T)0.5 * (z1.re + z2.re), (T)0.5 * (z1.im - z2.im));
@@ -160,6 +161,7 @@ istft_frames_kernel(const cplx<T>* __restrict__ S, const T* __restrict__ dual_wi
     QI_DYN_SMEM(smem_raw);
     const int R = 1 << g.logF;
     const int TC = g.TC, TP = TC + 1;
+    const int logTC = 31 - __clz(TC);
     cplx<T>* tile = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* tw = tile + (size_t)R * TP;
     const i64 chan = blockIdx.y;
@@ -167,8 +169,8 @@ istft_frames_kernel(const cplx<T>* __restrict__ S, const T* __restrict__ dual_wi
     const int K = (R >> 1) + 1;
     fill_twiddles<T>(tw, g.logF);
     for (int idx = threadIdx.x; idx < K * TC; idx += blockDim.x) {        // lanes along the frames (fastest axis of S)
-        const int c = idx % TC;
-        const int k = idx / TC;
+        const int c = idx & (TC - 1);
+        const int k = idx >> logTC;
         const i64 fa = frame0 + 2 * c, fb = fa + 1;
         cplx<T> xa = mk<T>((T)0, (T)0), xb = xa;
         if (fa < g.n_frames) xa = S[(chan * K + k) * g.n_frames + fa];
@@ -187,14 +189,15 @@ istft_frames_kernel(const cplx<T>* __restrict__ S, const T* __restrict__ dual_wi
     __syncthreads();
     tile_fft<T, FFT_INV>(tile, tw, g.logF, TC, TP);
     const T inv = (T)(1.0 / (double)R);
-    for (int idx = threadIdx.x; idx < g.nperseg * TC; idx += blockDim.x) {  // lanes along the samples of a slice
-        const int n = idx % g.nperseg;
-        const int c = idx / g.nperseg;
+    for (int c = 0; c < TC; ++c) {                                          // lanes along the samples of a slice
         const i64 fa = frame0 + 2 * c;
-        const cplx<T> v = tile[n * TP + c];
-        const T w = dual_win[n] * inv;
-        if (fa < g.n_frames) slices[(chan * g.n_frames + fa) * g.nperseg + n] = v.re * w;
-        if (fa + 1 < g.n_frames) slices[(chan * g.n_frames + fa + 1) * g.nperseg + n] = v.im * w;
+        if (fa >= g.n_frames) break;
+        for (int n = threadIdx.x; n < g.nperseg; n += blockDim.x) {
+            const cplx<T> v = tile[n * TP + c];
+            const T w = dual_win[n] * inv;
+            slices[(chan * g.n_frames + fa) * g.nperseg + n] = v.re * w;
+            if (fa + 1 < g.n_frames) slices[(chan * g.n_frames + fa + 1) * g.nperseg + n] = v.im * w;
+        }
     }
 }
 
