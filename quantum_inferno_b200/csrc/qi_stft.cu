@@ -36,17 +36,37 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
 
     fill_twiddles<T>(tw, g.logF);
     // gather (lanes along the sample axis -> coalesced global reads)
-    for (int idx = threadIdx.x; idx < R * TC; idx += blockDim.x) {
-        const int r = idx & (R - 1);
-        const int c = idx >> g.logF;
-        T va = (T)0, vb = (T)0;
-        if (r < g.nperseg) {
-            const i64 fa = frame0 + 2 * c, fb = fa + 1;
-            const i64 pa = fa * g.hop + r - g.pad_left, pb = fb * g.hop + r - g.pad_left;
-            if (fa < g.n_frames && pa >= 0 && pa < g.n_points) va = x[pa];
-            if (fb < g.n_frames && pb >= 0 && pb < g.n_points) vb = x[pb];
+    // interior CTAs (every frame exists and lies inside the record) take the path without bounds checks
+    const i64 first = frame0 * g.hop - g.pad_left;
+    const bool interior = frame0 + 2 * TC <= g.n_frames && first >= 0 &&
+                          first + (i64)(2 * TC - 1) * g.hop + g.nperseg <= g.n_points &&
+                          (i64)(2 * TC - 1) * g.hop + R < (1ll << 30);
+    if (interior) {
+        const T* xb0 = x + first;
+        for (int idx = threadIdx.x; idx < R * TC; idx += blockDim.x) {
+            const int r = idx & (R - 1);
+            const int c = idx >> g.logF;
+            T va = (T)0, vb = (T)0;
+            if (r < g.nperseg) {
+                const int o = 2 * c * g.hop + r;
+                va = xb0[o];
+                vb = xb0[o + g.hop];
+            }
+            tile[r * TP + c] = mk<T>(va, vb);
         }
-        tile[r * TP + c] = mk<T>(va, vb);
+    } else {
+        for (int idx = threadIdx.x; idx < R * TC; idx += blockDim.x) {
+            const int r = idx & (R - 1);
+            const int c = idx >> g.logF;
+            T va = (T)0, vb = (T)0;
+            if (r < g.nperseg) {
+                const i64 fa = frame0 + 2 * c, fb = fa + 1;
+                const i64 pa = fa * g.hop + r - g.pad_left, pb = fb * g.hop + r - g.pad_left;
+                if (fa < g.n_frames && pa >= 0 && pa < g.n_points) va = x[pa];
+                if (fb < g.n_frames && pb >= 0 && pb < g.n_points) vb = x[pb];
+            }
+            tile[r * TP + c] = mk<T>(va, vb);
+        }
     }
     __syncthreads();
     // per-frame mean over the nperseg samples (scipy detrend='constant', after the zero extension)
@@ -97,8 +117,11 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
         const i64 fa = frame0 + 2 * c;
         if (out && active) {
             cplx<T>* o = out + (chan * K + k) * g.n_frames + fa;
-            if (fa < g.n_frames) o[0] = xa * sc;
-            if (fa + 1 < g.n_frames) o[1] = xb * sc;
+            if (interior) { o[0] = xa * sc; o[1] = xb * sc; }
+            else {
+                if (fa < g.n_frames) o[0] = xa * sc;
+                if (fa + 1 < g.n_frames) o[1] = xb * sc;
+            }
         }
         if (psd_acc) {
             double p = 0.0;
