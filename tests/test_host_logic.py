@@ -155,3 +155,25 @@ def test_no_cpu_fallback():
     pkg = os.path.join(ROOT, "quantum_inferno_b200")
     src = "".join(open(os.path.join(pkg, fn)).read() for fn in os.listdir(pkg) if fn.endswith(".py"))
     assert "qi_oracle" not in src and "libqi_emul" not in src and "import oracle" not in src
+
+
+def test_band_shard_cost_balance():
+    """distributed.band_shard: contiguous cover of the band table, at least one band per rank, balanced on the per-level
+    cost model of the multirate path (a level-0 band costs several deep bands)."""
+    from quantum_inferno_b200 import distributed
+    n, order = 1 << 24, 12
+    f = sc.log_frequency_hz_from_fft_points(800.0, n, order)
+    cost = distributed.band_cost(order, n, f, 800.0, {"dtype": "float32"})
+    assert len(cost) == len(f) and min(cost) >= 1.0 and cost[-1] > cost[0]          # high bands (level 0) cost more
+    assert distributed.band_cost(order, n, f, 800.0, {"dtype": "float64"}) is None     # exact method: equal cost
+    for world in (2, 3, 8):
+        edges = [distributed.band_shard(len(f), r, world, cost) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == len(f)
+        assert all(a[1] == b[0] for a, b in zip(edges[:-1], edges[1:])) and all(b1 > b0 for b0, b1 in edges)
+        loads = [sum(cost[b0:b1]) for b0, b1 in edges]
+        assert max(loads) < 1.25 * sum(cost) / world
+        counts = [b1 - b0 for b0, b1 in edges]
+        assert counts[0] > counts[-1]                                               # fewer of the expensive bands
+    with pytest.raises(ValueError):
+        distributed.band_shard(3, 0, 4)
+    assert [distributed.channel_shard(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
