@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define QI_ABI_VERSION 2
+#define QI_ABI_VERSION 3
 
 /* dtype of the arithmetic and of every real/complex buffer in a call */
 #define QI_F32 0
@@ -230,6 +230,37 @@ int qi_abs_log2(const void* in, int64_t n, int dtype, int is_complex, int square
  * in natural bin order.  workspace >= M*n complex elements. */
 int qi_rfft(const void* sig, int64_t M, int64_t n, int64_t sig_stride, int dtype, void* out,
             void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- after the path: display / picking summaries --------------------------
+ * Replaces quantum_inferno/utilities/sampling.py:13-50 (subsample) and :87-120 (subsample_2d): every row of
+ * in [M, n_in] (rows `stride` elements apart) is cut into groups of `factor` consecutive samples;
+ *   NTH     : out[m, j] = in[m, j*factor],                 n_out = ceil(n_in / factor)
+ *   others  : out[m, j] = mean / median / max / min of in[m, j*factor .. (j+1)*factor), n_out = floor(n_in / factor)
+ * (the remainder is dropped, as the reference truncates it).  NaNs propagate like numpy's.  The mean accumulates in
+ * fp64; median / max / min return input values (or the dtype's mean of the two middle ones) bit-exactly. */
+#define QI_SUB_NTH 0
+#define QI_SUB_AVERAGE 1
+#define QI_SUB_MEDIAN 2
+#define QI_SUB_MAX 3
+#define QI_SUB_MIN 4
+int qi_subsample(const void* in, int64_t M, int64_t n_in, int64_t stride, int64_t factor, int method, int dtype,
+                 void* out, int64_t n_out, void* stream);
+
+/* Replaces np.nanmax / np.nanmin / np.nanmax(np.abs()) / np.max of quantum_inferno/utilities/picker.py:34-53,141-144:
+ * out double [M, 4] = (max, min, max |x|, number of NaNs) of every row, NaNs ignored (all-NaN row -> NaN). */
+int qi_extrema(const void* in, int64_t M, int64_t n, int64_t stride, int dtype, double* out, void* stream);
+
+/* Replaces the scan of scipy.signal.find_peaks(x, height=h) called at quantum_inferno/utilities/picker.py:105,119,147:
+ * plateau-aware strict local maxima (scipy _local_maxima_1d: midpoint of a flat top, edges excluded) that satisfy
+ * x[peak] >= height when use_height != 0.  peaks int64 [capacity] receives the positions UNORDERED and values
+ * double [capacity] (or NULL) x at those positions; *count (device) the number found, which may exceed capacity
+ * (then only `capacity` were stored: call again with more room). */
+int qi_local_maxima(const void* in, int64_t n, int dtype, double height, int use_height, int64_t* peaks,
+                    double* values, int64_t capacity, int64_t* count, void* stream);
+
+/* Replaces `in_signal / np.nanmax(in_signal)` etc. of quantum_inferno/utilities/picker.py:46-53: out = in / divisor,
+ * the divisor rounded to the buffer's dtype first (numpy's array / same-dtype scalar). */
+int qi_divide(const void* in, int64_t n, int dtype, double divisor, void* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -608,3 +608,121 @@ def istft_tukey(spec, fs, alpha, segment_length, overlap_length, scaling="magnit
     plan = StftTukeyPlan(fs, alpha, segment_length, overlap_length, scaling)
     last = int((spec.shape[1] - 1) * plan.hop)
     return np.arange(0, last / fs, 1 / fs), plan.istft(spec, last)
+
+
+# ============================================================================ after the path
+# utilities/sampling.py:13-50,87-120 and utilities/picker.py:34-53,108-149 restated with numpy; scipy.signal.find_peaks
+# (scipy >= 1.15, scipy/signal/_peak_finding.py::find_peaks, _peak_finding_utils.pyx::_local_maxima_1d and
+# ::_select_by_peak_distance) restated for the two arguments the reference passes (height, distance).
+SUBSAMPLE_METHODS = ["average", "median", "max", "min", "nth"]     # utilities/sampling.py:10
+
+
+def subsample_2d(array, factor, method="nth"):
+    """utilities/sampling.py:87-120: group reductions along the second axis, remainder dropped (kept for "nth")."""
+    array = np.asarray(array)
+    if factor < 2:
+        return array
+    if method not in SUBSAMPLE_METHODS:
+        method = "nth"
+    if method == "nth":
+        return array[:, ::factor]
+    n_out = array.shape[1] // factor
+    groups = array[:, :n_out * factor].reshape(array.shape[0], n_out, factor)
+    if method == "average":
+        return groups.mean(axis=2)
+    if method == "median":
+        srt = np.sort(groups, axis=2)                               # NaNs sort last
+        mid = srt[:, :, factor // 2] if factor % 2 else (srt[:, :, factor // 2 - 1] + srt[:, :, factor // 2]) / 2
+        return np.where(np.isnan(srt[:, :, -1]), np.nan, mid).astype(array.dtype)
+    return groups.max(axis=2) if method == "max" else groups.min(axis=2)
+
+
+def subsample(timeseries, sample_rate_hz, factor, method="nth"):
+    """utilities/sampling.py:13-50."""
+    if factor < 2:
+        return timeseries, sample_rate_hz
+    return subsample_2d(np.asarray(timeseries)[None, :], factor, method)[0], sample_rate_hz / factor
+
+
+def local_maxima_1d(x):
+    """scipy _local_maxima_1d: midpoints of the flat tops that rise strictly on the left and fall strictly on the
+    right; the first and last sample never count.  Restated on runs of equal samples."""
+    x = np.asarray(x)
+    n = x.shape[0]
+    if n < 3:
+        return np.zeros(0, dtype=np.intp)
+    start = np.concatenate(([0], np.flatnonzero(x[1:] != x[:-1]) + 1))      # first index of every run
+    end = np.concatenate((start[1:], [n])) - 1                              # last index of every run
+    v = x[start]
+    inner = np.arange(1, len(start) - 1)
+    is_peak = (v[inner - 1] < v[inner]) & (v[inner + 1] < v[inner])
+    runs = inner[is_peak]
+    return ((start[runs] + end[runs]) // 2).astype(np.intp)
+
+
+def select_by_peak_distance(peaks, priority, distance):
+    """scipy _select_by_peak_distance: peaks in order of falling priority remove their neighbours nearer than
+    ceil(distance) samples."""
+    n = len(peaks)
+    d = int(np.ceil(distance))
+    keep = np.ones(n, dtype=bool)
+    order = np.argsort(priority)
+    for i in range(n - 1, -1, -1):
+        j = order[i]
+        if not keep[j]:
+            continue
+        k = j - 1
+        while k >= 0 and peaks[j] - peaks[k] < d:
+            keep[k] = False
+            k -= 1
+        k = j + 1
+        while k < n and peaks[k] - peaks[j] < d:
+            keep[k] = False
+            k += 1
+    return keep
+
+
+def find_peaks(x, height=None, distance=None):
+    """scipy.signal.find_peaks(x, height=, distance=)[0] (conditions applied in scipy's order: height, distance)."""
+    x = np.asarray(x)
+    peaks = local_maxima_1d(x)
+    if height is not None:
+        peaks = peaks[x[peaks] >= height]
+    if distance is not None:
+        peaks = peaks[select_by_peak_distance(peaks, x[peaks], distance)]
+    return peaks
+
+
+def to_log2_with_epsilon(x):
+    """utilities/rescaling.py:13-20."""
+    return np.log2(np.abs(x) + EPS64)
+
+
+def scale_signal_by_extraction_type(sig, extraction_type="sigmax"):
+    """utilities/picker.py:34-53."""
+    sig = np.asarray(sig)
+    if extraction_type == "sigmin":
+        return sig / np.nanmin(sig)
+    if extraction_type == "sigabs":
+        return sig / np.nanmax(np.abs(sig))
+    if extraction_type == "log2":
+        return to_log2_with_epsilon(sig)
+    if extraction_type == "log2max":
+        return to_log2_with_epsilon(sig) / np.nanmax(to_log2_with_epsilon(sig))
+    return sig / np.nanmax(sig)                                           # "sigmax" and the invalid-type default
+
+
+def find_peaks_by_extraction_type(timeseries, extraction_type="sigmax", height=0.7):
+    """utilities/picker.py:108-120."""
+    return find_peaks(scale_signal_by_extraction_type(timeseries, extraction_type), height=height)
+
+
+def find_peaks_with_bits(timeseries, sample_rate_hz, scaling_type="amplitude", threshold_bits=1,
+                         time_distance_seconds=0.1):
+    """utilities/picker.py:123-149."""
+    bits = to_log2_with_epsilon(timeseries)
+    if scaling_type == "log2":
+        height = np.max(bits) - threshold_bits
+    else:
+        height = np.max(timeseries) - 2 ** threshold_bits
+    return find_peaks(bits, height=height, distance=int(time_distance_seconds * sample_rate_hz))

@@ -271,3 +271,65 @@ def cwt_multirate(sig, bands, want_power=True, want_complex=False, want_band_sum
         call(0)
     return {"complex": out_c, "power": out_power, "band_sum": bsum, "info": out_info if want_info else None,
             "entropy_sum": ent, "band_sum_est": est, "total": total}
+
+
+def subsample(buf, factor, method, dt, rt=None):
+    """Run qi_subsample on a device buffer [M, n] (utilities/sampling.py:13-50,87-120).  Returns [M, n_out]."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    M, n = int(buf.shape[0]), int(buf.shape[1])
+    factor = int(factor)
+    n_out = -(-n // factor) if method == "nth" else n // factor
+    out = rt.empty((M, n_out), dt)
+    if n_out > 0 and M > 0:
+        rc = lib.qi_subsample(rt.ptr(buf), M, n, n, factor, _lib.SUBSAMPLE_METHOD_CODE[method], DTYPE_CODE[dt],
+                              rt.ptr(out), n_out, rt.stream())
+        _lib.check(lib, rc, "qi_subsample")
+    return out
+
+
+def extrema(buf, dt, rt=None):
+    """Run qi_extrema on a device buffer [M, n]: host float64 array [M, 4] = (nanmax, nanmin, nanmax|x|, #NaN)."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    M, n = int(buf.shape[0]), int(buf.shape[1])
+    out = rt.empty((M, 4), "float64")
+    rc = lib.qi_extrema(rt.ptr(buf), M, n, n, DTYPE_CODE[dt], rt.ptr(out), rt.stream())
+    _lib.check(lib, rc, "qi_extrema")
+    return rt.to_numpy(out)
+
+
+def local_maxima(buf, dt, height=None, rt=None, first_capacity=1 << 16):
+    """Run qi_local_maxima on a device record [n]: host arrays (positions int64 ascending, x there float64) of the
+    plateau-aware local maxima with x[peak] >= height (scipy.signal.find_peaks(x, height=height))."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    n = int(buf.shape[0])
+    cap = max(1, min(first_capacity, n // 2 + 1))
+    count = rt.empty((1,), "int64")
+    use_h = height is not None
+    h = float(height) if use_h else 0.0
+    while True:
+        peaks = rt.empty((cap,), "int64")
+        values = rt.empty((cap,), "float64")
+        rc = lib.qi_local_maxima(rt.ptr(buf), n, DTYPE_CODE[dt], h, int(use_h), rt.ptr(peaks), rt.ptr(values), cap,
+                                 rt.ptr(count), rt.stream())
+        _lib.check(lib, rc, "qi_local_maxima")
+        found = int(rt.to_numpy(count)[0])
+        if found <= cap:
+            pos, val = rt.to_numpy(peaks)[:found], rt.to_numpy(values)[:found]
+            order = np.argsort(pos, kind="stable")
+            return pos[order], val[order]
+        cap = found
+
+
+def divide(buf, dt, divisor, rt=None):
+    """out = buf / divisor in the buffer's dtype (qi_divide; utilities/picker.py:46-53)."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    n = int(np.prod(buf.shape))
+    out = rt.empty(buf.shape, dt)
+    if n:
+        rc = lib.qi_divide(rt.ptr(buf), n, DTYPE_CODE[dt], float(divisor), rt.ptr(out), rt.stream())
+        _lib.check(lib, rc, "qi_divide")
+    return out

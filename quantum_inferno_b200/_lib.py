@@ -12,7 +12,8 @@ import numpy as np
 
 QI_F32, QI_F64 = 0, 1
 QI_CONV_LINEAR_SAME, QI_CONV_CIRC_CORR = 0, 1
-QI_ABI_VERSION = 2
+SUBSAMPLE_METHOD_CODE = {"nth": 0, "average": 1, "median": 2, "max": 3, "min": 4}
+QI_ABI_VERSION = 3
 QI_N_CATEGORIES = 7
 CATEGORY_NAMES = ("fft_fwd", "inv_first", "inv_mid", "inv_last", "info", "stft", "other")
 
@@ -61,6 +62,10 @@ SIGNATURES = {
     "qi_tdr_marginal": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]),
     "qi_rfft": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
     "qi_stx_windows": (_c_int, [_c_vp, _c_int, _c_i64, _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
+    "qi_subsample": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_vp, _c_i64, _c_vp]),
+    "qi_extrema": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp]),
+    "qi_local_maxima": (_c_int, [_c_vp, _c_i64, _c_int, _c_dbl, _c_int, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
+    "qi_divide": (_c_int, [_c_vp, _c_i64, _c_int, _c_dbl, _c_vp, _c_vp]),
 }
 
 

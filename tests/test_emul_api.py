@@ -247,3 +247,18 @@ def test_short_time_fft_tukey(golden, dtype, tol):
     assert rel(obj.stft(batch)[1], obj.stft(x[::-1].copy())) < 1e-15
     with pytest.raises(NotImplementedError):
         obj.stft_detrend(x, "linear")
+
+
+# ----------------------------------------------------------------------------- after the path
+def test_subsample(golden, capsys):
+    from tests import _pick_checks as pc
+    pc.check_subsample_golden(golden)
+    pc.check_subsample_edges(capsys)
+    pc.check_subsample_vs_oracle()
+
+
+def test_picker(golden, capsys):
+    from tests import _pick_checks as pc
+    pc.check_picker_golden(golden)
+    pc.check_picker_edges(capsys)
+    pc.check_picker_vs_oracle(n=30000)

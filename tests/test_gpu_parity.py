@@ -429,3 +429,35 @@ def test_host_pipelined_equals_resident(torch_cuda, n_chan, chunks):
         # the fp64 sums are accumulated with atomics: equal up to the order of the additions
         assert torch.allclose(r.band_power, ref.band_power, rtol=1e-12) and torch.allclose(r.total_power, ref.total_power, rtol=1e-12)
         assert torch.allclose(r.band_entropy_bits, ref.band_entropy_bits, rtol=0, atol=1e-9)
+
+
+# ----------------------------------------------------------------------------- after the path
+def test_subsample_gpu(torch_cuda, golden, capsys):
+    from tests import _pick_checks as pc
+    pc.check_subsample_golden(golden)
+    pc.check_subsample_edges(capsys)
+    pc.check_subsample_vs_oracle()
+
+
+def test_picker_gpu(torch_cuda, golden, capsys):
+    from tests import _pick_checks as pc
+    pc.check_picker_golden(golden)
+    pc.check_picker_edges(capsys)
+    pc.check_picker_vs_oracle()
+
+
+def test_subsample_plane_properties(torch_cuda):
+    """Display reduction of a [bands, 2^22] fp32 plane kept on the device: size-independent properties
+    (min <= median <= max, mean inside them, factor f then g == factor f*g for max / min / nth, tensor in -> tensor out)."""
+    from quantum_inferno_b200.utilities import sampling
+    torch = torch_cuda
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    p = torch.rand((12, 1 << 22), generator=gen, device="cuda", dtype=torch.float32) ** 4
+    red = {m: sampling.subsample_2d(p, 32, m) for m in ("average", "median", "max", "min", "nth")}
+    assert all(isinstance(v, torch.Tensor) and v.shape == (12, 1 << 17) for v in red.values())
+    assert bool((red["min"] <= red["median"]).all()) and bool((red["median"] <= red["max"]).all())
+    assert bool((red["min"] <= red["average"]).all()) and bool((red["average"] <= red["max"]).all())
+    assert torch.equal(red["max"], p.reshape(12, -1, 32).amax(dim=2)) and torch.equal(red["nth"], p[:, ::32])
+    for m in ("max", "min", "nth"):
+        assert torch.equal(sampling.subsample_2d(sampling.subsample_2d(p, 32, m), 64, m), sampling.subsample_2d(p, 2048, m))
+    assert torch.equal(sampling.subsample_2d(p, 2048, "median"), p.reshape(12, -1, 2048).sort(dim=2).values[:, :, 1023:1025].sum(dim=2) / 2)

@@ -163,3 +163,36 @@ def test_short_time_fft_tukey(golden):
     nd = int(g["fft_nd"])
     assert g["c0_mag"].shape == (nd // 2 + 1, len(x) // (nd // 2) + 1)
     assert np.allclose(x[:len(g["c0_xr"])], g["c0_xr"], atol=1e-14)
+
+
+# ----------------------------------------------------------------------------- after the path
+def test_subsample_oracle(golden):
+    g = golden("pick")
+    for dt in ("float64", "float32"):
+        plane = g["plane"].astype(dt)
+        for f in g["factors"]:
+            for m in ("average", "median", "max", "min", "nth"):
+                got, want = orc.subsample_2d(plane, int(f), m), g[f"sub2d_{dt}_{int(f)}_{m}"]
+                assert got.shape == want.shape and got.dtype == want.dtype
+                assert np.array_equal(got, want, equal_nan=True), (dt, f, m)
+    for f in (2, 5, 64, 200):
+        for m in ("average", "median", "max", "min", "nth"):
+            y, rate = orc.subsample(g["row"], 800.0, f, m)
+            assert np.array_equal(y, g[f"sub1d_{f}_{m}"]) and rate == float(g[f"sub1d_{f}_{m}_rate"])
+
+
+def test_picker_oracle(golden):
+    g = golden("pick")
+    x = g["x"]
+    for et in ("sigmax", "sigmin", "sigabs", "log2", "log2max"):
+        assert np.array_equal(orc.scale_signal_by_extraction_type(x, et), g[f"scaled_{et}"])
+        for h in (0.7, 0.3):
+            assert np.array_equal(orc.find_peaks_by_extraction_type(x, et, h), g[f"peaks_{et}_{h}"]), (et, h)
+    for st in ("amplitude", "log2"):
+        for tb in (1, 3):
+            for dist in (0.1, 0.01, 0.5):
+                assert np.array_equal(orc.find_peaks_with_bits(x, 800.0, st, tb, dist), g[f"bits_{st}_{tb}_{dist}"])
+    assert np.array_equal(orc.find_peaks_with_bits(g["noise"], 800.0, "log2", 2, 0.05), g["noise_peaks_bits"])
+    assert np.array_equal(orc.find_peaks_by_extraction_type(g["noise"], "sigmax", 0.5), g["noise_peaks_sigmax"])
+    assert len(g["peaks_sigmax_0.3"]) > len(g["peaks_sigmax_0.7"]) > 0          # the fixture is not vacuous
+    assert len(g["bits_log2_3_0.01"]) > len(g["bits_log2_3_0.5"]) > 0

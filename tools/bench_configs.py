@@ -137,6 +137,32 @@ def cfg6():
     return out
 
 
+def cfg7():
+    """the display / picking summaries of a TFR that stays in HBM.  subsample_2d of one channel's
+    [60, 2^24] fp32 power plane (4.0 GB, larger than L2) to the reference's 2^19-sample mesh (factor 32) and to a
+    coarse overview (factor 2048), and find_peaks_with_bits on a 2^26-sample fp32 record.  Algorithmic bytes: one read
+    of the input + the reduced output."""
+    from quantum_inferno_b200.utilities import picker, sampling
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    p = torch.rand((60, 1 << 24), generator=gen, device=DEV, dtype=torch.float32) ** 4
+    out = {"config": "cfg7: subsample_2d [60, 2^24] fp32; find_peaks_with_bits 2^26 fp32", "hbm_peak_GBps": 6547.2}
+    for f in (32, 2048):
+        for m in ("average", "max", "median", "nth"):
+            ms, y = timed(lambda: sampling.subsample_2d(p, f, m))
+            nbytes = (p.numel() if m != "nth" else y.numel() * 8) * 4 + y.numel() * 4   # nth touches one 32 B sector per output
+            out[f"{m}_x{f}"] = {"ms": ms, "alg_GBps": nbytes / ms / 1e6, "samples_per_s": p.numel() / ms * 1e3}
+    del p
+    k = torch.arange(1 << 26, device=DEV, dtype=torch.float32)
+    x = torch.randn(1 << 26, generator=gen, device=DEV) * 0.05
+    for c in range(1, 64):
+        x += (1.0 + 0.5 * (c % 3)) * torch.exp(-0.5 * ((k - c * (1 << 20)) / 2000.0) ** 2)
+    ms, pk = timed(lambda: picker.find_peaks_with_bits(x, FS, "amplitude", 1, 0.1))
+    out["find_peaks_with_bits"] = {"ms": ms, "peaks": int(len(pk)), "samples_per_s": x.numel() / ms * 1e3,
+                                   "alg_GBps": x.numel() * 4 * 4 / ms / 1e6,
+                                   "note": "four streaming passes over the record: log2 (read+write), extrema, local maxima"}
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg1", "cfg2", "cfg3", "cfg4"]
     for name in which:
