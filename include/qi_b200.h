@@ -258,6 +258,13 @@ int qi_extrema(const void* in, int64_t M, int64_t n, int64_t stride, int dtype, 
 int qi_local_maxima(const void* in, int64_t n, int dtype, double height, int use_height, int64_t* peaks,
                     double* values, int64_t capacity, int64_t* count, void* stream);
 
+/* HOST function (no device work): the minimum-distance selection of scipy.signal.find_peaks(distance=)
+ * (scipy/signal/_peak_finding_utils.pyx::_select_by_peak_distance) on the short candidate list that
+ * qi_local_maxima returned.  peaks HOST int64 [n] ascending; order HOST int64 [n] = argsort of the priorities
+ * (ascending; the highest priority is visited first); keep HOST uint8 [n] out: 1 = kept.  A kept peak removes every
+ * neighbour nearer than `distance` samples. */
+int qi_select_peaks_by_distance(const int64_t* peaks, const int64_t* order, int64_t n, int64_t distance, uint8_t* keep);
+
 /* Replaces `in_signal / np.nanmax(in_signal)` etc. of quantum_inferno/utilities/picker.py:46-53: out = in / divisor,
  * the divisor rounded to the buffer's dtype first (numpy's array / same-dtype scalar). */
 int qi_divide(const void* in, int64_t n, int dtype, double divisor, void* out, void* stream);

@@ -65,6 +65,7 @@ SIGNATURES = {
     "qi_subsample": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_vp, _c_i64, _c_vp]),
     "qi_extrema": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp]),
     "qi_local_maxima": (_c_int, [_c_vp, _c_i64, _c_int, _c_dbl, _c_int, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
+    "qi_select_peaks_by_distance": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp]),
     "qi_divide": (_c_int, [_c_vp, _c_i64, _c_int, _c_dbl, _c_vp, _c_vp]),
 }
 

@@ -144,6 +144,75 @@ subsample_small_kernel(const T* __restrict__ in, i64 stride, i64 n_out, int fact
     }
 }
 
+// ---------------------------------------------------------------- register path: factor = V * 2^k (or a divisor of V)
+// V = samples per 128-bit load.  A thread reduces its own vector, 2^k <= 32 neighbouring lanes finish the group with
+// xor-shuffles: no shared memory, four independent 128-bit loads in flight per thread.  "average" / "max" / "min" only.
+template <typename T, int METHOD> QI_DEV T sub_combine(T r, T v) {
+    if (METHOD == QI_SUB_MAX) return (v > r || v != v) ? v : r;      // NaN-propagating: once r is NaN it stays
+    return (v < r || v != v) ? v : r;
+}
+template <typename T, int METHOD>
+__global__ void __launch_bounds__(256)
+subsample_vec_kernel(const T* __restrict__ in, i64 stride, i64 n_vec, int factor, T* __restrict__ out, i64 n_out) {
+    constexpr int V = 16 / (int)sizeof(T), U = 4;
+    typedef double Acc;
+    const i64 m = blockIdx.y;
+    const T* row = in + m * stride;
+    T* orow = out + m * n_out;
+    const int lanes = factor >= V ? factor / V : 1;                   // lanes that share a group
+    const int per = factor >= V ? V : factor;                         // samples of one group inside a vector (fp32, factor 2: 2)
+    for (i64 base = (i64)blockIdx.x * (256 * U); base < n_vec; base += (i64)gridDim.x * (256 * U)) {
+        T v[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const i64 idx = base + u * 256 + threadIdx.x;
+            if (idx < n_vec) {
+                if (sizeof(T) == 4) {
+                    const float4 w = *reinterpret_cast<const float4*>(row + idx * V);
+                    v[u][0] = (T)w.x; v[u][1] = (T)w.y; v[u][V - 2] = (T)w.z; v[u][V - 1] = (T)w.w;
+                } else {
+                    const double2 w = *reinterpret_cast<const double2*>(row + idx * V);
+                    v[u][0] = (T)w.x; v[u][V - 1] = (T)w.y;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) v[u][e] = (T)0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const i64 idx = base + u * 256 + threadIdx.x;
+            const bool live = idx < n_vec;
+            if (per == V) {                                           // whole vector belongs to one group
+                if (METHOD == QI_SUB_AVERAGE) {
+                    Acc s = 0;
+#pragma unroll
+                    for (int e = 0; e < V; ++e) s += (Acc)v[u][e];
+                    for (int o = lanes >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (live && (threadIdx.x & (lanes - 1)) == 0) orow[idx / lanes] = (T)(s / (Acc)factor);
+                } else {
+                    T r = v[u][0];
+#pragma unroll
+                    for (int e = 1; e < V; ++e) r = sub_combine<T, METHOD>(r, v[u][e]);
+                    for (int o = lanes >> 1; o > 0; o >>= 1) r = sub_combine<T, METHOD>(r, __shfl_xor_sync(0xffffffffu, r, o));
+                    if (live && (threadIdx.x & (lanes - 1)) == 0) orow[idx / lanes] = r;
+                }
+            } else if (live) {                                        // factor 2 with four samples per vector
+                T r0, r1;
+                if (METHOD == QI_SUB_AVERAGE) {
+                    r0 = (T)(((Acc)v[u][0] + (Acc)v[u][1]) / (Acc)2);
+                    r1 = (T)(((Acc)v[u][V - 2] + (Acc)v[u][V - 1]) / (Acc)2);
+                } else {
+                    r0 = sub_combine<T, METHOD>(v[u][0], v[u][1]);
+                    r1 = sub_combine<T, METHOD>(v[u][V - 2], v[u][V - 1]);
+                }
+                orow[2 * idx] = r0;
+                orow[2 * idx + 1] = r1;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- long groups: one warp per group
 // k-th smallest (0-based) of src[0..count) by a most-significant-byte-first radix select; hist: 256 ints of this warp.
 template <typename T>
@@ -240,7 +309,17 @@ subsample_nth_kernel(const T* __restrict__ in, i64 stride, i64 n_out, i64 factor
 
 template <typename T, int METHOD>
 static void subsample_launch(const T* in, i64 M, i64 stride, i64 factor, T* out, i64 n_out, cudaStream_t st) {
-    if (factor <= SUB_SMALL_MAX) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const bool pow2 = (factor & (factor - 1)) == 0 && factor <= 32 * V && (factor >= V || factor == 2);
+    const bool aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && stride % V == 0;
+    if (METHOD != QI_SUB_MEDIAN && pow2 && aligned && (n_out * factor) % V == 0) {
+        const i64 n_vec = n_out * factor / V;
+        i64 blocks = (n_vec + 1023) / 1024;
+        const i64 cap = (148 * 8 * 8 + M - 1) / M;
+        if (blocks > cap) blocks = cap;
+        dim3 grid((unsigned)blocks, (unsigned)M);
+        QI_LAUNCH((subsample_vec_kernel<T, METHOD>), grid, dim3(256), 0, st, in, stride, n_vec, (int)factor, out, n_out);
+    } else if (factor <= SUB_SMALL_MAX) {
         const int f = (int)factor;
         int lanes = 1;
         while (lanes < 32 && lanes * 8 <= f) lanes <<= 1;          // >= 8 samples per lane
@@ -388,6 +467,19 @@ int qi_extrema(const void* in, int64_t M, int64_t n, int64_t stride, int dtype, 
         QI_LAUNCH((qi::extrema_kernel<double>), grid, dim3(256), 0, st, static_cast<const double*>(in), (qi::i64)n, (qi::i64)stride, acc);
     QI_LAUNCH((qi::extrema_decode_kernel), dim3((unsigned)((M + 255) / 256)), dim3(256), 0, st, acc, (qi::i64)M);
     return qi::check_cuda("qi_extrema");
+}
+
+int qi_select_peaks_by_distance(const int64_t* peaks, const int64_t* order, int64_t n, int64_t distance, uint8_t* keep) {
+    if (n < 0 || distance < 1 || (n > 0 && (!peaks || !order || !keep))) return QI_ERR_ARG;
+    for (int64_t i = 0; i < n; ++i) keep[i] = 1;
+    for (int64_t i = n - 1; i >= 0; --i) {
+        const int64_t j = order[i];
+        if (j < 0 || j >= n) return QI_ERR_ARG;
+        if (!keep[j]) continue;
+        for (int64_t k = j - 1; k >= 0 && peaks[j] - peaks[k] < distance; --k) keep[k] = 0;
+        for (int64_t k = j + 1; k < n && peaks[k] - peaks[j] < distance; ++k) keep[k] = 0;
+    }
+    return QI_OK;
 }
 
 int qi_divide(const void* in, int64_t n, int dtype, double divisor, void* out, void* stream) {

@@ -14,7 +14,7 @@ from typing import Optional, Tuple, Union
 
 import numpy as np
 
-from .. import _driver
+from .. import _driver, _lib
 from .._runtime import finish, get_runtime
 from ..scales_dyadic import get_epsilon
 
@@ -64,26 +64,17 @@ def scale_signal_by_extraction_type(in_signal: np.ndarray, extraction_type: str 
     return finish(rt, _scaled(rt, x, dt, extraction_type), want_numpy)
 
 
-def _select_by_peak_distance(peaks: np.ndarray, priority: np.ndarray, distance: float) -> np.ndarray:
-    """Host restatement of scipy/signal/_peak_finding_utils.pyx::_select_by_peak_distance on the candidate list:
-    highest priority first, every kept peak removes its neighbours closer than ``distance`` samples."""
-    n = peaks.shape[0]
-    distance_ = int(np.ceil(distance))
-    keep = np.ones(n, dtype=bool)
-    order = np.argsort(priority)
-    for i in range(n - 1, -1, -1):
-        j = order[i]
-        if not keep[j]:
-            continue
-        k = j - 1
-        while 0 <= k and peaks[j] - peaks[k] < distance_:
-            keep[k] = False
-            k -= 1
-        k = j + 1
-        while k < n and peaks[k] - peaks[j] < distance_:
-            keep[k] = False
-            k += 1
-    return keep
+def _select_by_peak_distance(lib, peaks: np.ndarray, priority: np.ndarray, distance: float) -> np.ndarray:
+    """scipy/signal/_peak_finding_utils.pyx::_select_by_peak_distance on the candidate list (host, compiled:
+    ``qi_select_peaks_by_distance``): highest priority first, every kept peak removes its neighbours closer than
+    ceil(distance) samples.  The visiting order is numpy's own argsort of the priorities, as in scipy."""
+    peaks = np.ascontiguousarray(peaks, dtype=np.int64)
+    order = np.ascontiguousarray(np.argsort(priority), dtype=np.int64)
+    keep = np.empty(peaks.shape[0], dtype=np.uint8)
+    rc = lib.qi_select_peaks_by_distance(peaks.ctypes.data, order.ctypes.data, peaks.shape[0], int(np.ceil(distance)),
+                                         keep.ctypes.data)
+    _lib.check(lib, rc, "qi_select_peaks_by_distance")
+    return keep.astype(bool)
 
 
 def _find_peaks(rt, x, dt, height, distance=None) -> np.ndarray:
@@ -92,7 +83,7 @@ def _find_peaks(rt, x, dt, height, distance=None) -> np.ndarray:
         raise ValueError("`distance` must be greater or equal to 1")
     peaks, priority = _driver.local_maxima(x, dt, height=height, rt=rt)
     if distance is not None and peaks.size:
-        peaks = peaks[_select_by_peak_distance(peaks, priority, distance)]
+        peaks = peaks[_select_by_peak_distance(rt.lib, peaks, priority, distance)]
     return peaks
 
 

@@ -78,6 +78,27 @@ def check_subsample_vs_oracle(rng_seed=3):
             assert np.allclose(a[ok], b[ok], rtol=1e-5 if dt == "float32" else 1e-12)
 
 
+def check_subsample_vector_path():
+    """Power-of-two factors on 16-byte aligned rows take the register / shuffle kernel (subsample_vec_kernel)."""
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200.utilities import sampling
+    rng = np.random.default_rng(9)
+    for dt in ("float32", "float64"):
+        p = rng.standard_normal((3, 5 * 1024 + 72)).astype(dt)
+        p[0, 1000] = np.nan
+        p[1, 2049] = np.inf
+        p[2, 4097] = -np.inf
+        p[2, 64:128] = -3.5
+        for f in (2, 4, 8, 16, 32, 64, 128):
+            for m in ("max", "min", "nth"):
+                assert same(sampling.subsample_2d(p, f, m), orc.subsample_2d(p, f, m)), (dt, f, m)
+            a, b = sampling.subsample_2d(p, f, "average"), orc.subsample_2d(p, f, "average")
+            assert a.shape == b.shape and a.dtype == b.dtype
+            assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.isinf(a), np.isinf(b))
+            ok = np.isfinite(b)
+            assert np.allclose(a[ok], b[ok], rtol=2e-6 if dt == "float32" else 1e-13, atol=1e-7 if dt == "float32" else 1e-15)
+
+
 def check_picker_golden(golden):
     from quantum_inferno_b200.utilities import picker
     g = golden("pick")

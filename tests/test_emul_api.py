@@ -255,6 +255,7 @@ def test_subsample(golden, capsys):
     pc.check_subsample_golden(golden)
     pc.check_subsample_edges(capsys)
     pc.check_subsample_vs_oracle()
+    pc.check_subsample_vector_path()
 
 
 def test_picker(golden, capsys):

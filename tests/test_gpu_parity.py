@@ -437,6 +437,7 @@ def test_subsample_gpu(torch_cuda, golden, capsys):
     pc.check_subsample_golden(golden)
     pc.check_subsample_edges(capsys)
     pc.check_subsample_vs_oracle()
+    pc.check_subsample_vector_path()
 
 
 def test_picker_gpu(torch_cuda, golden, capsys):
