@@ -269,6 +269,34 @@ int qi_select_peaks_by_distance(const int64_t* peaks, const int64_t* order, int6
  * the divisor rounded to the buffer's dtype first (numpy's array / same-dtype scalar). */
 int qi_divide(const void* in, int64_t n, int dtype, double divisor, void* out, void* stream);
 
+/* ---- before the path: zero-phase IIR filtering ----------------------------
+ * Replaces scipy.signal.filtfilt(b, a, x) as called by quantum_inferno/styx_fft.py:60-149 (butter_bandpass /
+ * butter_highpass / butter_lowpass) and quantum_inferno/synth/synthetic_signals.py:180-192 (antialias_half_nyquist),
+ * and scipy.signal.sosfiltfilt(sos, x) as called by quantum_inferno/utilities/picker.py:56-76 (apply_bandpass):
+ * odd extension by `padlen` samples, forward recursion from zi * ext[0], recursion over the reversed result from
+ * zi * y[-1], middle n samples kept (scipy's method="pad", padtype="odd").  The recursions run as a blocked parallel
+ * scan in fp64 whatever the record dtype.
+ *   form QI_IIR_BA : n_coef = number of taps (b and a zero-padded to the same length, a[0] == 1), direct form II
+ *                    transposed as scipy's lfilter; zi = scipy.signal.lfilter_zi(b, a)        [n_coef - 1 values]
+ *   form QI_IIR_SOS: n_coef = number of second-order sections, sos[s] = (b0, b1, b2, 1, a1, a2) as scipy's sosfilt;
+ *                    zi = scipy.signal.sosfilt_zi(sos) flattened                              [2 * n_coef values]
+ *   tukey_alpha >= 0: the record is first multiplied by scipy.signal.windows.tukey(n, tukey_alpha) (styx_fft.py:88-89)
+ *   sig / out: real [M, n] of `dtype` (out rows are n apart); n > padlen (else QI_ERR_ARG, scipy raises ValueError). */
+#define QI_IIR_BA 0
+#define QI_IIR_SOS 1
+#define QI_IIR_MAX_STATE 16
+typedef struct {
+    int32_t form;
+    int32_t n_coef;
+    double b[QI_IIR_MAX_STATE + 1];
+    double a[QI_IIR_MAX_STATE + 1];
+    double sos[QI_IIR_MAX_STATE / 2][6];
+    double zi[QI_IIR_MAX_STATE];
+} QiIirFilter;
+size_t qi_filtfilt_workspace_bytes(int64_t M, int64_t n, int padlen, int n_state);
+int qi_filtfilt(const void* sig, int64_t M, int64_t n, int64_t stride, const QiIirFilter* filter /*HOST*/, int padlen,
+                double tukey_alpha, int dtype, void* out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -726,3 +726,118 @@ def find_peaks_with_bits(timeseries, sample_rate_hz, scaling_type="amplitude", t
     else:
         height = np.max(timeseries) - 2 ** threshold_bits
     return find_peaks(bits, height=height, distance=int(time_distance_seconds * sample_rate_hz))
+
+
+# ============================================================================ before the path
+# styx_fft.py:60-149 (butter_bandpass / butter_highpass / butter_lowpass), synth/synthetic_signals.py:180-192
+# (antialias_half_nyquist) and utilities/picker.py:56-76 (apply_bandpass) call scipy.signal.filtfilt / sosfiltfilt
+# (scipy >= 1.15).  Their published algorithm is restated here sample by sample: scipy/signal/_lfilter.c.in (direct
+# form II transposed), _sosfilt.pyx (biquad cascade), _signaltools.py::lfilter_zi / sosfilt_zi / filtfilt /
+# sosfiltfilt (method="pad", padtype="odd"), windows/_windows.py::tukey.  `dtype=np.longdouble` runs the SAME
+# recursion in 80-bit arithmetic: the arbiter when float64 evaluations of these ill-conditioned recursions disagree.
+# The filter taps themselves come from scipy.signal.butter (design formulas, not record arithmetic).
+def tukey(m, alpha):
+    """scipy.signal.windows.tukey(m, alpha, sym=True)."""
+    if m == 1 or alpha <= 0:
+        return np.ones(m)
+    k = np.arange(m)
+    if alpha >= 1.0:
+        return 0.5 - 0.5 * np.cos(2.0 * np.pi * k / (m - 1))
+    width = int(np.floor(alpha * (m - 1) / 2.0))
+    n1, n3 = k[:width + 1], k[m - width - 1:]
+    w1 = 0.5 * (1 + np.cos(np.pi * (-1 + 2.0 * n1 / alpha / (m - 1))))
+    w3 = 0.5 * (1 + np.cos(np.pi * (-2.0 / alpha + 1 + 2.0 * n3 / alpha / (m - 1))))
+    return np.concatenate((w1, np.ones(m - 2 * width - 2), w3))
+
+
+def lfilter_zi(b, a):
+    """scipy.signal.lfilter_zi: the direct-form-II-transposed state of the step response's steady state."""
+    b, a = np.atleast_1d(np.asarray(b, dtype=np.float64)), np.atleast_1d(np.asarray(a, dtype=np.float64))
+    b, a = b / a[0], a / a[0]
+    n = max(len(a), len(b))
+    a, b = np.r_[a, np.zeros(n - len(a))], np.r_[b, np.zeros(n - len(b))]
+    companion_t = np.zeros((n - 1, n - 1))
+    companion_t[:, 0] = -a[1:]
+    companion_t[np.arange(n - 2), np.arange(1, n - 1)] = 1.0
+    return np.linalg.solve(np.eye(n - 1) - companion_t, b[1:] - a[1:] * b[0])
+
+
+def lfilter(b, a, x, zi, dtype=np.float64):
+    """scipy.signal.lfilter(b, a, x, zi=zi)[0] for a[0] == 1 (scipy/signal/_lfilter.c.in)."""
+    n = max(len(a), len(b))
+    b = np.r_[np.asarray(b, dtype=dtype), np.zeros(n - len(b), dtype=dtype)]
+    a = np.r_[np.asarray(a, dtype=dtype), np.zeros(n - len(a), dtype=dtype)]
+    z = np.asarray(zi, dtype=dtype).copy()
+    y = np.empty(len(x), dtype=dtype)
+    for i, xn in enumerate(np.asarray(x, dtype=dtype)):
+        yn = z[0] + b[0] * xn
+        for k in range(n - 2):
+            z[k] = z[k + 1] + xn * b[k + 1] - yn * a[k + 1]
+        z[n - 2] = xn * b[n - 1] - yn * a[n - 1]
+        y[i] = yn
+    return y
+
+
+def sosfilt_zi(sos):
+    """scipy.signal.sosfilt_zi."""
+    sos = np.asarray(sos, dtype=np.float64)
+    zi = np.empty((sos.shape[0], 2))
+    scale = 1.0
+    for s in range(sos.shape[0]):
+        b, a = sos[s, :3], sos[s, 3:]
+        zi[s] = scale * lfilter_zi(b, a)
+        scale *= b.sum() / a.sum()
+    return zi
+
+
+def sosfilt(sos, x, zi, dtype=np.float64):
+    """scipy.signal.sosfilt(sos, x, zi=zi)[0] (scipy/signal/_sosfilt.pyx)."""
+    sos = np.asarray(sos, dtype=dtype)
+    z = np.asarray(zi, dtype=dtype).copy()
+    y = np.empty(len(x), dtype=dtype)
+    for i, x_cur in enumerate(np.asarray(x, dtype=dtype)):
+        for s in range(sos.shape[0]):
+            x_new = sos[s, 0] * x_cur + z[s, 0]
+            z[s, 0] = sos[s, 1] * x_cur - sos[s, 4] * x_new + z[s, 1]
+            z[s, 1] = sos[s, 2] * x_cur - sos[s, 5] * x_new
+            x_cur = x_new
+        y[i] = x_cur
+    return y
+
+
+def _odd_ext(x, n):
+    return np.concatenate((2 * x[0] - x[n:0:-1], x, 2 * x[-1] - x[-2:-n - 2:-1]))
+
+
+def filtfilt(b, a, x, dtype=np.float64):
+    """scipy.signal.filtfilt(b, a, x): odd extension by 3 * ntaps, forward and backward lfilter from the steady state."""
+    b, a = np.atleast_1d(np.asarray(b, dtype=np.float64)), np.atleast_1d(np.asarray(a, dtype=np.float64))
+    b, a = b / a[0], a / a[0]
+    edge = 3 * max(len(a), len(b))
+    if len(x) <= edge:
+        raise ValueError(f"The length of the input vector x must be greater than padlen, which is {edge}.")
+    ext = _odd_ext(np.asarray(x, dtype=dtype), edge)
+    zi = lfilter_zi(b, a).astype(dtype)
+    y = lfilter(b, a, ext, zi * ext[0], dtype)
+    y = lfilter(b, a, y[::-1], zi * y[-1], dtype)
+    return y[::-1][edge:-edge]
+
+
+def sosfiltfilt(sos, x, dtype=np.float64):
+    """scipy.signal.sosfiltfilt(sos, x)."""
+    sos = np.asarray(sos, dtype=np.float64)
+    ntaps = 2 * sos.shape[0] + 1
+    ntaps -= min((sos[:, 2] == 0).sum(), (sos[:, 5] == 0).sum())
+    edge = 3 * int(ntaps)
+    if len(x) <= edge:
+        raise ValueError(f"The length of the input vector x must be greater than padlen, which is {edge}.")
+    ext = _odd_ext(np.asarray(x, dtype=dtype), edge)
+    zi = sosfilt_zi(sos).astype(dtype)
+    y = sosfilt(sos, ext, zi * ext[0], dtype)
+    y = sosfilt(sos, y[::-1], zi * y[-1], dtype)
+    return y[::-1][edge:-edge]
+
+
+def butter_filtfilt(b, a, sig, tukey_alpha, dtype=np.float64):
+    """styx_fft.py:87-90: filtfilt(b, a, sig * tukey(len(sig), alpha))."""
+    return filtfilt(b, a, np.asarray(sig, dtype=np.float64) * tukey(len(sig), tukey_alpha), dtype)

@@ -333,3 +333,39 @@ def divide(buf, dt, divisor, rt=None):
         rc = lib.qi_divide(rt.ptr(buf), n, DTYPE_CODE[dt], float(divisor), rt.ptr(out), rt.stream())
         _lib.check(lib, rc, "qi_divide")
     return out
+
+
+def filtfilt(sig, dt, padlen, tukey_alpha=None, b=None, a=None, sos=None, zi=None, rt=None):
+    """Run qi_filtfilt on a device buffer [M, n]: scipy.signal.filtfilt(b, a, x) (ba form) or sosfiltfilt(sos, x) along
+    the last axis, optionally after a Tukey taper.  b, a, sos, zi: host float64 (designed by the caller)."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    M, n = int(sig.shape[0]), int(sig.shape[1])
+    filt = np.zeros(1, dtype=_lib.IIR_FILTER)
+    if sos is None:
+        b, a = np.atleast_1d(np.asarray(b, dtype=np.float64)), np.atleast_1d(np.asarray(a, dtype=np.float64))
+        ntaps = max(len(a), len(b))
+        if ntaps - 1 > _lib.QI_IIR_MAX_STATE or ntaps < 2:
+            raise ValueError(f"filter order must be 1..{_lib.QI_IIR_MAX_STATE}")
+        filt["form"], filt["n_coef"] = _lib.QI_IIR_BA, ntaps
+        filt["b"][0, :len(b)] = b / a[0]
+        filt["a"][0, :len(a)] = a / a[0]
+        n_state = ntaps - 1
+    else:
+        sos = np.asarray(sos, dtype=np.float64)
+        if sos.ndim != 2 or sos.shape[1] != 6 or not 1 <= sos.shape[0] <= _lib.QI_IIR_MAX_STATE // 2:
+            raise ValueError(f"sos must be [1..{_lib.QI_IIR_MAX_STATE // 2}, 6]")
+        filt["form"], filt["n_coef"] = _lib.QI_IIR_SOS, sos.shape[0]
+        filt["sos"][0, :sos.shape[0]] = sos
+        n_state = 2 * sos.shape[0]
+    zi = np.asarray(zi, dtype=np.float64).reshape(-1)
+    filt["zi"][0, :n_state] = zi[:n_state]
+    if n <= padlen:
+        raise ValueError(f"The length of the input vector x must be greater than padlen, which is {padlen}.")
+    nbytes = lib.qi_filtfilt_workspace_bytes(M, n, int(padlen), n_state)
+    ws = rt.workspace(nbytes)
+    out = rt.empty((M, n), dt)
+    rc = lib.qi_filtfilt(rt.ptr(sig), M, n, n, filt.ctypes.data, int(padlen), -1.0 if tukey_alpha is None else float(tukey_alpha),
+                         DTYPE_CODE[dt], rt.ptr(out), rt.ptr(ws), nbytes, rt.stream())
+    _lib.check(lib, rc, "qi_filtfilt")
+    return out

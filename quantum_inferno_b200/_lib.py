@@ -28,6 +28,10 @@ STX_BAND = np.dtype([("sigma", "<f8"), ("shift", "<i8")], align=True)
 MR_BAND = np.dtype([("omega", "<f8"), ("scale", "<f8"), ("amp", "<f8"), ("level", "<i4"), ("reserved", "<i4")],
                    align=True)
 
+QI_IIR_BA, QI_IIR_SOS, QI_IIR_MAX_STATE = 0, 1, 16
+IIR_FILTER = np.dtype([("form", "<i4"), ("n_coef", "<i4"), ("b", "<f8", (17,)), ("a", "<f8", (17,)),
+                       ("sos", "<f8", (8, 6)), ("zi", "<f8", (16,))], align=True)
+
 _c_vp, _c_i64, _c_int, _c_sz, _c_dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t, ctypes.c_double
 
 # name -> (restype, argtypes); every symbol include/qi_b200.h declares
@@ -66,6 +70,8 @@ SIGNATURES = {
     "qi_extrema": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp]),
     "qi_local_maxima": (_c_int, [_c_vp, _c_i64, _c_int, _c_dbl, _c_int, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp]),
     "qi_select_peaks_by_distance": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp]),
+    "qi_filtfilt_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int, _c_int]),
+    "qi_filtfilt": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_dbl, _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
     "qi_divide": (_c_int, [_c_vp, _c_i64, _c_int, _c_dbl, _c_vp, _c_vp]),
 }
 

@@ -6,14 +6,19 @@ The reference delegates to scipy.signal.stft / welch; here the frame gather, det
 scaling are one CUDA kernel (csrc/qi_stft.cu) with scipy's exact edge semantics: zero extension by
 nperseg//2 on both sides, zero padding to a whole number of hops, per-frame mean removal after the
 extension, DFT-even (periodic) window, scale 1/sum(window).  ``nfft`` must be a power of two (it always is
-through the *_pow2 defaults).  The Butterworth filters of the reference module are IIR pre-processing,
-not part of the FFT hot path, and are not provided.  Keyword-only extra: ``dtype``.
+through the *_pow2 defaults).  Keyword-only extra: ``dtype``.
+
+The Butterworth pre-filters of the reference module (styx_fft.py:60-149: Tukey taper, ``scipy.signal.butter``,
+``scipy.signal.filtfilt``) run on the device too: scipy designs the (b, a) taps and the steady-state initial
+conditions on the host (a few dozen numbers; ``_iir.py`` re-factors the rounded taps into second-order sections so
+that the blocked evaluation stays well conditioned), and the taper, the odd extension and the two recursions over the
+record are the blocked parallel scan of csrc/qi_iir.cu (fp64 arithmetic; 2-D [channels, points] input accepted).
 """
 from typing import Tuple
 
 import numpy as np
 
-from . import _driver, _plan
+from . import _driver, _iir, _plan
 from .scales_dyadic import cycles_from_order
 from ._runtime import dtype_name, finish, get_runtime
 from .utilities.calculations import get_num_points
@@ -126,3 +131,73 @@ def stft_from_sig(sig_wf, frequency_sample_rate_hz: float, band_order_nth: float
     stft_complex *= stft_scaling
     stft_bits = to_log2_with_epsilon(stft_complex)
     return stft_complex, stft_bits, time_stft_s, frequency_stft_hz
+
+
+# ----------------------------------------------------------------------------- Butterworth pre-filters (styx_fft.py:60-149)
+def _butter_filtfilt(sig_wf, b, a, tukey_alpha):
+    """signal.filtfilt(b, a, sig * tukey(len(sig), alpha)) along the last axis (reference styx_fft.py:87-90)."""
+    rt = get_runtime()
+    want_numpy = not rt.is_device_array(sig_wf)
+    name = str(sig_wf.dtype).replace("torch.", "") if not want_numpy else np.asarray(sig_wf).dtype.name
+    dt = name if name in ("float32", "float64") else "float64"
+    x = rt.asarray(sig_wf, dt)
+    lead = tuple(int(v) for v in x.shape[:-1])
+    x2 = rt.reshape(x, (int(np.prod(lead)) if lead else 1, int(x.shape[-1])))
+    padlen = 3 * max(len(a), len(b))                                  # scipy.signal.filtfilt default
+    sos = _iir.tf2sos_exact(b, a)                                     # same transfer function, well-conditioned form
+    out = _driver.filtfilt(x2, dt, padlen, tukey_alpha=tukey_alpha, sos=sos, zi=_iir.sosfilt_zi(sos), rt=rt)
+    return finish(rt, rt.reshape(out, lead + (int(x.shape[-1]),)), want_numpy)
+
+
+def butter_bandpass(sig_wf: np.ndarray, frequency_sample_rate_hz: float, frequency_cut_low_hz, frequency_cut_high_hz,
+                    filter_order: int = 4, tukey_alpha: float = 0.5) -> np.ndarray:
+    """
+    Tukey-tapered zero-phase Butterworth band-pass (reference styx_fft.py:60-90).
+
+    :return: filtered signal waveform
+    """
+    from scipy import signal
+    nyquist = 0.5 * frequency_sample_rate_hz
+    edge_low = frequency_cut_low_hz / nyquist
+    edge_high = frequency_cut_high_hz / nyquist
+    if edge_high >= 1:
+        print(
+            f"Warning: Frequency cutoff {frequency_cut_high_hz} greater than Nyquist {nyquist} Hz, using half Nyquist"
+        )
+        edge_high = 0.5  # Half of nyquist
+    [b, a] = signal.butter(N=filter_order, Wn=[edge_low, edge_high], btype="bandpass")
+    return _butter_filtfilt(sig_wf, b, a, tukey_alpha)
+
+
+def butter_highpass(sig_wf: np.ndarray, frequency_sample_rate_hz: float, frequency_cut_low_hz, filter_order: int = 4,
+                    tukey_alpha: float = 0.5) -> np.ndarray:
+    """
+    Tukey-tapered zero-phase Butterworth high-pass (reference styx_fft.py:93-120).
+
+    :return: filtered signal waveform
+    """
+    from scipy import signal
+    edge_low = frequency_cut_low_hz / (0.5 * frequency_sample_rate_hz)
+    if edge_low >= 1:
+        raise ValueError(
+            f"Frequency cutoff {frequency_cut_low_hz} is greater than Nyquist {0.5*frequency_sample_rate_hz}"
+        )
+    [b, a] = signal.butter(N=filter_order, Wn=[edge_low], btype="highpass")
+    return _butter_filtfilt(sig_wf, b, a, tukey_alpha)
+
+
+def butter_lowpass(sig_wf: np.ndarray, frequency_sample_rate_hz: float, frequency_cut_high_hz, filter_order: int = 4,
+                   tukey_alpha: float = 0.5) -> np.ndarray:
+    """
+    Tukey-tapered zero-phase Butterworth low-pass (reference styx_fft.py:123-149).
+
+    :return: filtered signal waveform
+    """
+    from scipy import signal
+    edge_high = frequency_cut_high_hz / (0.5 * frequency_sample_rate_hz)
+    if edge_high >= 1:
+        raise ValueError(
+            f"Frequency cutoff {frequency_cut_high_hz} is greater than Nyquist {0.5*frequency_sample_rate_hz}"
+        )
+    [b, a] = signal.butter(N=filter_order, Wn=[edge_high], btype="lowpass")
+    return _butter_filtfilt(sig_wf, b, a, tukey_alpha)

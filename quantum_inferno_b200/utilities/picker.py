@@ -8,7 +8,8 @@ The O(n) work runs in csrc/qi_pick.cu on the record where it lies (HBM): extrema
 (``qi_abs_log2``), and the plateau-aware local-maximum scan of ``scipy.signal.find_peaks`` fused with its height
 test (``qi_local_maxima``).  What is left for the host is the short list of candidate peaks: sorting it and
 scipy's priority-ordered minimum-distance selection (``_select_by_peak_distance``), O(#peaks).  Peak indices are
-bit-exact.  The Butterworth band-pass variants (:56-105) are pre-processing (IIR) and are not provided.
+bit-exact.  The Butterworth band-pass variants (:56-105) design the sections with scipy on the host and run
+``sosfiltfilt`` over the record as the blocked parallel scan of csrc/qi_iir.cu.
 """
 from typing import Optional, Tuple, Union
 
@@ -62,6 +63,49 @@ def scale_signal_by_extraction_type(in_signal: np.ndarray, extraction_type: str 
     """
     rt, x, dt, want_numpy = _device_record(in_signal)
     return finish(rt, _scaled(rt, x, dt, extraction_type), want_numpy)
+
+
+def _bandpassed(rt, x, dt, filter_band, sample_rate_hz, filter_order):
+    """sosfiltfilt(butter(order, band, fs, "band", "sos"), x) on a device record (reference utilities/picker.py:56-76)."""
+    from scipy.signal import butter, sosfilt_zi
+    if filter_band[0] < 0 or filter_band[1] > sample_rate_hz / 2:
+        raise ValueError(f"Invalid bandpass filter band, {filter_band}, for sample rate {sample_rate_hz}")
+    if filter_band[0] >= filter_band[1]:
+        raise ValueError(
+            f"Invalid bandpass filter band, {filter_band}, the lower bound must be less than the upper bound"
+        )
+    sos = butter(filter_order, filter_band, fs=sample_rate_hz, btype="band", output="sos")
+    ntaps = 2 * sos.shape[0] + 1                                       # scipy.signal.sosfiltfilt's default padding
+    ntaps -= min((sos[:, 2] == 0).sum(), (sos[:, 5] == 0).sum())
+    out = _driver.filtfilt(rt.reshape(x, (1, x.shape[0])), dt, 3 * int(ntaps), sos=sos, zi=sosfilt_zi(sos), rt=rt)
+    return rt.reshape(out, (x.shape[0],))
+
+
+def apply_bandpass(timeseries: np.ndarray, filter_band: Tuple[float, float], sample_rate_hz: float,
+                   filter_order: int = 7) -> np.ndarray:
+    """
+    Zero-phase Butterworth band-pass in second-order sections (reference utilities/picker.py:56-76).
+
+    :return: filtered signal
+    """
+    rt, x, dt, want_numpy = _device_record(timeseries)
+    return finish(rt, _bandpassed(rt, x, dt, filter_band, sample_rate_hz, filter_order), want_numpy)
+
+
+def find_peaks_by_extraction_type_with_bandpass(timeseries: np.ndarray, filter_band: Tuple[float, float],
+                                                sample_rate_hz: float, filter_order: int = 7,
+                                                extraction_type: str = "sigmax", height: Optional[float] = 0.7,
+                                                *args) -> np.ndarray:
+    """
+    Peaks of the band-passed, scaled record that reach ``height`` (reference utilities/picker.py:79-105); the record
+    stays on the device from the filter to the peak scan.
+
+    :return: sample positions of the peaks (int64, ascending)
+    """
+    _no_extra(args)
+    rt, x, dt, _ = _device_record(timeseries)
+    filtered = _bandpassed(rt, x, dt, filter_band, sample_rate_hz, filter_order)
+    return _find_peaks(rt, _scaled(rt, filtered, dt, extraction_type), dt, height)
 
 
 def _select_by_peak_distance(lib, peaks: np.ndarray, priority: np.ndarray, distance: float) -> np.ndarray:

@@ -263,3 +263,11 @@ def test_picker(golden, capsys):
     pc.check_picker_golden(golden)
     pc.check_picker_edges(capsys)
     pc.check_picker_vs_oracle(n=30000)
+
+
+# ----------------------------------------------------------------------------- before the path
+def test_butter_filters(golden, capsys):
+    from tests import _iir_checks as ic
+    ic.check_butter_golden(golden, capsys)
+    ic.check_picker_bandpass_golden(golden)
+    ic.check_filtfilt_vs_oracle(n=9000)

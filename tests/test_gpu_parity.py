@@ -462,3 +462,32 @@ def test_subsample_plane_properties(torch_cuda):
     for m in ("max", "min", "nth"):
         assert torch.equal(sampling.subsample_2d(sampling.subsample_2d(p, 32, m), 64, m), sampling.subsample_2d(p, 2048, m))
     assert torch.equal(sampling.subsample_2d(p, 2048, "median"), p.reshape(12, -1, 2048).sort(dim=2).values[:, :, 1023:1025].sum(dim=2) / 2)
+
+
+# ----------------------------------------------------------------------------- before the path
+def test_butter_filters_gpu(torch_cuda, golden, capsys):
+    from tests import _iir_checks as ic
+    ic.check_butter_golden(golden, capsys)
+    ic.check_picker_bandpass_golden(golden)
+    ic.check_filtfilt_vs_oracle(n=20000)
+
+
+def test_filtfilt_long_record_properties(torch_cuda):
+    """16 x 2^20 float64 records kept on the device: linearity, time reversal (filtfilt commutes with reversing the
+    record), and the zero-phase pass band (a 60 Hz tone goes through a 10-100 Hz band-pass unchanged in the middle)."""
+    from quantum_inferno_b200 import styx_fft
+    torch = torch_cuda
+    n = 1 << 20
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((16, n), generator=gen, device="cuda", dtype=torch.float64)
+    y = torch.randn((16, n), generator=gen, device="cuda", dtype=torch.float64)
+    f = lambda v: styx_fft.butter_bandpass(v, FS, 10.0, 100.0, 4, 0.0)
+    fx, fy = f(x), f(y)
+    assert isinstance(fx, torch.Tensor) and fx.shape == x.shape
+    scale = float(fx.abs().max())
+    assert float((f(2.0 * x - 3.0 * y) - (2.0 * fx - 3.0 * fy)).abs().max()) < 1e-11 * scale
+    assert float((f(x.flip(1)).flip(1) - fx).abs().max()) < 1e-11 * scale
+    k = torch.arange(n, device="cuda", dtype=torch.float64)
+    tone = torch.cos(2 * np.pi * 60.0 / FS * k)[None, :]
+    mid = slice(n // 4, 3 * n // 4)
+    assert float((f(tone)[0, mid] - tone[0, mid]).abs().max()) < 1e-4          # |H(60 Hz)|^2 = 1 - 5e-5 for this design

@@ -196,3 +196,29 @@ def test_picker_oracle(golden):
     assert np.array_equal(orc.find_peaks_by_extraction_type(g["noise"], "sigmax", 0.5), g["noise_peaks_sigmax"])
     assert len(g["peaks_sigmax_0.3"]) > len(g["peaks_sigmax_0.7"]) > 0          # the fixture is not vacuous
     assert len(g["bits_log2_3_0.01"]) > len(g["bits_log2_3_0.5"]) > 0
+
+
+# ----------------------------------------------------------------------------- before the path
+def test_filtfilt_oracle(golden):
+    """The float64 restatement of scipy's filtfilt / sosfiltfilt reproduces the reference's outputs (same recursion,
+    same order of operations); the long-double run of it stays within the recursion's own rounding noise."""
+    g = golden("iir")
+    x = g["x"]
+    for name in ("lowpass_100", "highpass_5", "bandpass_10_100", "bandpass_58_62", "bandpass_nyq", "lowpass_o5", "antialias"):
+        alpha = float(g[f"{name}_alpha"])
+        xt = x if alpha < 0 else x * orc.tukey(len(x), alpha)
+        got = orc.filtfilt(g[f"{name}_b"], g[f"{name}_a"], xt)
+        ref = g[f"{name}_ref"]
+        noise = np.max(np.abs(ref - g[f"{name}_truth"])) / np.max(np.abs(ref))
+        assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) <= max(2.0 * noise, 1e-14), name
+        assert noise < 1e-7
+    for name in ("pick_100_200_o7", "pick_1_10_o4", "pick_50_70_o2"):
+        got, ref = orc.sosfiltfilt(g[f"{name}_sos"], x), g[f"{name}_ref"]
+        noise = np.max(np.abs(ref - g[f"{name}_truth"])) / np.max(np.abs(ref))
+        assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) <= max(2.0 * noise, 1e-14) and noise < 1e-11, name
+    b, a = g["bandpass_10_100_b"], g["bandpass_10_100_a"]
+    from scipy import signal
+    assert np.allclose(orc.lfilter_zi(b, a), signal.lfilter_zi(b, a), rtol=1e-9, atol=0)
+    assert np.allclose(orc.sosfilt_zi(g["pick_1_10_o4_sos"]), signal.sosfilt_zi(g["pick_1_10_o4_sos"]), rtol=1e-9)
+    for m, al in ((100, 0.3), (101, 0.5), (64, 1.0), (10, 0.0), (7, 0.9)):
+        assert np.allclose(orc.tukey(m, al), signal.windows.tukey(m, al), rtol=0, atol=1e-15)

@@ -163,6 +163,26 @@ def cfg7():
     return out
 
 
+def cfg8():
+    """the Butterworth pre-filters in front of the path.  butter_bandpass (order 4 -> 4 sections,
+    Tukey taper fused) on 16 x 2^22 records, float64 and float32 I/O (fp64 arithmetic), and the picker's order-7
+    sosfiltfilt on one 2^24 record.  Algorithmic bytes: record read + result written (2 x element size per sample);
+    real traffic is ~48 B per sample (three kernels per direction, fp64 intermediate)."""
+    from quantum_inferno_b200 import styx_fft
+    from quantum_inferno_b200.utilities import picker
+    x = synth_batch_torch(torch, 1 << 22, list(range(16)), DEV)
+    out = {"config": "cfg8: butter_bandpass 10-100 Hz order 4, 16 x 2^22; picker.apply_bandpass order 7, 1 x 2^24"}
+    for dt, xx in (("float32", x), ("float64", x.double())):
+        ms, y = timed(lambda: styx_fft.butter_bandpass(xx, FS, 10.0, 100.0))
+        out[dt] = {"ms": ms, "samples_per_s": xx.numel() / ms * 1e3, "alg_GBps": 2 * xx.numel() * xx.element_size() / ms / 1e6,
+                   "traffic_model_GBps": 48.0 * xx.numel() / ms / 1e6}
+    del x, xx
+    r = synth_batch_torch(torch, 1 << 24, [0], DEV)[0].double()
+    ms, y = timed(lambda: picker.apply_bandpass(r, (100.0, 200.0), FS, 7))
+    out["sos_order7"] = {"ms": ms, "samples_per_s": r.numel() / ms * 1e3, "alg_GBps": 16.0 * r.numel() / ms / 1e6}
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg1", "cfg2", "cfg3", "cfg4"]
     for name in which:
