@@ -473,8 +473,9 @@ def test_butter_filters_gpu(torch_cuda, golden, capsys):
 
 
 def test_filtfilt_long_record_properties(torch_cuda):
-    """16 x 2^20 float64 records kept on the device: linearity, time reversal (filtfilt commutes with reversing the
-    record), and the zero-phase pass band (a 60 Hz tone goes through a 10-100 Hz band-pass unchanged in the middle)."""
+    """16 x 2^20 float64 records kept on the device: linearity, time reversal (away from the padded edges filtfilt
+    commutes with reversing the record: |H|^2 has zero phase), and the pass band (a 60 Hz tone goes through a
+    10-100 Hz band-pass unchanged in the middle)."""
     from quantum_inferno_b200 import styx_fft
     torch = torch_cuda
     n = 1 << 20
@@ -486,8 +487,8 @@ def test_filtfilt_long_record_properties(torch_cuda):
     assert isinstance(fx, torch.Tensor) and fx.shape == x.shape
     scale = float(fx.abs().max())
     assert float((f(2.0 * x - 3.0 * y) - (2.0 * fx - 3.0 * fy)).abs().max()) < 1e-11 * scale
-    assert float((f(x.flip(1)).flip(1) - fx).abs().max()) < 1e-11 * scale
+    mid = slice(n // 4, 3 * n // 4)
+    assert float((f(x.flip(1)).flip(1) - fx)[:, mid].abs().max()) < 1e-11 * scale
     k = torch.arange(n, device="cuda", dtype=torch.float64)
     tone = torch.cos(2 * np.pi * 60.0 / FS * k)[None, :]
-    mid = slice(n // 4, 3 * n // 4)
     assert float((f(tone)[0, mid] - tone[0, mid]).abs().max()) < 1e-4          # |H(60 Hz)|^2 = 1 - 5e-5 for this design
