@@ -20,7 +20,7 @@ struct StftGeom {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g, cplx<T>* __restrict__ out,
             double* __restrict__ psd_acc) {
     QI_DYN_SMEM(smem_raw);
@@ -42,17 +42,30 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
                           first + (i64)(2 * TC - 1) * g.hop + g.nperseg <= g.n_points &&
                           (i64)(2 * TC - 1) * g.hop + R < (1ll << 30);
     if (interior) {
+        // eight (frame a, frame b) sample pairs per thread are requested before the first is stored: the gather is the
+        // only HBM-latency-bound phase of the kernel and needs the loads in flight, not one dependent pair per trip
         const T* xb0 = x + first;
-        for (int idx = threadIdx.x; idx < R * TC; idx += blockDim.x) {
-            const int r = idx & (R - 1);
-            const int c = idx >> g.logF;
-            T va = (T)0, vb = (T)0;
-            if (r < g.nperseg) {
-                const int o = 2 * c * g.hop + r;
-                va = xb0[o];
-                vb = xb0[o + g.hop];
+        constexpr int GU = 8;
+        const int total_g = R * TC;
+        for (int base = threadIdx.x; base < total_g; base += blockDim.x * GU) {
+            T va[GU], vb[GU];
+#pragma unroll
+            for (int u = 0; u < GU; ++u) {
+                const int idx = base + u * (int)blockDim.x;
+                const int r = idx & (R - 1);
+                const int c = idx >> g.logF;
+                va[u] = (T)0; vb[u] = (T)0;
+                if (idx < total_g && r < g.nperseg) {
+                    const int o = 2 * c * g.hop + r;
+                    va[u] = xb0[o];
+                    vb[u] = xb0[o + g.hop];
+                }
             }
-            tile[r * TP + c] = mk<T>(va, vb);
+#pragma unroll
+            for (int u = 0; u < GU; ++u) {
+                const int idx = base + u * (int)blockDim.x;
+                if (idx < total_g) tile[(idx & (R - 1)) * TP + (idx >> g.logF)] = mk<T>(va[u], vb[u]);
+            }
         }
     } else {
         for (int idx = threadIdx.x; idx < R * TC; idx += blockDim.x) {
