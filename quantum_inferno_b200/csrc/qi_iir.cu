@@ -95,7 +95,7 @@ QI_DEV double iir_input(const IirIo& io, i64 m, i64 p, int backward) {
 
 // z += P * left over a 256-entry state table; the scan both kernels share.  st: [256][KP + 1] shared doubles.
 template <int KP>
-QI_DEV void iir_block_scan(double* z, double* st, const double* __restrict__ mats) {
+QI_DEV void iir_block_scan(double* z, double* st, const double* mats) {
     const int tid = threadIdx.x;
 #pragma unroll
     for (int r = 0; r < KP; ++r) st[tid * (KP + 1) + r] = z[r];
@@ -124,24 +124,27 @@ QI_DEV void iir_block_scan(double* z, double* st, const double* __restrict__ mat
     }
 }
 
-// grid: (ntiles, M); dynamic shared memory: (IIR_T * IIR_PITCH + IIR_T * (KP + 1)) doubles
+// grid: (ntiles, M); dynamic shared memory: (IIR_T * IIR_PITCH + IIR_T * (KP + 1) + IIR_LEVELS * KP * KP) doubles.
+// The chunk's samples stay in the shared tile (not in registers) and the level matrices are staged in shared memory,
+// so that three CTAs share an SM.
 template <int KP, bool FINAL>
-__global__ void __launch_bounds__(IIR_T)
+__global__ void __launch_bounds__(IIR_T, (KP <= 8 ? 3 : 2))
 iir_tile_kernel(IirCoef c, IirIo io, int backward, const double* __restrict__ mats, double* __restrict__ agg,
                 const double* __restrict__ tile_in, i64 ntiles) {
     QI_DYN_SMEM(raw);
     double* tile = reinterpret_cast<double*>(raw);
     double* st = tile + IIR_T * IIR_PITCH;
+    double* smats = st + IIR_T * (KP + 1);
     const int tid = threadIdx.x;
     const i64 m = blockIdx.y, t = blockIdx.x, p0 = t * IIR_TILE;
+    for (int i = tid; i < IIR_LEVELS * KP * KP; i += IIR_T) smats[i] = mats[i];
     for (int i = tid; i < IIR_TILE; i += IIR_T) {
         const i64 p = p0 + i;
         tile[(i / IIR_L) * IIR_PITCH + (i % IIR_L)] = p < io.n_ext ? iir_input(io, m, p, backward) : 0.0;
     }
     __syncthreads();
-    double xs[IIR_L], z[KP], s0[KP];
-#pragma unroll
-    for (int i = 0; i < IIR_L; ++i) xs[i] = tile[tid * IIR_PITCH + i];
+    double* xs = tile + tid * IIR_PITCH;
+    double z[KP], s0[KP];
 #pragma unroll
     for (int r = 0; r < KP; ++r) {
         s0[r] = (FINAL && tid == 0) ? tile_in[(m * ntiles + t) * KP + r] : 0.0;
@@ -149,7 +152,7 @@ iir_tile_kernel(IirCoef c, IirIo io, int backward, const double* __restrict__ ma
     }
 #pragma unroll
     for (int i = 0; i < IIR_L; ++i) iir_step<KP, double>(c, xs[i], z);
-    iir_block_scan<KP>(z, st, mats);
+    iir_block_scan<KP>(z, st, smats);
     if (!FINAL) {
         if (tid == IIR_T - 1) {
 #pragma unroll
@@ -162,7 +165,7 @@ iir_tile_kernel(IirCoef c, IirIo io, int backward, const double* __restrict__ ma
         for (int r = 0; r < KP; ++r) s0[r] = st[(tid - 1) * (KP + 1) + r];
     }
 #pragma unroll
-    for (int i = 0; i < IIR_L; ++i) tile[tid * IIR_PITCH + i] = iir_step<KP, double>(c, xs[i], s0);
+    for (int i = 0; i < IIR_L; ++i) xs[i] = iir_step<KP, double>(c, xs[i], s0);
     __syncthreads();
     for (int i = tid; i < IIR_TILE; i += IIR_T) {
         const i64 p = p0 + i;
@@ -269,7 +272,7 @@ static int filtfilt_impl(const IirCoef& c, IirIo io, i64 M, void* ws, size_t ws_
     double* d_in = reinterpret_cast<double*>(base + mats_bytes + vec_bytes);
     io.y1 = reinterpret_cast<double*>(base + mats_bytes + 2 * vec_bytes);
     stage_to_device(d_mats, host.data(), mats_bytes, st);
-    const size_t smem = sizeof(double) * (IIR_T * IIR_PITCH + IIR_T * (KP + 1));
+    const size_t smem = sizeof(double) * (IIR_T * IIR_PITCH + IIR_T * (KP + 1) + IIR_LEVELS * KP * KP);
 #ifndef QI_EMUL
     cudaFuncSetAttribute(iir_tile_kernel<KP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(iir_tile_kernel<KP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

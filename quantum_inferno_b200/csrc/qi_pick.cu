@@ -151,8 +151,21 @@ template <typename T, int METHOD> QI_DEV T sub_combine(T r, T v) {
     if (METHOD == QI_SUB_MAX) return (v > r || v != v) ? v : r;      // NaN-propagating: once r is NaN it stays
     return (v < r || v != v) ? v : r;
 }
+#ifndef QI_EMUL
+// float: the hardware's NaN-propagating max / min (numpy's semantics) in one instruction
+template <> QI_DEV float sub_combine<float, QI_SUB_MAX>(float r, float v) {
+    float o;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(o) : "f"(r), "f"(v));
+    return o;
+}
+template <> QI_DEV float sub_combine<float, QI_SUB_MIN>(float r, float v) {
+    float o;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(o) : "f"(r), "f"(v));
+    return o;
+}
+#endif
 template <typename T, int METHOD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 subsample_vec_kernel(const T* __restrict__ in, i64 stride, i64 n_vec, int factor, T* __restrict__ out, i64 n_out) {
     constexpr int V = 16 / (int)sizeof(T), U = 4;
     typedef double Acc;
@@ -161,6 +174,7 @@ subsample_vec_kernel(const T* __restrict__ in, i64 stride, i64 n_vec, int factor
     T* orow = out + m * n_out;
     const int lanes = factor >= V ? factor / V : 1;                   // lanes that share a group
     const int per = factor >= V ? V : factor;                         // samples of one group inside a vector (fp32, factor 2: 2)
+    const Acc inv = (Acc)1 / (Acc)factor;                             // factor is a power of two here: s * inv == s / factor exactly
     for (i64 base = (i64)blockIdx.x * (256 * U); base < n_vec; base += (i64)gridDim.x * (256 * U)) {
         T v[U][V];
 #pragma unroll
@@ -189,7 +203,7 @@ subsample_vec_kernel(const T* __restrict__ in, i64 stride, i64 n_vec, int factor
 #pragma unroll
                     for (int e = 0; e < V; ++e) s += (Acc)v[u][e];
                     for (int o = lanes >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (live && (threadIdx.x & (lanes - 1)) == 0) orow[idx / lanes] = (T)(s / (Acc)factor);
+                    if (live && (threadIdx.x & (lanes - 1)) == 0) orow[idx / lanes] = (T)(s * inv);
                 } else {
                     T r = v[u][0];
 #pragma unroll
