@@ -297,6 +297,15 @@ size_t qi_filtfilt_workspace_bytes(int64_t M, int64_t n, int padlen, int n_state
 int qi_filtfilt(const void* sig, int64_t M, int64_t n, int64_t stride, const QiIirFilter* filter /*HOST*/, int padlen,
                 double tukey_alpha, int dtype, void* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- device-side synthetic inputs -----------------------------------------
+ * Replaces the array expressions of quantum_inferno/synth/benchmark_signals.py:92-101 (quantum_chirp) and :323-335
+ * (well_tempered_tone).  For k = 0..n-1 (every one of the M rows gets the same waveform):
+ *   time = (k + k0) - t_center;  u = time / chirp_scale;  phase = omega * time + half_gamma * u^2
+ *   out_re = A cos(phase), out_im = A sin(phase) (or NULL), A = exp(-0.5 u^2) if gauss else 1
+ * float64 arithmetic in the reference's order; outputs real [M, n] of `dtype`, rows `stride` apart. */
+int qi_synth_chirp(int64_t M, int64_t n, int64_t stride, int64_t k0, double t_center, double omega, double half_gamma,
+                   double chirp_scale, int gauss, int dtype, void* out_re, void* out_im, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -841,3 +841,35 @@ def sosfiltfilt(sos, x, dtype=np.float64):
 def butter_filtfilt(b, a, sig, tukey_alpha, dtype=np.float64):
     """styx_fft.py:87-90: filtfilt(b, a, sig * tukey(len(sig), alpha))."""
     return filtfilt(b, a, np.asarray(sig, dtype=np.float64) * tukey(len(sig), tukey_alpha), dtype)
+
+
+# ============================================================================ synthetic inputs (SURVEY 8f rank 2)
+def well_tempered_tone(fs=800.0, f_center=60.0, duration_s=10.24, fft_s=0.64, use_fft_frequency=True):
+    """synth/benchmark_signals.py:268-355 (deterministic branch): cos(2 pi f_c n) with f_c snapped to an FFT bin."""
+    n = 2 ** int(np.log2(duration_s * fs))
+    n_fft = 2 ** int(np.log2(fft_s * fs))
+    f_pos = np.fft.rfftfreq(n_fft, d=1 / fs)
+    f_fft = f_pos[np.argmin(np.abs(f_pos - f_center))]
+    f_c = (f_fft if use_fft_frequency else f_center) / fs
+    k = np.arange(n)
+    return np.cos(2.0 * np.pi * f_c * k), k / fs, n_fft, fs, f_fft, fs / n_fft
+
+
+def decimate(x, q, dtype=np.float64):
+    """scipy.signal.decimate(x, q, zero_phase=True): sosfiltfilt with cheby1(8, 0.05, 0.8 / q), every q-th sample
+    (the Chebyshev sections are scipy's design; the record arithmetic is restated)."""
+    from scipy.signal import cheby1
+    return sosfiltfilt(cheby1(8, 0.05, 0.8 / q, output="sos"), x, dtype)[::q]
+
+
+def quantum_chirp(omega, order=12.0, gamma=0.0, gauss=True, oversample_scale=2):
+    """synth/benchmark_signals.py:57-109."""
+    if omega >= 0.8 * np.pi:
+        omega = np.pi * 2 ** (-1 / order)
+    chirp_scale = (3.0 / 4.0 * np.pi * order / omega) * np.sqrt(1 + gamma ** 2)
+    support = 2 ** int(np.ceil(np.log2(2.0 * np.pi * chirp_scale)))
+    time0 = np.arange(oversample_scale * support)
+    time = time0 - time0[-1] / 2
+    phase = omega * time + 0.5 * gamma * (time / chirp_scale) ** 2
+    wf = np.exp(-0.5 * (time / chirp_scale) ** 2 + 1j * phase) if gauss else np.exp(1j * phase)
+    return decimate(np.real(wf), oversample_scale) + 1j * decimate(np.imag(wf), oversample_scale), support

@@ -369,3 +369,18 @@ def filtfilt(sig, dt, padlen, tukey_alpha=None, b=None, a=None, sos=None, zi=Non
                          DTYPE_CODE[dt], rt.ptr(out), rt.ptr(ws), nbytes, rt.stream())
     _lib.check(lib, rc, "qi_filtfilt")
     return out
+
+
+def synth_chirp(n, dt, omega, t_center=0.0, half_gamma=0.0, chirp_scale=1.0, gauss=False, want_imag=False, rt=None):
+    """Run qi_synth_chirp: device buffer [1, n] (real part) or [2, n] (real, imaginary) of the Gabor chirp / tone
+    (synth/benchmark_signals.py:92-101, :323-335)."""
+    rt = rt or get_runtime()
+    lib = rt.lib
+    n = int(n)
+    out = rt.empty((2 if want_imag else 1, n), dt)
+    itemsize = 4 if dt == "float32" else 8
+    rc = lib.qi_synth_chirp(1, n, n, 0, float(t_center), float(omega), float(half_gamma), float(chirp_scale),
+                            int(bool(gauss)), DTYPE_CODE[dt], rt.ptr(out), rt.ptr(out) + n * itemsize if want_imag else None,
+                            rt.stream())
+    _lib.check(lib, rc, "qi_synth_chirp")
+    return out

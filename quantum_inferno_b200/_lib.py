@@ -72,6 +72,8 @@ SIGNATURES = {
     "qi_select_peaks_by_distance": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp]),
     "qi_filtfilt_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int, _c_int]),
     "qi_filtfilt": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_dbl, _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
+    "qi_synth_chirp": (_c_int, [_c_i64, _c_i64, _c_i64, _c_i64, _c_dbl, _c_dbl, _c_dbl, _c_dbl, _c_int, _c_int, _c_vp, _c_vp,
+                                _c_vp]),
     "qi_divide": (_c_int, [_c_vp, _c_i64, _c_int, _c_dbl, _c_vp, _c_vp]),
 }
 

@@ -271,3 +271,10 @@ def test_butter_filters(golden, capsys):
     ic.check_butter_golden(golden, capsys)
     ic.check_picker_bandpass_golden(golden)
     ic.check_filtfilt_vs_oracle(n=9000)
+
+
+# ----------------------------------------------------------------------------- synthetic inputs
+def test_synth_and_decimate(golden, capsys):
+    from tests import _synth_checks as sc
+    sc.check_synth_golden(golden, capsys)
+    sc.check_decimate_golden(golden)

@@ -496,3 +496,16 @@ def test_filtfilt_long_record_properties(torch_cuda):
     gain = float(np.abs(signal.freqz(b, a, worN=[60.0], fs=FS)[1][0]) ** 2)       # zero phase, |H|^2 amplitude
     assert 0.99 < gain < 1.0
     assert float((f(tone)[0, mid] - gain * tone[0, mid]).abs().max()) < 1e-9
+
+
+# ----------------------------------------------------------------------------- synthetic inputs
+def test_synth_and_decimate_gpu(torch_cuda, golden, capsys):
+    from tests import _synth_checks as sc
+    sc.check_synth_golden(golden, capsys)
+    sc.check_decimate_golden(golden)
+    # bench-size tone made on the device: 2^24 samples, stays a tensor, equals the closed form at probe points
+    from quantum_inferno_b200.synth import benchmark_signals as bs
+    sig, t, nfft, fs, fc, df = bs.well_tempered_tone(800.0, 60.0, (1 << 24) / 800.0, 0.64, dtype="float32", device_out=True)
+    assert isinstance(sig, torch_cuda.Tensor) and sig.shape == (1 << 24,) and sig.dtype == torch_cuda.float32
+    k = np.array([0, 1, 12345, (1 << 23) + 7, (1 << 24) - 1])
+    assert np.max(np.abs(sig[k].cpu().numpy() - np.cos(2.0 * np.pi * (fc / fs) * k))) < 2e-7

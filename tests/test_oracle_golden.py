@@ -222,3 +222,20 @@ def test_filtfilt_oracle(golden):
     assert np.allclose(orc.sosfilt_zi(g["pick_1_10_o4_sos"]), signal.sosfilt_zi(g["pick_1_10_o4_sos"]), rtol=1e-9)
     for m, al in ((100, 0.3), (101, 0.5), (64, 1.0), (10, 0.0), (7, 0.9)):
         assert np.allclose(orc.tukey(m, al), signal.windows.tukey(m, al), rtol=0, atol=1e-15)
+
+
+# ----------------------------------------------------------------------------- synthetic inputs
+def test_synth_oracle(golden):
+    g = golden("synth")
+    sig, t, nfft, fs, fc, df = orc.well_tempered_tone()
+    assert np.array_equal(sig, g["tone0_sig"]) and np.array_equal(t, g["tone0_t"])
+    assert np.array_equal([nfft, fs, fc, df], g["tone0_meta"])
+    sig = orc.well_tempered_tone(800.0, 61.3, 20.48, 1.28, use_fft_frequency=False)[0]
+    assert np.array_equal(sig, g["tone1_sig"])
+    for i, kw in enumerate([dict(omega=2 * np.pi * 60 / 800, order=3), dict(omega=0.3, order=12, gamma=0.7),
+                            dict(omega=0.9 * np.pi, order=6, gauss=False), dict(omega=0.2, order=3, oversample_scale=4)]):
+        wf, support = orc.quantum_chirp(**kw)
+        assert support == int(g[f"chirp{i}_support"])
+        assert np.max(np.abs(wf - g[f"chirp{i}_wf"])) / np.max(np.abs(g[f"chirp{i}_wf"])) < 1e-12
+    for q in (2, 4, 10):
+        assert np.max(np.abs(orc.decimate(g["x"], q) - g[f"dec_{q}"])) / np.max(np.abs(g[f"dec_{q}"])) < 1e-11
