@@ -12,7 +12,7 @@
 
 namespace qi {
 
-struct DevStxBand { double q; long long shift; };   // q = sigma*2*pi/n
+struct DevStxBand { double q; long long shift; long long kmax; };   // q = sigma*2*pi/n; |k| > kmax: the window underflows to 0
 
 template <typename T> struct SrcStxSpec {
     const cplx<T>* spec; const DevStxBand* bands; int band0; CwtGeom geo;
@@ -21,9 +21,11 @@ template <typename T> struct SrcStxSpec {
         const DevStxBand b = bands[band0 + (int)(batch / geo.n_channels)];
         const i64 n = 1ll << geo.logL;
         const i64 k = (i64)brev_bits((unsigned)e, geo.logL);
+        const i64 ks = (k < (n >> 1)) ? k : k - n;                 // signed bin (fftfreq ordering)
+        // beyond kmax exp() returns exactly 0 in T: same product, without the gather and the exponential
+        if (ks > b.kmax || -ks > b.kmax) return mk<T>((T)0, (T)0);
         const i64 ksrc = (k + b.shift) & (n - 1);
         const cplx<T> X = spec[(chan << geo.logL) + (i64)brev_bits((unsigned)ksrc, geo.logL)];
-        const i64 ks = (k < (n >> 1)) ? k : k - n;                 // signed bin (fftfreq ordering)
         const T u = (T)b.q * (T)ks;
         const T w = exp((T)-0.5 * u * u) * (T)(1.0 / (double)n);
         return X * w;
@@ -58,11 +60,16 @@ template <typename T> static StxLayout stx_layout(i64 C, i64 N, int B, int group
     return lo;
 }
 
-static void upload_stx_bands(const QiStxBand* hb, int B, i64 N, DevStxBand* d_bands, cudaStream_t st) {
+// u_zero: |u| from which exp(-0.5 u^2) is exactly 0 in the arithmetic type (below the smallest subnormal, with margin:
+// float32 exp(-104) = 6.8e-46 < 2^-150; float64 exp(-746) < 2^-1075)
+static void upload_stx_bands(const QiStxBand* hb, int B, i64 N, double u_zero, DevStxBand* d_bands, cudaStream_t st) {
     std::vector<DevStxBand> db(B);
     for (int b = 0; b < B; ++b) {
         db[b].q = hb[b].sigma * 2.0 * M_PI / (double)N;
         db[b].shift = ((hb[b].shift % N) + N) % N;
+        const double aq = fabs(db[b].q);
+        const double km = aq > 0.0 ? ceil(u_zero / aq) + 2.0 : (double)N;
+        db[b].kmax = km < (double)N ? (long long)km : (long long)N;
     }
     stage_to_device(d_bands, db.data(), sizeof(DevStxBand) * (size_t)B, st);
 }
@@ -77,7 +84,7 @@ static int stx_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiStxBa
     DevStxBand* d_bands = reinterpret_cast<DevStxBand*>(base + lo.off_bands);
     cplx<T>* spec = reinterpret_cast<cplx<T>*>(base + lo.off_spec);
     cplx<T>* work = reinterpret_cast<cplx<T>*>(base + lo.off_work);
-    upload_stx_bands(hb, B, N, d_bands, st);
+    upload_stx_bands(hb, B, N, sizeof(T) == 4 ? 14.5 : 38.7, d_bands, st);
 
     CwtGeom geo;
     geo.n_points = N; geo.n_channels = C; geo.n_bands = B; geo.logL = lo.logL;
@@ -122,7 +129,7 @@ template <typename T>
 static int stx_windows_impl(const QiStxBand* hb, int B, i64 N, void* out, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (ws_bytes < sizeof(DevStxBand) * (size_t)B) return QI_ERR_WORKSPACE;
     DevStxBand* d_bands = static_cast<DevStxBand*>(ws);
-    upload_stx_bands(hb, B, N, d_bands, st);
+    upload_stx_bands(hb, B, N, 1e300, d_bands, st);
     dim3 grid((unsigned)((N + 255) / 256), (unsigned)B);
     QI_LAUNCH((stx_windows_kernel<T>), grid, dim3(256), 0, st, d_bands, N, static_cast<cplx<T>*>(out));
     return check_cuda("qi_stx_windows");
