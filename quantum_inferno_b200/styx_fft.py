@@ -125,12 +125,14 @@ def stft_from_sig(sig_wf, frequency_sample_rate_hz: float, band_order_nth: float
     if len(sig_wf) < time_fft_nd:
         raise ValueError(f"Signal length: {len(sig_wf)} is less than time_fft_nd: {time_fft_nd}")
     stft_scaling = 2 * np.sqrt(np.pi) / time_fft_nd
+    rt = get_runtime()
+    want_numpy = not rt.is_device_array(sig_wf)
     frequency_stft_hz, time_stft_s, stft_complex = stft_complex_pow2(
-        sig_wf=sig_wf, frequency_sample_rate_hz=frequency_sample_rate_hz, segment_points=time_fft_nd, alpha=1.0,
-        dtype=dtype)
+        sig_wf=rt.asarray(sig_wf, dtype_name(dtype)), frequency_sample_rate_hz=frequency_sample_rate_hz,
+        segment_points=time_fft_nd, alpha=1.0, dtype=dtype)                 # stays on the device
     stft_complex *= stft_scaling
     stft_bits = to_log2_with_epsilon(stft_complex)
-    return stft_complex, stft_bits, time_stft_s, frequency_stft_hz
+    return finish(rt, stft_complex, want_numpy), finish(rt, stft_bits, want_numpy), time_stft_s, frequency_stft_hz
 
 
 # ----------------------------------------------------------------------------- Butterworth pre-filters (styx_fft.py:60-149)
