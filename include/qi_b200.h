@@ -237,7 +237,8 @@ int qi_rfft(const void* sig, int64_t M, int64_t n, int64_t sig_stride, int dtype
  *   NTH     : out[m, j] = in[m, j*factor],                 n_out = ceil(n_in / factor)
  *   others  : out[m, j] = mean / median / max / min of in[m, j*factor .. (j+1)*factor), n_out = floor(n_in / factor)
  * (the remainder is dropped, as the reference truncates it).  NaNs propagate like numpy's.  The mean accumulates in
- * fp64; median / max / min return input values (or the dtype's mean of the two middle ones) bit-exactly. */
+ * fp64 (float32 records on the 128-bit path: the four samples of one load are first added in float32); median / max /
+ * min return input values (or the dtype's mean of the two middle ones) bit-exactly. */
 #define QI_SUB_NTH 0
 #define QI_SUB_AVERAGE 1
 #define QI_SUB_MEDIAN 2

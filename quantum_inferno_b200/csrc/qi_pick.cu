@@ -261,9 +261,10 @@ subsample_vec_kernel(const T* __restrict__ in, i64 stride, i64 n_vec, int factor
             const bool live = idx < n_vec;
             if (per == V) {                                           // whole vector belongs to one group
                 if (METHOD == QI_SUB_AVERAGE) {
-                    Acc s = 0;
-#pragma unroll
-                    for (int e = 0; e < V; ++e) s += (Acc)v[u][e];
+                    // the samples of one 128-bit load are added in the record's own dtype (fp32: three additions, as
+                    // numpy's float32 mean would), every level above that in fp64
+                    const Acc s0 = (Acc)((v[u][0] + v[u][1]) + (v[u][V - 2] + v[u][V - 1]));
+                    Acc s = (sizeof(T) == 4) ? s0 : (Acc)v[u][0] + (Acc)v[u][V - 1];
                     for (int o = lanes >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                     if (live && (threadIdx.x & (lanes - 1)) == 0) orow[idx / lanes] = (T)(s * inv);
                 } else {

@@ -6,7 +6,7 @@ Block sub-sampling of records and time-frequency planes on the B200 -- drop-in f
 This is the step AFTER the time-frequency path: a [bands, time] power plane that lives in HBM is reduced to a
 displayable mesh (``scales_dyadic.DEFAULT_MESH_POW2_PIXELS``) without leaving the device.  All five methods run in
 csrc/qi_pick.cu (one streaming read of the plane); numpy in -> numpy out, CUDA tensor in -> tensor out.  The mean
-accumulates in fp64; "median" / "max" / "min" / "nth" are bit-exact.  float32 and float64 are computed as they are,
+accumulates in fp64 (above the four float32 samples of one 128-bit load); "median" / "max" / "min" / "nth" are bit-exact.  float32 and float64 are computed as they are,
 any other dtype is converted to float64 first.  ``decimate_timeseries`` / ``decimate_timeseries_collection``
 (:123-146, ``scipy.signal.decimate(zero_phase=True)``) run scipy's own order-8 Chebyshev cascade through the blocked
 IIR scan of csrc/qi_iir.cu and keep every q-th sample; the interpolating resamplers (:53-84) are not provided.

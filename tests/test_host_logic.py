@@ -143,6 +143,42 @@ def test_c_abi_exports_every_declared_symbol():
     assert lib.qi_cwt_workspace_bytes(1, 4096, 27, 4, 1, 0, 1) > 4096 * 2 * 16 * 2
 
 
+def test_host_side_of_the_next_rows():
+    """Compiled host code and host bookkeeping of the SURVEY 8(f) rows that needs no GPU: scipy's minimum-distance
+    peak selection (qi_select_peaks_by_distance), struct mirrors and argument checks of the new entry points, and the
+    exact transfer-function -> sections factoring of the pre-filters."""
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("libqi_b200.so not built (run __graft_entry__.build())")
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import _iir
+    lib = _lib.bind(ctypes.CDLL(_lib.LIB_PATH))
+    rng = np.random.default_rng(4)
+    for n, dist in ((0, 3), (1, 3), (500, 1), (500, 7), (500, 40), (2000, 1000)):
+        peaks = np.sort(rng.choice(20000, size=n, replace=False)).astype(np.int64)
+        prio = rng.standard_normal(n)
+        order = np.ascontiguousarray(np.argsort(prio), dtype=np.int64)
+        keep = np.zeros(n, dtype=np.uint8)
+        assert lib.qi_select_peaks_by_distance(peaks.ctypes.data, order.ctypes.data, n, dist, keep.ctypes.data) == 0
+        assert np.array_equal(keep.astype(bool), orc.select_by_peak_distance(peaks, prio, dist)), (n, dist)
+    assert lib.qi_select_peaks_by_distance(None, None, 5, 3, None) == -1
+    assert _lib.IIR_FILTER.itemsize == 8 + 17 * 8 * 2 + 48 * 8 + 16 * 8
+    assert lib.qi_filtfilt_workspace_bytes(1, 4096, 27, 8) > 8 * (4096 + 54)
+    assert lib.qi_filtfilt_workspace_bytes(1, 4096, 27, 17) == 0
+    assert lib.qi_subsample(None, 1, 8, 8, 2, 1, 0, None, 4, None) == -1
+    assert lib.qi_synth_chirp(1, 8, 8, 0, 0.0, 0.1, 0.0, 0.0, 0, 1, None, None, None) == -1
+    # factoring the reference's rounded taps: sections multiply back to the taps (float64 product of the sections is
+    # good to 1e-9 for these designs; the exactness itself is asserted against the long-double recursion elsewhere)
+    from scipy import signal
+    for b, a in (signal.butter(4, [0.025, 0.25], btype="bandpass"), signal.butter(5, 0.3), signal.butter(2, 0.1, btype="highpass")):
+        sos = _iir.tf2sos_exact(b, a)
+        bb, aa = np.ones(1), np.ones(1)
+        for sec in sos:
+            bb, aa = np.convolve(bb, sec[:3]), np.convolve(aa, sec[3:])
+        assert np.allclose(np.trim_zeros(bb, "b"), b, rtol=1e-7, atol=1e-12 * np.max(np.abs(b)))
+        assert np.allclose(np.trim_zeros(aa, "b"), a, rtol=1e-7, atol=1e-9)
+        assert np.all(sos[:, 3] == 1.0) and sos.shape == ((len(a)) // 2, 6)
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path raises; it never routes through the oracle or numpy."""
     import torch
@@ -153,7 +189,8 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError):
         styx_cwt.cwt_complex_any_scale_pow2(3, np.zeros(256), 800.0)
     pkg = os.path.join(ROOT, "quantum_inferno_b200")
-    src = "".join(open(os.path.join(pkg, fn)).read() for fn in os.listdir(pkg) if fn.endswith(".py"))
+    src = "".join(open(os.path.join(d, fn)).read() for d in (pkg, os.path.join(pkg, "utilities"), os.path.join(pkg, "synth"))
+                  for fn in os.listdir(d) if fn.endswith(".py"))
     assert "qi_oracle" not in src and "libqi_emul" not in src and "import oracle" not in src
 
 
