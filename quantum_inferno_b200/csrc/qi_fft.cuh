@@ -195,19 +195,37 @@ fft_pass_kernel(PassGeom g, Src src, Dst dst) {
     fill_twiddles<T>(tw, g.logR);
 
     const bool row_major = (g.logS == 0);        // rows contiguous in memory -> lanes along r
-    for (int idx = threadIdx.x; idx < nelem; idx += blockDim.x) {
-        int r, c;
-        if (row_major) { r = idx & (R - 1); c = idx >> g.logR; }
-        else { c = idx & (TC - 1); r = idx >> logTC; }
-        const i64 col = col0 + c;
-        const i64 e = pass_elem(g, r, col);
-        cplx<T> v = src.load(batch, e);
-        if (DIR == FFT_INV && g.logS > 0) {
-            const unsigned long long inner = (unsigned long long)(col & ((1ll << g.logS) - 1));
-            const unsigned k = brev_bits((unsigned)r, g.logR);
-            if (inner * k) v = mul_conj(v, conj(unit_root<T>(inner * k, twlog)));
+    // four loads per thread are requested before the first is consumed: this phase is bound by HBM / L2 latency
+    constexpr int LU = 4;
+    for (int base = threadIdx.x; base < nelem; base += blockDim.x * LU) {
+        cplx<T> v[LU];
+#pragma unroll
+        for (int u = 0; u < LU; ++u) {
+            const int idx = base + u * (int)blockDim.x;
+            if (idx < nelem) {
+                int r, c;
+                if (row_major) { r = idx & (R - 1); c = idx >> g.logR; }
+                else { c = idx & (TC - 1); r = idx >> logTC; }
+                v[u] = src.load(batch, pass_elem(g, r, col0 + c));
+            }
         }
-        tile[r * TP + c] = v;
+#pragma unroll
+        for (int u = 0; u < LU; ++u) {
+            const int idx = base + u * (int)blockDim.x;
+            if (idx < nelem) {
+                int r, c;
+                if (row_major) { r = idx & (R - 1); c = idx >> g.logR; }
+                else { c = idx & (TC - 1); r = idx >> logTC; }
+                const i64 col = col0 + c;
+                cplx<T> w = v[u];
+                if (DIR == FFT_INV && g.logS > 0) {
+                    const unsigned long long inner = (unsigned long long)(col & ((1ll << g.logS) - 1));
+                    const unsigned k = brev_bits((unsigned)r, g.logR);
+                    if (inner * k) w = mul_conj(w, conj(unit_root<T>(inner * k, twlog)));
+                }
+                tile[r * TP + c] = w;
+            }
+        }
     }
     __syncthreads();
     tile_fft<T, DIR>(tile, tw, g.logR, TC, TP);
