@@ -30,6 +30,7 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
     cplx<T>* tile = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* tw = tile + (size_t)R * TP;
     T* means = reinterpret_cast<T*>(tw + R);              // 2*TC means
+    double* bsum = reinterpret_cast<double*>(means + 2 * TC);   // 2*TC + 16 hop-block sums (fused path)
     const i64 chan = blockIdx.y;
     const i64 frame0 = (i64)blockIdx.x * (2 * TC);
     const T* x = sig + chan * g.sig_stride;
@@ -41,6 +42,34 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
     const bool interior = frame0 + 2 * TC <= g.n_frames && first >= 0 &&
                           first + (i64)(2 * TC - 1) * g.hop + g.nperseg <= g.n_points &&
                           (i64)(2 * TC - 1) * g.hop + R < (1ll << 30);
+    // Interior CTAs whose frames are whole numbers of hops apart make the frame means first (sums of hop-sized blocks
+    // of the span, one warp per block, every sample read once more from L1 / L2) and then gather (x - mean) * window
+    // straight into the tile: no separate mean and window passes over shared memory.
+    const int hops_per_frame = g.nperseg / g.hop;
+    const bool fused = interior && hops_per_frame * g.hop == g.nperseg && hops_per_frame <= 16;
+    if (fused) {
+        const T* xb0 = x + first;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        const int nblk = 2 * TC - 1 + hops_per_frame;
+        if (g.detrend) {
+            for (int blk = warp; blk < nblk; blk += nw) {
+                const T* pb = xb0 + (i64)blk * g.hop;
+                double s0 = 0.0, s1 = 0.0;
+                int i = lane;
+                for (; i + 32 < g.hop; i += 64) { s0 += (double)pb[i]; s1 += (double)pb[i + 32]; }
+                if (i < g.hop) s0 += (double)pb[i];
+                const double s = warp_sum(s0 + s1);
+                if (lane == 0) bsum[blk] = s;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * TC) {
+            double s = 0.0;
+            if (g.detrend) for (int j = 0; j < hops_per_frame; ++j) s += bsum[threadIdx.x + j];
+            means[threadIdx.x] = (T)(s / (double)g.nperseg);
+        }
+        __syncthreads();
+    }
     if (interior) {
         // eight (frame a, frame b) sample pairs per thread are requested before the first is stored: the gather is the
         // only HBM-latency-bound phase of the kernel and needs the loads in flight, not one dependent pair per trip
@@ -64,7 +93,16 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
 #pragma unroll
             for (int u = 0; u < GU; ++u) {
                 const int idx = base + u * (int)blockDim.x;
-                if (idx < total_g) tile[(idx & (R - 1)) * TP + (idx >> g.logF)] = mk<T>(va[u], vb[u]);
+                if (idx < total_g) {
+                    const int r = idx & (R - 1), c = idx >> g.logF;
+                    cplx<T> v = mk<T>(va[u], vb[u]);
+                    if (fused && r < g.nperseg) {
+                        const T w = window[r];
+                        v.re = (v.re - means[2 * c]) * w;
+                        v.im = (v.im - means[2 * c + 1]) * w;
+                    }
+                    tile[r * TP + c] = v;
+                }
             }
         }
     } else {
@@ -83,7 +121,7 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
     }
     __syncthreads();
     // per-frame mean over the nperseg samples (scipy detrend='constant', after the zero extension)
-    {
+    if (!fused) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
         for (int col = warp; col < 2 * TC; col += nw) {
             double s = 0.0;
@@ -97,18 +135,18 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
             s = warp_sum(s);
             if (lane == 0) means[col] = (T)(s / (double)g.nperseg);
         }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < g.nperseg * TC; idx += blockDim.x) {
+            const int c = idx & (TC - 1);                   // TC is a power of two
+            const int r = idx >> logTC;
+            const T w = window[r];
+            cplx<T> v = tile[r * TP + c];
+            v.re = (v.re - means[2 * c]) * w;
+            v.im = (v.im - means[2 * c + 1]) * w;
+            tile[r * TP + c] = v;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < g.nperseg * TC; idx += blockDim.x) {
-        const int c = idx & (TC - 1);                   // TC is a power of two
-        const int r = idx >> logTC;
-        const T w = window[r];
-        cplx<T> v = tile[r * TP + c];
-        v.re = (v.re - means[2 * c]) * w;
-        v.im = (v.im - means[2 * c + 1]) * w;
-        tile[r * TP + c] = v;
-    }
-    __syncthreads();
     tile_fft<T, FFT_FWD>(tile, tw, g.logF, TC, TP);
     // Hermitian split + store, lanes along frames (time is the fastest output axis)
     const int K = (R >> 1) + 1;
@@ -157,7 +195,7 @@ static int stft_impl(const void* sig, i64 C, i64 n_points, i64 stride, const voi
     // <= ~100 KB per CTA so that two CTAs (2 x 512 threads) share an SM; fall back to one big CTA for long FFTs
     size_t budget = 100 * 1024;
     int TC = 16;
-    auto need = [&](int tc) { return ((size_t)nfft * (tc + 2)) * sizeof(cplx<T>) + 2 * tc * sizeof(T) + 64; };
+    auto need = [&](int tc) { return ((size_t)nfft * (tc + 2)) * sizeof(cplx<T>) + 2 * tc * sizeof(T) + (2 * tc + 16) * sizeof(double) + 64; };
     while (TC > 2 && need(TC) > budget) TC >>= 1;
     if (need(TC) > budget) { budget = 200 * 1024; while (TC > 1 && need(TC) > budget) TC >>= 1; }
     if (need(TC) > budget) return QI_ERR_UNSUPPORTED;

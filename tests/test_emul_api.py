@@ -64,6 +64,21 @@ def test_stx(golden, tag, xkey, order, dtype, tol):
     assert np.array_equal(f, g[tag + "_f"]) and rel(c, g[tag + "_c"]) < tol
 
 
+def test_stft_interior_fused_path():
+    """Records long enough for interior CTAs (frame means from hop-block sums, (x - mean) * window applied in the
+    gather): every hop ratio of the fused path and one that falls back, against the oracle's scipy restatement."""
+    from oracle import qi_oracle as orc
+    k = np.arange(40000)
+    x = np.random.default_rng(0).standard_normal((2, 40000)) + 3.0 + np.cos(2 * np.pi * 60 / 800 * k)
+    for seg, ov, nfft in ((256, None, None), (256, 192, 512), (128, 96, None), (300, 100, 512), (200, 150, 256), (250, 100, 256)):
+        f0, t0, z0 = orc.stft_complex_pow2(x, FS, seg, ov, nfft, alpha=0.25)
+        for dtype, tol in (("float64", 1e-12), ("float32", 3e-6)):
+            f, t, z = styx_fft.stft_complex_pow2(x, FS, seg, ov, nfft, alpha=0.25, dtype=dtype)
+            assert z.shape == z0.shape and rel(z, z0) < tol, (seg, ov, nfft, dtype)
+    f, p = styx_fft.welch_power_pow2(x, FS, 256)
+    assert rel(p, orc.welch_power_pow2(x, FS, 256)[1]) < 1e-12
+
+
 @pytest.mark.parametrize("tag,kw", [
     ("lin", dict()), ("geo", dict(is_geometric=True)), ("inf", dict(is_geometric=True, is_inferno=True)),
     ("opt", dict(factor_q=0.5, power_p=1.0, power_r=0.5, frequency_min=10.0, frequency_max=300.0, frequency_step=5.0))])

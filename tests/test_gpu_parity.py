@@ -509,3 +509,18 @@ def test_synth_and_decimate_gpu(torch_cuda, golden, capsys):
     assert isinstance(sig, torch_cuda.Tensor) and sig.shape == (1 << 24,) and sig.dtype == torch_cuda.float32
     k = np.array([0, 1, 12345, (1 << 23) + 7, (1 << 24) - 1])
     assert np.max(np.abs(sig[k].cpu().numpy() - np.cos(2.0 * np.pi * (fc / fs) * k))) < 2e-7
+
+
+def test_stft_interior_fused_path_gpu(torch_cuda):
+    """The fused mean / window gather of the interior CTAs for every hop ratio, and the fallback, against the oracle."""
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import styx_fft
+    k = np.arange(100000)
+    x = np.random.default_rng(0).standard_normal((3, 100000)) + 3.0 + np.cos(2 * np.pi * 60 / 800 * k)
+    for seg, ov, nfft in ((1024, None, None), (256, 192, 512), (128, 96, None), (300, 100, 512), (200, 150, 256), (250, 100, 256)):
+        f0, t0, z0 = orc.stft_complex_pow2(x, FS, seg, ov, nfft, alpha=0.25)
+        for dtype, tol in (("float64", 1e-12), ("float32", 3e-6)):
+            f, t, z = styx_fft.stft_complex_pow2(x, FS, seg, ov, nfft, alpha=0.25, dtype=dtype)
+            assert z.shape == z0.shape and rel(z, z0) < tol, (seg, ov, nfft, dtype)
+    f, p = styx_fft.welch_power_pow2(x, FS, 256)
+    assert rel(p, orc.welch_power_pow2(x, FS, 256)[1]) < 1e-12
