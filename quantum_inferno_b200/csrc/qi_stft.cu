@@ -230,7 +230,7 @@ struct IstftGeom {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 istft_frames_kernel(const cplx<T>* __restrict__ S, const T* __restrict__ dual_win, IstftGeom g, T* __restrict__ slices) {
     QI_DYN_SMEM(smem_raw);
     const int R = 1 << g.logF;
@@ -242,22 +242,40 @@ istft_frames_kernel(const cplx<T>* __restrict__ S, const T* __restrict__ dual_wi
     const i64 frame0 = (i64)blockIdx.x * (2 * TC);
     const int K = (R >> 1) + 1;
     fill_twiddles<T>(tw, g.logF);
-    for (int idx = threadIdx.x; idx < K * TC; idx += blockDim.x) {        // lanes along the frames (fastest axis of S)
-        const int c = idx & (TC - 1);
-        const int k = idx >> logTC;
-        const i64 fa = frame0 + 2 * c, fb = fa + 1;
-        cplx<T> xa = mk<T>((T)0, (T)0), xb = xa;
-        if (fa < g.n_frames) xa = S[(chan * K + k) * g.n_frames + fa];
-        if (fb < g.n_frames) xb = S[(chan * K + k) * g.n_frames + fb];
-        if (g.roll) {               // undo the rotation of the forward transform: bin k times exp(-2 pi i k roll / nfft)
-            const cplx<T> ph = conj(unit_root<T>((unsigned long long)(((i64)k * g.roll) & (R - 1)), g.logF));
-            xa = xa * ph; xb = xb * ph;
+    // lanes along the frames (fastest axis of S); four spectrum pairs per thread are requested before the first is used
+    constexpr int LU = 4;
+    for (int base = threadIdx.x; base < K * TC; base += blockDim.x * LU) {
+        cplx<T> xa_[LU], xb_[LU];
+#pragma unroll
+        for (int u = 0; u < LU; ++u) {
+            const int idx = base + u * (int)blockDim.x;
+            xa_[u] = mk<T>((T)0, (T)0);
+            xb_[u] = xa_[u];
+            if (idx < K * TC) {
+                const int c = idx & (TC - 1);
+                const int k = idx >> logTC;
+                const i64 fa = frame0 + 2 * c, fb = fa + 1;
+                if (fa < g.n_frames) xa_[u] = S[(chan * K + k) * g.n_frames + fa];
+                if (fb < g.n_frames) xb_[u] = S[(chan * K + k) * g.n_frames + fb];
+            }
         }
-        if (k == 0 || k == R / 2) {                                        // irfft ignores these imaginary parts
-            tile[(int)brev_bits((unsigned)k, g.logF) * TP + c] = mk<T>(xa.re, xb.re);
-        } else {
-            tile[(int)brev_bits((unsigned)k, g.logF) * TP + c] = mk<T>(xa.re - xb.im, xa.im + xb.re);
-            tile[(int)brev_bits((unsigned)(R - k), g.logF) * TP + c] = mk<T>(xa.re + xb.im, xb.re - xa.im);
+#pragma unroll
+        for (int u = 0; u < LU; ++u) {
+            const int idx = base + u * (int)blockDim.x;
+            if (idx >= K * TC) continue;
+            const int c = idx & (TC - 1);
+            const int k = idx >> logTC;
+            cplx<T> xa = xa_[u], xb = xb_[u];
+            if (g.roll) {           // undo the rotation of the forward transform: bin k times exp(-2 pi i k roll / nfft)
+                const cplx<T> ph = conj(unit_root<T>((unsigned long long)(((i64)k * g.roll) & (R - 1)), g.logF));
+                xa = xa * ph; xb = xb * ph;
+            }
+            if (k == 0 || k == R / 2) {                                    // irfft ignores these imaginary parts
+                tile[(int)brev_bits((unsigned)k, g.logF) * TP + c] = mk<T>(xa.re, xb.re);
+            } else {
+                tile[(int)brev_bits((unsigned)k, g.logF) * TP + c] = mk<T>(xa.re - xb.im, xa.im + xb.re);
+                tile[(int)brev_bits((unsigned)(R - k), g.logF) * TP + c] = mk<T>(xa.re + xb.im, xb.re - xa.im);
+            }
         }
     }
     __syncthreads();
