@@ -17,6 +17,13 @@
 #pragma once
 #include "qi_platform.cuh"
 
+// loads requested per thread before the first is consumed in the load phase of a pass.  Measured on B200 (Stockwell
+// 16 x 2^18 and the exact CWT bench): 1 -> 3.11 ms / 412 ms, 2 -> 3.32 / 446, 4 -> 3.21 / 422: the passes are
+// instruction-bound, not latency-bound, so the simple loop stays (make EXTRA=-DQI_FFT_LOADS_IN_FLIGHT=n to repeat).
+#ifndef QI_FFT_LOADS_IN_FLIGHT
+#define QI_FFT_LOADS_IN_FLIGHT 1
+#endif
+
 namespace qi {
 
 enum { FFT_FWD = 0, FFT_INV = 1 };
@@ -195,8 +202,7 @@ fft_pass_kernel(PassGeom g, Src src, Dst dst) {
     fill_twiddles<T>(tw, g.logR);
 
     const bool row_major = (g.logS == 0);        // rows contiguous in memory -> lanes along r
-    // four loads per thread are requested before the first is consumed: this phase is bound by HBM / L2 latency
-    constexpr int LU = 4;
+    constexpr int LU = QI_FFT_LOADS_IN_FLIGHT;
     for (int base = threadIdx.x; base < nelem; base += blockDim.x * LU) {
         cplx<T> v[LU];
 #pragma unroll
