@@ -302,9 +302,16 @@ istft_ola_kernel(const T* __restrict__ slices, IstftGeom g, T* __restrict__ out)
     const i64 k = g.k0 + i;
     // frames p with first_start + p*hop <= k < first_start + p*hop + nperseg
     const i64 d = k - g.first_start;
-    i64 p_hi = d >= 0 ? d / g.hop : -((-d + g.hop - 1) / g.hop);                       // floor(d / hop)
     const i64 e = d - (g.nperseg - 1);
-    i64 p_lo = e > 0 ? (e + g.hop - 1) / g.hop : -((-e) / g.hop);                      // ceil(e / hop)
+    i64 p_hi, p_lo;
+    if ((g.hop & (g.hop - 1)) == 0) {                                                   // hop = 2^s: arithmetic shifts
+        const int sh = 31 - __clz(g.hop);
+        p_hi = d >> sh;                                                                 // floor(d / hop)
+        p_lo = -((-e) >> sh);                                                           // ceil(e / hop)
+    } else {
+        p_hi = d >= 0 ? d / g.hop : -((-d + g.hop - 1) / g.hop);
+        p_lo = e > 0 ? (e + g.hop - 1) / g.hop : -((-e) / g.hop);
+    }
     if (p_lo < g.frame_lo) p_lo = g.frame_lo;
     if (p_hi > g.frame_hi - 1) p_hi = g.frame_hi - 1;
     T acc = (T)0;
