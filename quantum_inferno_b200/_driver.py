@@ -79,13 +79,28 @@ def atoms_time(bands, n_points, fs, dt, xtime=None, rt=None):
     return out
 
 
-def stx_fft(sig, bands, dt, want_complex=True, want_power=False, want_band_sum=False, rt=None):
+def stx_fft(sig, bands, dt, want_complex=True, want_power=False, want_band_sum=False, rt=None, method="exact"):
+    """Run qi_stx_fft (method="exact") or qi_stx_multirate (method="multirate": float32, records of 2^m >= 4096
+    samples, decimated voices + polyphase interpolation)."""
     rt = rt or get_runtime()
     lib = rt.lib
     C, N = int(sig.shape[0]), int(sig.shape[1])
     bands = np.ascontiguousarray(bands, dtype=_lib.STX_BAND)
     B = len(bands)
     code = DTYPE_CODE[dt]
+    if method == "multirate":
+        if dt != "float32" or want_band_sum or N < 4096:
+            raise ValueError("method='multirate' needs dtype float32, records of 2^m >= 4096 samples and no band sums")
+        nbytes = lib.qi_stx_multirate_workspace_bytes(C, N, bands.ctypes.data, B)
+        ws = rt.workspace(nbytes)
+        out_c = rt.empty((C, B, N), COMPLEX_OF[dt]) if want_complex else None
+        out_p = rt.empty((C, B, N), dt) if want_power else None
+        rc = lib.qi_stx_multirate(rt.ptr(sig), C, N, N, bands.ctypes.data, B, rt.ptr(out_c), rt.ptr(out_p), rt.ptr(ws),
+                                  nbytes, rt.stream())
+        _lib.check(lib, rc, "qi_stx_multirate")
+        return {"complex": out_c, "power": out_p, "band_sum": None}
+    if method != "exact":
+        raise ValueError("method must be 'exact' or 'multirate'")
 
     def ws_bytes(group):
         return lib.qi_stx_workspace_bytes(C, N, B, group, code)

@@ -107,8 +107,12 @@ def tfr_stx_fft(sig_wf, time_sample_interval: float, scale_order_input: float = 
 
 
 def stx_complex_any_scale_pow2(band_order_nth: float, sig_wf, frequency_sample_rate_hz: float, *,
-                               dtype=None, outputs: str = "complex"):
+                               dtype=None, outputs: str = "complex", method: str = "exact"):
     """Stockwell transform on the standard order-N band table (reference styx_stx.py:195-236).
+
+    ``method="multirate"`` (keyword-only extension; float32, 2^m >= 4096 samples) computes every voice at its own
+    decimated rate and interpolates it to the full rate: relative L2 error ~3e-6 against the exact method (north-star
+    float32 tolerance 1e-4), a fraction of the memory traffic.
 
     :return: frequency_stx_hz [B], time_stx_s [N], tfr_stx [B, N] (or [C, B, N] for 2-D input)
     """
@@ -119,7 +123,8 @@ def stx_complex_any_scale_pow2(band_order_nth: float, sig_wf, frequency_sample_r
     n_fft_pow2 = int(sig.shape[1])
     _require_pow2(n_fft_pow2)
     frequency_stx_hz, bands = _plan.stx_bands(band_order_nth, n_fft_pow2, frequency_sample_rate_hz)
-    res = _driver.stx_fft(sig, bands, dt, want_complex=outputs != "power", want_power=outputs == "power", rt=rt)
+    res = _driver.stx_fft(sig, bands, dt, want_complex=outputs != "power", want_power=outputs == "power", rt=rt,
+                          method=method)
     buf = res["power"] if outputs == "power" else res["complex"]
     return (frequency_stx_hz, np.arange(n_fft_pow2) / frequency_sample_rate_hz,
             finish(rt, buf[0] if was_1d else buf, want_numpy))

@@ -190,6 +190,7 @@ static inline unsigned long long atomicMin(unsigned long long* p, unsigned long 
 // math intrinsics used by the kernels
 static inline void sincospi(double x, double* s, double* c) { *s = std::sin(M_PI * x); *c = std::cos(M_PI * x); }
 static inline void sincospif(float x, float* s, float* c) { *s = (float)std::sin(M_PI * (double)x); *c = (float)std::cos(M_PI * (double)x); }
+static inline double sinpi(double x) { return std::sin(M_PI * x); }
 static inline double cospi(double x) { return std::cos(M_PI * x); }
 static inline float exp2f_(float x) { return std::exp2(x); }
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }

@@ -90,6 +90,27 @@ def test_stx_general(golden, tag, kw):
     assert rel(win, g[f"gen_{tag}_win"]) < 1e-12
 
 
+def test_stx_multirate():
+    """Decimated voices + polyphase interpolation (float32 opt-in) against the oracle: north-star float32 tolerance
+    1e-4 relative L2 per plane, and per band (no band may hide behind the strong ones)."""
+    from oracle import qi_oracle as orc
+    for n, order in ((8192, 3), (4096, 12)):
+        k = np.arange(n)
+        x = np.random.default_rng(n).standard_normal((2, n)) / 4 + np.cos(2 * np.pi * 60 / FS * k)
+        f, t, c = styx_stx.stx_complex_any_scale_pow2(order, x, FS, dtype="float32", method="multirate")
+        _, _, p = styx_stx.stx_complex_any_scale_pow2(order, x, FS, dtype="float32", method="multirate", outputs="power")
+        for ch in range(2):
+            f0, t0, c0 = orc.stx_complex_any_scale_pow2(order, x[ch], FS)
+            assert np.array_equal(f, f0) and c.shape == (2,) + c0.shape and c.dtype == np.complex64
+            assert np.linalg.norm(c[ch] - c0) / np.linalg.norm(c0) < 1e-5
+            assert max(np.linalg.norm(c[ch, b] - c0[b]) / np.linalg.norm(c0[b]) for b in range(len(f))) < 2e-5
+            assert np.linalg.norm(p[ch] - np.abs(c0) ** 2) / np.linalg.norm(np.abs(c0) ** 2) < 2e-5
+    with pytest.raises(ValueError):
+        styx_stx.stx_complex_any_scale_pow2(3, np.zeros(8192), FS, method="multirate")               # float64
+    with pytest.raises(ValueError):
+        styx_stx.stx_complex_any_scale_pow2(3, np.zeros(2048), FS, dtype="float32", method="multirate")
+
+
 def test_stx_errors(golden):
     g = golden("stx")
     with pytest.raises(TypeError):

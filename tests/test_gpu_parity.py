@@ -524,3 +524,22 @@ def test_stft_interior_fused_path_gpu(torch_cuda):
             assert z.shape == z0.shape and rel(z, z0) < tol, (seg, ov, nfft, dtype)
     f, p = styx_fft.welch_power_pow2(x, FS, 256)
     assert rel(p, orc.welch_power_pow2(x, FS, 256)[1]) < 1e-12
+
+
+@pytest.mark.parametrize("order,logn,chans", [(3, 16, 3), (6, 14, 2), (12, 13, 2), (3, 18, 1)])
+def test_stx_multirate_vs_oracle(torch_cuda, order, logn, chans):
+    """Multirate float32 Stockwell (decimated voices, polyphase interpolation) against the oracle and the exact method."""
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import styx_stx
+    n = 1 << logn
+    x = np.stack([synth(n, seed=3, chan=c) for c in range(chans)])
+    f, t, c = styx_stx.stx_complex_any_scale_pow2(order, x, FS, dtype="float32", method="multirate")
+    _, _, p = styx_stx.stx_complex_any_scale_pow2(order, x, FS, dtype="float32", method="multirate", outputs="power")
+    _, _, ce = styx_stx.stx_complex_any_scale_pow2(order, x, FS, dtype="float32")
+    assert c.shape == ce.shape and c.dtype == np.complex64 and l2(c, ce.astype(np.complex128)) < 1e-5
+    for ch in range(chans if logn <= 16 else 1):
+        f0, t0, c0 = orc.stx_complex_any_scale_pow2(order, x[ch], FS)
+        assert np.array_equal(f, f0)
+        assert np.linalg.norm(c[ch] - c0) / np.linalg.norm(c0) < TOL32_L2 / 10
+        assert max(np.linalg.norm(c[ch, b] - c0[b]) / np.linalg.norm(c0[b]) for b in range(len(f))) < TOL32_L2 / 5
+        assert l2(p[ch], np.abs(c0) ** 2) < TOL32_L2 / 5

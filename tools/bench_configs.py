@@ -87,6 +87,13 @@ def cfg3():
             cells = z.shape[0] * z.shape[1] * z.shape[2]
             out[f"order{order}_{dt}"] = {"ms": ms, "cells_per_s": cells / ms * 1e3, "bands": int(z.shape[1]),
                                           "channels": int(z.shape[0])}
+            if dt == "float32":       # multirate opt-in: decimated voices + polyphase interpolation (complex64 out: 8 B/cell)
+                ze = z
+                ms, (f, t, z) = timed(lambda: styx_stx.stx_complex_any_scale_pow2(order, xx, FS, dtype=dt, method="multirate"), reps=3)
+                err = float(torch.linalg.vector_norm(z - ze) / torch.linalg.vector_norm(ze))
+                out[f"order{order}_float32_multirate"] = {"ms": ms, "cells_per_s": cells / ms * 1e3, "alg_GBps": cells * 8 / ms / 1e6,
+                                                          "rel_l2_vs_exact": err}
+                del ze
             del z
             torch.cuda.empty_cache()
     return out
