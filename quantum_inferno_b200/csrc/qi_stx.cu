@@ -157,15 +157,16 @@ struct SrcStxDec {
     }
 };
 
-QI_DEV double stxmr_bessel_i0(double x) {
+// modified Bessel function I0 by its power series (32 terms: below 1e-19 of the sum for x <= 11.2)
+QI_HD double stxmr_bessel_i0(double x) {
     double s = 1.0, term = 1.0;
-    const double h = 0.5 * x;
-    for (int k = 1; k < 60; ++k) { term *= (h / k) * (h / k); s += term; }
+    const double hh = 0.25 * x * x;
+    for (int k = 1; k <= 32; ++k) { term *= hh / (double)(k * k); s += term; }
     return s;
 }
 
 // coef[j * D + p] = h(p - (j - 7) D)
-__global__ void stxmr_coef_kernel(float* __restrict__ coef, int logD) {
+__global__ void stxmr_coef_kernel(float* __restrict__ coef, int logD, double inv_i0_beta) {
     const int D = 1 << logD;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= STXMR_TAPS * D) return;
@@ -173,7 +174,7 @@ __global__ void stxmr_coef_kernel(float* __restrict__ coef, int logD) {
     const double t = (double)(p - (j - 7) * D);
     const double x = t / (8.0 * D);
     const double arg = 1.0 - x * x;
-    const double w = stxmr_bessel_i0(STXMR_BETA * sqrt(arg > 0.0 ? arg : 0.0)) / stxmr_bessel_i0(STXMR_BETA);
+    const double w = stxmr_bessel_i0(STXMR_BETA * sqrt(arg > 0.0 ? arg : 0.0)) * inv_i0_beta;
     const double y = t / (double)D;
     const double sinc = t == 0.0 ? 1.0 : sinpi(y) / (M_PI * y);
     coef[idx] = (float)(sinc * w);
@@ -194,18 +195,28 @@ stxmr_interp_kernel(const cplx<float>* __restrict__ dec, const int* __restrict__
     for (int i = threadIdx.x; i < nseg; i += blockDim.x) seg[i] = src[(m_base + i) & (K - 1)];
     __syncthreads();
     const i64 row = ((i64)chan * n_bands + band) << logN;
-    for (int o = threadIdx.x; o < STXMR_TILE; o += blockDim.x) {
-        const int p = o & (D - 1), ml = o >> logD;
+    // Thread (p, g): phase p = tid mod D, and the 8 consecutive decimated positions m = 8 g .. 8 g + 7 (256 / D threads
+    // share a phase).  Its sixteen coefficients and the 23 decimated samples under its window stay in registers: one
+    // shared-memory load per 1.4 outputs instead of 16 per output.
+    constexpr int PER = STXMR_TILE / 256;                             // outputs per thread
+    const int p = threadIdx.x & (D - 1), m0 = (threadIdx.x >> logD) * PER;
+    float cf[STXMR_TAPS];
+#pragma unroll
+    for (int j = 0; j < STXMR_TAPS; ++j) cf[j] = coef[(j << logD) + p];
+    cplx<float> win[PER + STXMR_TAPS - 1];
+#pragma unroll
+    for (int j = 0; j < PER + STXMR_TAPS - 1; ++j) win[j] = seg[m0 + j];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
         float re = 0.0f, im = 0.0f;
 #pragma unroll
         for (int j = 0; j < STXMR_TAPS; ++j) {
-            const float c = coef[(j << logD) + p];
-            const cplx<float> v = seg[ml + j];
-            re += c * v.re;
-            im += c * v.im;
+            re += cf[j] * win[i + j].re;
+            im += cf[j] * win[i + j].im;
         }
-        if (out_c) out_c[row + tile0 + o] = mk<float>(re, im);
-        if (out_p) out_p[row + tile0 + o] = re * re + im * im;
+        const i64 o = row + tile0 + ((i64)(m0 + i) << logD) + p;
+        if (out_c) out_c[o] = mk<float>(re, im);
+        if (out_p) out_p[o] = re * re + im * im;
     }
     (void)N;
 }
@@ -305,7 +316,7 @@ static int stx_multirate_impl(const void* sig, i64 C, i64 N, i64 stride, const Q
             if (!coef_ready[logD]) {
                 prof_set_category(QI_CAT_OTHER);
                 const int ncoef = STXMR_TAPS << logD;
-                QI_LAUNCH((stxmr_coef_kernel), dim3((unsigned)((ncoef + 255) / 256)), dim3(256), 0, st, cf, logD);
+                QI_LAUNCH((stxmr_coef_kernel), dim3((unsigned)((ncoef + 255) / 256)), dim3(256), 0, st, cf, logD, 1.0 / stxmr_bessel_i0(STXMR_BETA));
                 coef_ready[logD] = true;
             }
             const FftPlan pk = make_plan(lk, (int)sizeof(cplx<T>));
