@@ -200,6 +200,30 @@ stxmr_interp_kernel(const cplx<float>* __restrict__ dec, const int* __restrict__
     // shared-memory load per 1.4 outputs instead of 16 per output.
     constexpr int PER = STXMR_TILE / 256;                             // outputs per thread
     const int p = threadIdx.x & (D - 1), m0 = (threadIdx.x >> logD) * PER;
+#ifndef QI_EMUL
+    // (re, im) pairs go through the packed fma.rn.f32x2 with the coefficient duplicated in both halves: 16 instead of 32
+    // FMA instructions per output
+    unsigned long long cf2[STXMR_TAPS], win2[PER + STXMR_TAPS - 1];
+#pragma unroll
+    for (int j = 0; j < STXMR_TAPS; ++j) {
+        const float c = coef[(j << logD) + p];
+        asm("mov.b64 %0, {%1, %2};" : "=l"(cf2[j]) : "f"(c), "f"(c));
+    }
+#pragma unroll
+    for (int j = 0; j < PER + STXMR_TAPS - 1; ++j) win2[j] = *reinterpret_cast<const unsigned long long*>(&seg[m0 + j]);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        unsigned long long acc;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(acc) : "f"(0.0f));
+#pragma unroll
+        for (int j = 0; j < STXMR_TAPS; ++j) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(cf2[j]), "l"(win2[i + j]));
+        float re, im;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(re), "=f"(im) : "l"(acc));
+        const i64 o = row + tile0 + ((i64)(m0 + i) << logD) + p;
+        if (out_c) out_c[o] = mk<float>(re, im);
+        if (out_p) out_p[o] = re * re + im * im;
+    }
+#else
     float cf[STXMR_TAPS];
 #pragma unroll
     for (int j = 0; j < STXMR_TAPS; ++j) cf[j] = coef[(j << logD) + p];
@@ -218,6 +242,7 @@ stxmr_interp_kernel(const cplx<float>* __restrict__ dec, const int* __restrict__
         if (out_c) out_c[o] = mk<float>(re, im);
         if (out_p) out_p[o] = re * re + im * im;
     }
+#endif
     (void)N;
 }
 
