@@ -165,8 +165,11 @@ QI_HD double stxmr_bessel_i0(double x) {
     return s;
 }
 
-// coef[j * D + p] = h(p - (j - 7) D)
-__global__ void stxmr_coef_kernel(float* __restrict__ coef, int logD, double inv_i0_beta) {
+// table of decimation 2^logD (logD = blockIdx.y, slot logD of `coef_all`): coef[j * D + p] = h(p - (j - 7) D)
+__global__ void stxmr_coef_kernel(float* __restrict__ coef_all, unsigned need_mask, double inv_i0_beta) {
+    const int logD = blockIdx.y;
+    if (!((need_mask >> logD) & 1u)) return;
+    float* coef = coef_all + (size_t)logD * STXMR_TAPS * (1u << STXMR_MAX_LOGD);
     const int D = 1 << logD;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= STXMR_TAPS * D) return;
@@ -327,8 +330,15 @@ static int stx_multirate_impl(const void* sig, i64 C, i64 N, i64 stride, const Q
         if (p == 0) { SrcRealPad<T> s{static_cast<const T*>(sig), stride, N}; launch_pass<T, FFT_FWD>(plan, p, C, s, d, 0, st); }
         else { SrcComplex<T> s{spec, N}; launch_pass<T, FFT_FWD>(plan, p, C, s, d, 0, st); }
     }
+    // interpolator tables of every decimation in use: one launch
+    unsigned need_mask = 0;
+    for (int b = 0; b < B; ++b) if (logk[b] < logN) need_mask |= 1u << (logN - logk[b]);
+    if (need_mask) {
+        prof_set_category(QI_CAT_OTHER);
+        dim3 cgrid((unsigned)((STXMR_TAPS << STXMR_MAX_LOGD) / 256), (unsigned)(STXMR_MAX_LOGD + 1));
+        QI_LAUNCH((stxmr_coef_kernel), cgrid, dim3(256), 0, st, coef, need_mask, 1.0 / stxmr_bessel_i0(STXMR_BETA));
+    }
     // decimated groups
-    bool coef_ready[STXMR_MAX_LOGD + 1] = {false};
     size_t pos = 0;
     while (pos < ids.size()) {
         const int lk = logk[ids[pos]];
@@ -338,12 +348,6 @@ static int stx_multirate_impl(const void* sig, i64 C, i64 N, i64 stride, const Q
         if (lk < logN) {
             const int logD = logN - lk;
             float* cf = coef + (size_t)logD * STXMR_TAPS * (1u << STXMR_MAX_LOGD);
-            if (!coef_ready[logD]) {
-                prof_set_category(QI_CAT_OTHER);
-                const int ncoef = STXMR_TAPS << logD;
-                QI_LAUNCH((stxmr_coef_kernel), dim3((unsigned)((ncoef + 255) / 256)), dim3(256), 0, st, cf, logD, 1.0 / stxmr_bessel_i0(STXMR_BETA));
-                coef_ready[logD] = true;
-            }
             const FftPlan pk = make_plan(lk, (int)sizeof(cplx<T>));
             const i64 K = 1ll << lk;
             for (i64 sub = 0; sub < g; ) {                         // grid.y limit: chunks of bands
