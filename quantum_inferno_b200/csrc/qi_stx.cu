@@ -138,6 +138,7 @@ static int stx_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiStxBa
 constexpr int STXMR_TAPS = 16;
 constexpr int STXMR_MAX_LOGD = 8;
 constexpr int STXMR_TILE = 2048;
+constexpr int STXMR_SPAN = 4;                 // tiles per CTA of the interpolator (coefficients loaded once)
 constexpr double STXMR_U = 5.5;
 constexpr double STXMR_BETA = 11.2;
 
@@ -183,18 +184,20 @@ __global__ void stxmr_coef_kernel(float* __restrict__ coef_all, unsigned need_ma
     coef[idx] = (float)(sinc * w);
 }
 
-// grid: (n / STXMR_TILE, bands of the group, channels)
+// grid: (ceil(n / (STXMR_SPAN * STXMR_TILE)), bands of the group, channels)
 __global__ void __launch_bounds__(256)
 stxmr_interp_kernel(const cplx<float>* __restrict__ dec, const int* __restrict__ ids, int n_channels, int n_bands, int logN,
                     int logD, const float* __restrict__ coef, cplx<float>* __restrict__ out_c, float* __restrict__ out_p) {
-    __shared__ cplx<float> seg[STXMR_TILE / 2 + STXMR_TAPS];
+    __shared__ cplx<float> seg[STXMR_SPAN * STXMR_TILE / 2 + STXMR_TAPS];
     const int D = 1 << logD, logK = logN - logD;
     const i64 K = 1ll << logK, N = 1ll << logN;
-    const i64 tile0 = (i64)blockIdx.x * STXMR_TILE;
+    const i64 span0 = (i64)blockIdx.x * (STXMR_SPAN * STXMR_TILE);
+    const i64 left = (N - span0) / STXMR_TILE;
+    const int ntile = left < STXMR_SPAN ? (int)left : STXMR_SPAN;
     const int bi = blockIdx.y, chan = blockIdx.z, band = ids[bi];
     const cplx<float>* src = dec + (((i64)bi * n_channels + chan) << logK);
-    const i64 m_base = (tile0 >> logD) - 7;
-    const int nseg = (STXMR_TILE >> logD) + STXMR_TAPS;
+    const i64 m_base = (span0 >> logD) - 7;
+    const int nseg = ((ntile * STXMR_TILE) >> logD) + STXMR_TAPS;
     for (int i = threadIdx.x; i < nseg; i += blockDim.x) seg[i] = src[(m_base + i) & (K - 1)];
     __syncthreads();
     const i64 row = ((i64)chan * n_bands + band) << logN;
@@ -202,7 +205,7 @@ stxmr_interp_kernel(const cplx<float>* __restrict__ dec, const int* __restrict__
     // share a phase).  Its sixteen coefficients and the 23 decimated samples under its window stay in registers: one
     // shared-memory load per 1.4 outputs instead of 16 per output.
     constexpr int PER = STXMR_TILE / 256;                             // outputs per thread
-    const int p = threadIdx.x & (D - 1), m0 = (threadIdx.x >> logD) * PER;
+    const int p = threadIdx.x & (D - 1), mg = (threadIdx.x >> logD) * PER;
 #ifndef QI_EMUL
     // (re, im) pairs go through the packed fma.rn.f32x2 with the coefficient duplicated in both halves: 16 instead of 32
     // FMA instructions per output
@@ -212,243 +215,251 @@ stxmr_interp_kernel(const cplx<float>* __restrict__ dec, const int* __restrict__
         const float c = coef[(j << logD) + p];
         asm("mov.b64 %0, {%1, %2};" : "=l"(cf2[j]) : "f"(c), "f"(c));
     }
+    for (int tl = 0; tl < ntile; ++tl) {
+        const int m0 = tl * (STXMR_TILE >> logD) + mg;
+        const i64 tile0 = span0;
 #pragma unroll
-    for (int j = 0; j < PER + STXMR_TAPS - 1; ++j) win2[j] = *reinterpret_cast<const unsigned long long*>(&seg[m0 + j]);
+        for (int j = 0; j < PER + STXMR_TAPS - 1; ++j) win2[j] = *reinterpret_cast<const unsigned long long*>(&seg[m0 + j]);
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        unsigned long long acc;
-        asm("mov.b64 %0, {%1, %1};" : "=l"(acc) : "f"(0.0f));
+        for (int i = 0; i < PER; ++i) {
+            unsigned long long acc;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(acc) : "f"(0.0f));
 #pragma unroll
-        for (int j = 0; j < STXMR_TAPS; ++j) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(cf2[j]), "l"(win2[i + j]));
-        float re, im;
-        asm("mov.b64 {%0, %1}, %2;" : "=f"(re), "=f"(im) : "l"(acc));
-        const i64 o = row + tile0 + ((i64)(m0 + i) << logD) + p;
-        if (out_c) out_c[o] = mk<float>(re, im);
-        if (out_p) out_p[o] = re * re + im * im;
+            for (int j = 0; j < STXMR_TAPS; ++j) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(cf2[j]), "l"(win2[i + j]));
+            float re, im;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(re), "=f"(im) : "l"(acc));
+            const i64 o = row + tile0 + ((i64)(m0 + i) << logD) + p;
+            if (out_c) out_c[o] = mk<float>(re, im);
+            if (out_p) out_p[o] = re * re + im * im;
+        }
     }
 #else
-    float cf[STXMR_TAPS];
+        float cf[STXMR_TAPS];
 #pragma unroll
-    for (int j = 0; j < STXMR_TAPS; ++j) cf[j] = coef[(j << logD) + p];
-    cplx<float> win[PER + STXMR_TAPS - 1];
+        for (int j = 0; j < STXMR_TAPS; ++j) cf[j] = coef[(j << logD) + p];
+    for (int tl = 0; tl < ntile; ++tl) {
+        const int m0 = tl * (STXMR_TILE >> logD) + mg;
+        const i64 tile0 = span0;
+        cplx<float> win[PER + STXMR_TAPS - 1];
 #pragma unroll
-    for (int j = 0; j < PER + STXMR_TAPS - 1; ++j) win[j] = seg[m0 + j];
+        for (int j = 0; j < PER + STXMR_TAPS - 1; ++j) win[j] = seg[m0 + j];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        float re = 0.0f, im = 0.0f;
+        for (int i = 0; i < PER; ++i) {
+            float re = 0.0f, im = 0.0f;
 #pragma unroll
-        for (int j = 0; j < STXMR_TAPS; ++j) {
-            re += cf[j] * win[i + j].re;
-            im += cf[j] * win[i + j].im;
+            for (int j = 0; j < STXMR_TAPS; ++j) {
+                re += cf[j] * win[i + j].re;
+                im += cf[j] * win[i + j].im;
+            }
+            const i64 o = row + tile0 + ((i64)(m0 + i) << logD) + p;
+            if (out_c) out_c[o] = mk<float>(re, im);
+            if (out_p) out_p[o] = re * re + im * im;
         }
-        const i64 o = row + tile0 + ((i64)(m0 + i) << logD) + p;
-        if (out_c) out_c[o] = mk<float>(re, im);
-        if (out_p) out_p[o] = re * re + im * im;
     }
 #endif
-    (void)N;
-}
-
-struct StxMrBandPlan { int logK; };
-
-struct StxMrLayout { size_t off_bands, off_ids, off_spec, off_work, off_dec, off_coef, total; i64 gx; };
-
-static int stxmr_logk(double q, i64 N, int logN) {
-    const double kmax = ceil(STXMR_U / fabs(q)) + 1.0;
-    int logK = logN - STXMR_MAX_LOGD;
-    if (logK < 6) logK = 6;
-    while (logK < logN && (double)(1ll << logK) < 4.0 * kmax + 4.0) ++logK;
-    return logK;
-}
-
-static StxMrLayout stxmr_layout(i64 C, i64 N, const QiStxBand* hb, int B) {
-    StxMrLayout lo;
-    const int logN = ceil_log2_i64(N);
-    size_t dec_elems = 0;
-    int count[64] = {0};
-    for (int b = 0; b < B; ++b) ++count[stxmr_logk(hb[b].sigma * 2.0 * M_PI / (double)N, N, logN)];
-    for (int lk = 0; lk < logN; ++lk) {
-        const size_t e = (size_t)count[lk] * (size_t)C << lk;
-        dec_elems = e > dec_elems ? e : dec_elems;
+        (void)N;
     }
-    i64 gx = (i64)((1ull << 30) / ((size_t)C * (size_t)N * sizeof(cplx<float>)));   // exact bands per launch: <= 1 GiB of scratch
-    if (gx < 1) gx = 1;
-    if (gx > count[logN]) gx = count[logN] > 0 ? count[logN] : 1;
-    while (gx * C > 65535 && gx > 1) --gx;
-    lo.gx = gx;
-    const size_t work_elems = dec_elems > (size_t)gx * C * N ? dec_elems : (size_t)gx * C * N;
-    size_t o = 0;
-    lo.off_bands = o; o = align_up(o + sizeof(DevStxBand) * (size_t)B, 256);
-    lo.off_ids = o; o = align_up(o + sizeof(int) * (size_t)B, 256);
-    lo.off_spec = o; o = align_up(o + sizeof(cplx<float>) * (size_t)C * N, 256);
-    lo.off_work = o; o = align_up(o + sizeof(cplx<float>) * work_elems, 256);
-    lo.off_dec = o; o = align_up(o + sizeof(cplx<float>) * (dec_elems ? dec_elems : 1), 256);
-    lo.off_coef = o; o = align_up(o + sizeof(float) * STXMR_TAPS * (size_t)(STXMR_MAX_LOGD + 1) * (1u << STXMR_MAX_LOGD), 256);
-    lo.total = o;
-    return lo;
-}
 
-static int stx_multirate_impl(const void* sig, i64 C, i64 N, i64 stride, const QiStxBand* hb, int B, void* out_c, void* out_p,
-                              void* ws, size_t ws_bytes, cudaStream_t st) {
-    typedef float T;
-    const int logN = ceil_log2_i64(N);
-    const StxMrLayout lo = stxmr_layout(C, N, hb, B);
-    if (ws_bytes < lo.total) return QI_ERR_WORKSPACE;
-    unsigned char* base = static_cast<unsigned char*>(ws);
-    DevStxBand* d_bands = reinterpret_cast<DevStxBand*>(base + lo.off_bands);
-    int* d_ids = reinterpret_cast<int*>(base + lo.off_ids);
-    cplx<T>* spec = reinterpret_cast<cplx<T>*>(base + lo.off_spec);
-    cplx<T>* work = reinterpret_cast<cplx<T>*>(base + lo.off_work);
-    cplx<T>* dec = reinterpret_cast<cplx<T>*>(base + lo.off_dec);
-    float* coef = reinterpret_cast<float*>(base + lo.off_coef);
+    struct StxMrBandPlan { int logK; };
 
-    // band table (decimated bands carry the 5.5-sigma cut-off, exact bands the float32 underflow point) and the band
-    // ids ordered by transform length
-    std::vector<DevStxBand> db(B);
-    std::vector<int> logk(B), ids;
-    for (int b = 0; b < B; ++b) {
-        db[b].q = hb[b].sigma * 2.0 * M_PI / (double)N;
-        db[b].shift = ((hb[b].shift % N) + N) % N;
-        logk[b] = stxmr_logk(db[b].q, N, logN);
-        const double aq = fabs(db[b].q);
-        const double km = aq > 0.0 ? ceil((logk[b] < logN ? STXMR_U : 14.5) / aq) + (logk[b] < logN ? 1.0 : 2.0) : (double)N;
-        db[b].kmax = km < (double)N ? (long long)km : (long long)N;
-    }
-    for (int lk = 0; lk <= logN; ++lk)
-        for (int b = 0; b < B; ++b) if (logk[b] == lk) ids.push_back(b);
-    stage_to_device(d_bands, db.data(), sizeof(DevStxBand) * (size_t)B, st);
-    stage_to_device(d_ids, ids.data(), sizeof(int) * (size_t)B, st);
+    struct StxMrLayout { size_t off_bands, off_ids, off_spec, off_work, off_dec, off_coef, total; i64 gx; };
 
-    CwtGeom geo;
-    geo.n_points = N; geo.n_channels = C; geo.n_bands = B; geo.logL = logN;
-    geo.conv_mode = QI_CONV_LINEAR_SAME; geo.fs = 0; geo.centre_idx = 0; geo.half_shift = 0; geo.d_min = 0; geo.d_max = 0;
-    const FftPlan plan = make_plan(logN, (int)sizeof(cplx<T>));
-    const T one = (T)1;
-    prof_set_category(QI_CAT_FFT_FWD);
-    for (int p = 0; p < plan.npass; ++p) {
-        DstComplex<T> d{spec, N, one};
-        if (p == 0) { SrcRealPad<T> s{static_cast<const T*>(sig), stride, N}; launch_pass<T, FFT_FWD>(plan, p, C, s, d, 0, st); }
-        else { SrcComplex<T> s{spec, N}; launch_pass<T, FFT_FWD>(plan, p, C, s, d, 0, st); }
+    static int stxmr_logk(double q, i64 N, int logN) {
+        const double kmax = ceil(STXMR_U / fabs(q)) + 1.0;
+        int logK = logN - STXMR_MAX_LOGD;
+        if (logK < 6) logK = 6;
+        while (logK < logN && (double)(1ll << logK) < 4.0 * kmax + 4.0) ++logK;
+        return logK;
     }
-    // interpolator tables of every decimation in use: one launch
-    unsigned need_mask = 0;
-    for (int b = 0; b < B; ++b) if (logk[b] < logN) need_mask |= 1u << (logN - logk[b]);
-    if (need_mask) {
-        prof_set_category(QI_CAT_OTHER);
-        dim3 cgrid((unsigned)((STXMR_TAPS << STXMR_MAX_LOGD) / 256), (unsigned)(STXMR_MAX_LOGD + 1));
-        QI_LAUNCH((stxmr_coef_kernel), cgrid, dim3(256), 0, st, coef, need_mask, 1.0 / stxmr_bessel_i0(STXMR_BETA));
-    }
-    // decimated groups
-    size_t pos = 0;
-    while (pos < ids.size()) {
-        const int lk = logk[ids[pos]];
-        size_t end = pos;
-        while (end < ids.size() && logk[ids[end]] == lk) ++end;
-        const int g = (int)(end - pos);
-        if (lk < logN) {
-            const int logD = logN - lk;
-            float* cf = coef + (size_t)logD * STXMR_TAPS * (1u << STXMR_MAX_LOGD);
-            const FftPlan pk = make_plan(lk, (int)sizeof(cplx<T>));
-            const i64 K = 1ll << lk;
-            for (i64 sub = 0; sub < g; ) {                         // grid.y limit: chunks of bands
-                i64 gs = g - sub;
-                while (gs * C > 65535) --gs;
-                const i64 nb = gs * C;
-                SrcStxDec s1{spec, d_bands, d_ids + pos + sub, (int)C, logN, lk};
-                for (int p = pk.npass - 1; p >= 0; --p) {
-                    const bool first = (p == pk.npass - 1), last = (p == 0);
-                    SrcComplex<T> s2{work, K};
-                    DstComplex<T> dw{work, K, one}, dd{dec, K, one};
-                    prof_set_category(first ? QI_CAT_INV_FIRST : QI_CAT_INV_MID);
-                    if (first && last) launch_pass<T, FFT_INV>(pk, p, nb, s1, dd, 0, st);
-                    else if (first) launch_pass<T, FFT_INV>(pk, p, nb, s1, dw, 0, st);
-                    else if (last) launch_pass<T, FFT_INV>(pk, p, nb, s2, dd, 0, st);
-                    else launch_pass<T, FFT_INV>(pk, p, nb, s2, dw, 0, st);
-                }
-                prof_set_category(QI_CAT_INV_LAST);
-                dim3 grid((unsigned)(N / STXMR_TILE), (unsigned)gs, (unsigned)C);
-                QI_LAUNCH((stxmr_interp_kernel), grid, dim3(256), 0, st, (const cplx<T>*)dec, (const int*)(d_ids + pos + sub), (int)C, B,
-                          logN, logD, (const float*)cf, static_cast<cplx<T>*>(out_c), static_cast<T*>(out_p));
-                sub += gs;
-            }
-        } else {
-            // exact bands: the two full-length passes, over maximal runs of consecutive band indices
-            size_t r0 = pos;
-            while (r0 < end) {
-                size_t r1 = r0 + 1;
-                while (r1 < end && ids[r1] == ids[r1 - 1] + 1 && (i64)(r1 - r0) < lo.gx) ++r1;
-                const int band0 = ids[r0], gr = (int)(r1 - r0);
-                const i64 nb = (i64)gr * C;
-                for (int p = plan.npass - 1; p >= 0; --p) {
-                    const bool first = (p == plan.npass - 1), last = (p == 0);
-                    SrcStxSpec<T> s1{spec, d_bands, band0, geo};
-                    SrcComplex<T> s2{work, N};
-                    DstComplex<T> d1{work, N, one};
-                    DstCwtOut<T> d2{static_cast<cplx<T>*>(out_c), static_cast<T*>(out_p), nullptr, band0, geo, 0.0};
-                    prof_set_category(last ? QI_CAT_INV_LAST : (first ? QI_CAT_INV_FIRST : QI_CAT_INV_MID));
-                    if (first && last) launch_pass<T, FFT_INV>(plan, p, nb, s1, d2, 256, st);
-                    else if (first) launch_pass<T, FFT_INV>(plan, p, nb, s1, d1, 0, st);
-                    else if (last) launch_pass<T, FFT_INV>(plan, p, nb, s2, d2, 256, st);
-                    else launch_pass<T, FFT_INV>(plan, p, nb, s2, d1, 0, st);
-                }
-                r0 = r1;
-            }
+
+    static StxMrLayout stxmr_layout(i64 C, i64 N, const QiStxBand* hb, int B) {
+        StxMrLayout lo;
+        const int logN = ceil_log2_i64(N);
+        size_t dec_elems = 0;
+        int count[64] = {0};
+        for (int b = 0; b < B; ++b) ++count[stxmr_logk(hb[b].sigma * 2.0 * M_PI / (double)N, N, logN)];
+        for (int lk = 0; lk < logN; ++lk) {
+            const size_t e = (size_t)count[lk] * (size_t)C << lk;
+            dec_elems = e > dec_elems ? e : dec_elems;
         }
-        pos = end;
+        i64 gx = (i64)((1ull << 30) / ((size_t)C * (size_t)N * sizeof(cplx<float>)));   // exact bands per launch: <= 1 GiB of scratch
+        if (gx < 1) gx = 1;
+        if (gx > count[logN]) gx = count[logN] > 0 ? count[logN] : 1;
+        while (gx * C > 65535 && gx > 1) --gx;
+        lo.gx = gx;
+        const size_t work_elems = dec_elems > (size_t)gx * C * N ? dec_elems : (size_t)gx * C * N;
+        size_t o = 0;
+        lo.off_bands = o; o = align_up(o + sizeof(DevStxBand) * (size_t)B, 256);
+        lo.off_ids = o; o = align_up(o + sizeof(int) * (size_t)B, 256);
+        lo.off_spec = o; o = align_up(o + sizeof(cplx<float>) * (size_t)C * N, 256);
+        lo.off_work = o; o = align_up(o + sizeof(cplx<float>) * work_elems, 256);
+        lo.off_dec = o; o = align_up(o + sizeof(cplx<float>) * (dec_elems ? dec_elems : 1), 256);
+        lo.off_coef = o; o = align_up(o + sizeof(float) * STXMR_TAPS * (size_t)(STXMR_MAX_LOGD + 1) * (1u << STXMR_MAX_LOGD), 256);
+        lo.total = o;
+        return lo;
     }
-    prof_set_category(QI_CAT_OTHER);
-    return check_cuda("qi_stx_multirate");
-}
 
-template <typename T>
-static int stx_windows_impl(const QiStxBand* hb, int B, i64 N, void* out, void* ws, size_t ws_bytes, cudaStream_t st) {
-    if (ws_bytes < sizeof(DevStxBand) * (size_t)B) return QI_ERR_WORKSPACE;
-    DevStxBand* d_bands = static_cast<DevStxBand*>(ws);
-    upload_stx_bands(hb, B, N, 1e300, d_bands, st);
-    dim3 grid((unsigned)((N + 255) / 256), (unsigned)B);
-    QI_LAUNCH((stx_windows_kernel<T>), grid, dim3(256), 0, st, d_bands, N, static_cast<cplx<T>*>(out));
-    return check_cuda("qi_stx_windows");
-}
+    static int stx_multirate_impl(const void* sig, i64 C, i64 N, i64 stride, const QiStxBand* hb, int B, void* out_c, void* out_p,
+                                  void* ws, size_t ws_bytes, cudaStream_t st) {
+        typedef float T;
+        const int logN = ceil_log2_i64(N);
+        const StxMrLayout lo = stxmr_layout(C, N, hb, B);
+        if (ws_bytes < lo.total) return QI_ERR_WORKSPACE;
+        unsigned char* base = static_cast<unsigned char*>(ws);
+        DevStxBand* d_bands = reinterpret_cast<DevStxBand*>(base + lo.off_bands);
+        int* d_ids = reinterpret_cast<int*>(base + lo.off_ids);
+        cplx<T>* spec = reinterpret_cast<cplx<T>*>(base + lo.off_spec);
+        cplx<T>* work = reinterpret_cast<cplx<T>*>(base + lo.off_work);
+        cplx<T>* dec = reinterpret_cast<cplx<T>*>(base + lo.off_dec);
+        float* coef = reinterpret_cast<float*>(base + lo.off_coef);
 
-}  // namespace qi
+        // band table (decimated bands carry the 5.5-sigma cut-off, exact bands the float32 underflow point) and the band
+        // ids ordered by transform length
+        std::vector<DevStxBand> db(B);
+        std::vector<int> logk(B), ids;
+        for (int b = 0; b < B; ++b) {
+            db[b].q = hb[b].sigma * 2.0 * M_PI / (double)N;
+            db[b].shift = ((hb[b].shift % N) + N) % N;
+            logk[b] = stxmr_logk(db[b].q, N, logN);
+            const double aq = fabs(db[b].q);
+            const double km = aq > 0.0 ? ceil((logk[b] < logN ? STXMR_U : 14.5) / aq) + (logk[b] < logN ? 1.0 : 2.0) : (double)N;
+            db[b].kmax = km < (double)N ? (long long)km : (long long)N;
+        }
+        for (int lk = 0; lk <= logN; ++lk)
+            for (int b = 0; b < B; ++b) if (logk[b] == lk) ids.push_back(b);
+        stage_to_device(d_bands, db.data(), sizeof(DevStxBand) * (size_t)B, st);
+        stage_to_device(d_ids, ids.data(), sizeof(int) * (size_t)B, st);
 
-extern "C" {
+        CwtGeom geo;
+        geo.n_points = N; geo.n_channels = C; geo.n_bands = B; geo.logL = logN;
+        geo.conv_mode = QI_CONV_LINEAR_SAME; geo.fs = 0; geo.centre_idx = 0; geo.half_shift = 0; geo.d_min = 0; geo.d_max = 0;
+        const FftPlan plan = make_plan(logN, (int)sizeof(cplx<T>));
+        const T one = (T)1;
+        prof_set_category(QI_CAT_FFT_FWD);
+        for (int p = 0; p < plan.npass; ++p) {
+            DstComplex<T> d{spec, N, one};
+            if (p == 0) { SrcRealPad<T> s{static_cast<const T*>(sig), stride, N}; launch_pass<T, FFT_FWD>(plan, p, C, s, d, 0, st); }
+            else { SrcComplex<T> s{spec, N}; launch_pass<T, FFT_FWD>(plan, p, C, s, d, 0, st); }
+        }
+        // interpolator tables of every decimation in use: one launch
+        unsigned need_mask = 0;
+        for (int b = 0; b < B; ++b) if (logk[b] < logN) need_mask |= 1u << (logN - logk[b]);
+        if (need_mask) {
+            prof_set_category(QI_CAT_OTHER);
+            dim3 cgrid((unsigned)((STXMR_TAPS << STXMR_MAX_LOGD) / 256), (unsigned)(STXMR_MAX_LOGD + 1));
+            QI_LAUNCH((stxmr_coef_kernel), cgrid, dim3(256), 0, st, coef, need_mask, 1.0 / stxmr_bessel_i0(STXMR_BETA));
+        }
+        // decimated groups
+        size_t pos = 0;
+        while (pos < ids.size()) {
+            const int lk = logk[ids[pos]];
+            size_t end = pos;
+            while (end < ids.size() && logk[ids[end]] == lk) ++end;
+            const int g = (int)(end - pos);
+            if (lk < logN) {
+                const int logD = logN - lk;
+                float* cf = coef + (size_t)logD * STXMR_TAPS * (1u << STXMR_MAX_LOGD);
+                const FftPlan pk = make_plan(lk, (int)sizeof(cplx<T>));
+                const i64 K = 1ll << lk;
+                for (i64 sub = 0; sub < g; ) {                         // grid.y limit: chunks of bands
+                    i64 gs = g - sub;
+                    while (gs * C > 65535) --gs;
+                    const i64 nb = gs * C;
+                    SrcStxDec s1{spec, d_bands, d_ids + pos + sub, (int)C, logN, lk};
+                    for (int p = pk.npass - 1; p >= 0; --p) {
+                        const bool first = (p == pk.npass - 1), last = (p == 0);
+                        SrcComplex<T> s2{work, K};
+                        DstComplex<T> dw{work, K, one}, dd{dec, K, one};
+                        prof_set_category(first ? QI_CAT_INV_FIRST : QI_CAT_INV_MID);
+                        if (first && last) launch_pass<T, FFT_INV>(pk, p, nb, s1, dd, 0, st);
+                        else if (first) launch_pass<T, FFT_INV>(pk, p, nb, s1, dw, 0, st);
+                        else if (last) launch_pass<T, FFT_INV>(pk, p, nb, s2, dd, 0, st);
+                        else launch_pass<T, FFT_INV>(pk, p, nb, s2, dw, 0, st);
+                    }
+                    prof_set_category(QI_CAT_INV_LAST);
+                    dim3 grid((unsigned)((N + STXMR_SPAN * STXMR_TILE - 1) / (STXMR_SPAN * STXMR_TILE)), (unsigned)gs, (unsigned)C);
+                    QI_LAUNCH((stxmr_interp_kernel), grid, dim3(256), 0, st, (const cplx<T>*)dec, (const int*)(d_ids + pos + sub), (int)C, B,
+                              logN, logD, (const float*)cf, static_cast<cplx<T>*>(out_c), static_cast<T*>(out_p));
+                    sub += gs;
+                }
+            } else {
+                // exact bands: the two full-length passes, over maximal runs of consecutive band indices
+                size_t r0 = pos;
+                while (r0 < end) {
+                    size_t r1 = r0 + 1;
+                    while (r1 < end && ids[r1] == ids[r1 - 1] + 1 && (i64)(r1 - r0) < lo.gx) ++r1;
+                    const int band0 = ids[r0], gr = (int)(r1 - r0);
+                    const i64 nb = (i64)gr * C;
+                    for (int p = plan.npass - 1; p >= 0; --p) {
+                        const bool first = (p == plan.npass - 1), last = (p == 0);
+                        SrcStxSpec<T> s1{spec, d_bands, band0, geo};
+                        SrcComplex<T> s2{work, N};
+                        DstComplex<T> d1{work, N, one};
+                        DstCwtOut<T> d2{static_cast<cplx<T>*>(out_c), static_cast<T*>(out_p), nullptr, band0, geo, 0.0};
+                        prof_set_category(last ? QI_CAT_INV_LAST : (first ? QI_CAT_INV_FIRST : QI_CAT_INV_MID));
+                        if (first && last) launch_pass<T, FFT_INV>(plan, p, nb, s1, d2, 256, st);
+                        else if (first) launch_pass<T, FFT_INV>(plan, p, nb, s1, d1, 0, st);
+                        else if (last) launch_pass<T, FFT_INV>(plan, p, nb, s2, d2, 256, st);
+                        else launch_pass<T, FFT_INV>(plan, p, nb, s2, d1, 0, st);
+                    }
+                    r0 = r1;
+                }
+            }
+            pos = end;
+        }
+        prof_set_category(QI_CAT_OTHER);
+        return check_cuda("qi_stx_multirate");
+    }
 
-size_t qi_stx_workspace_bytes(int64_t C, int64_t N, int B, int group, int dtype) {
-    if (C <= 0 || N <= 0 || B <= 0) return 0;
-    return dtype == QI_F32 ? qi::stx_layout<float>(C, N, B, group).total : qi::stx_layout<double>(C, N, B, group).total;
-}
+    template <typename T>
+    static int stx_windows_impl(const QiStxBand* hb, int B, i64 N, void* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+        if (ws_bytes < sizeof(DevStxBand) * (size_t)B) return QI_ERR_WORKSPACE;
+        DevStxBand* d_bands = static_cast<DevStxBand*>(ws);
+        upload_stx_bands(hb, B, N, 1e300, d_bands, st);
+        dim3 grid((unsigned)((N + 255) / 256), (unsigned)B);
+        QI_LAUNCH((stx_windows_kernel<T>), grid, dim3(256), 0, st, d_bands, N, static_cast<cplx<T>*>(out));
+        return check_cuda("qi_stx_windows");
+    }
 
-int qi_stx_fft(const void* sig, int64_t C, int64_t N, int64_t stride, const QiStxBand* bands, int B, int dtype,
-               void* out_tfr, void* out_power, double* band_sum, void* ws, size_t ws_bytes, int group, void* stream) {
-    if (!sig || !bands || !ws || C <= 0 || N <= 0 || B <= 0 || stride < N) return QI_ERR_ARG;
-    if (N & (N - 1)) return QI_ERR_ARG;
-    if (N > (1ll << 30)) return QI_ERR_UNSUPPORTED;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (dtype == QI_F32) return qi::stx_fft_impl<float>(sig, C, N, stride, bands, B, out_tfr, out_power, band_sum, ws, ws_bytes, group, st);
-    if (dtype == QI_F64) return qi::stx_fft_impl<double>(sig, C, N, stride, bands, B, out_tfr, out_power, band_sum, ws, ws_bytes, group, st);
-    return QI_ERR_ARG;
-}
+    }  // namespace qi
 
-size_t qi_stx_multirate_workspace_bytes(int64_t C, int64_t N, const QiStxBand* bands, int B) {
-    if (C <= 0 || N < qi::STXMR_TILE * 2 || (N & (N - 1)) || B <= 0 || !bands) return 0;
-    return qi::stxmr_layout(C, N, bands, B).total;
-}
+    extern "C" {
 
-int qi_stx_multirate(const void* sig, int64_t C, int64_t N, int64_t stride, const QiStxBand* bands, int B, void* out_tfr,
-                     void* out_power, void* ws, size_t ws_bytes, void* stream) {
-    if (!sig || !bands || !ws || C <= 0 || C > 65535 || N <= 0 || B <= 0 || stride < N || (!out_tfr && !out_power)) return QI_ERR_ARG;
-    if ((N & (N - 1)) || N < qi::STXMR_TILE * 2) return QI_ERR_ARG;
-    if (N > (1ll << 30)) return QI_ERR_UNSUPPORTED;
-    return qi::stx_multirate_impl(sig, C, N, stride, bands, B, out_tfr, out_power, ws, ws_bytes, static_cast<cudaStream_t>(stream));
-}
+    size_t qi_stx_workspace_bytes(int64_t C, int64_t N, int B, int group, int dtype) {
+        if (C <= 0 || N <= 0 || B <= 0) return 0;
+        return dtype == QI_F32 ? qi::stx_layout<float>(C, N, B, group).total : qi::stx_layout<double>(C, N, B, group).total;
+    }
 
-int qi_stx_windows(const QiStxBand* bands, int B, int64_t N, int dtype, void* out, void* ws, size_t ws_bytes, void* stream) {
-    if (!bands || !out || !ws || B <= 0 || N <= 0) return QI_ERR_ARG;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (dtype == QI_F32) return qi::stx_windows_impl<float>(bands, B, N, out, ws, ws_bytes, st);
-    if (dtype == QI_F64) return qi::stx_windows_impl<double>(bands, B, N, out, ws, ws_bytes, st);
-    return QI_ERR_ARG;
-}
+    int qi_stx_fft(const void* sig, int64_t C, int64_t N, int64_t stride, const QiStxBand* bands, int B, int dtype,
+                   void* out_tfr, void* out_power, double* band_sum, void* ws, size_t ws_bytes, int group, void* stream) {
+        if (!sig || !bands || !ws || C <= 0 || N <= 0 || B <= 0 || stride < N) return QI_ERR_ARG;
+        if (N & (N - 1)) return QI_ERR_ARG;
+        if (N > (1ll << 30)) return QI_ERR_UNSUPPORTED;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (dtype == QI_F32) return qi::stx_fft_impl<float>(sig, C, N, stride, bands, B, out_tfr, out_power, band_sum, ws, ws_bytes, group, st);
+        if (dtype == QI_F64) return qi::stx_fft_impl<double>(sig, C, N, stride, bands, B, out_tfr, out_power, band_sum, ws, ws_bytes, group, st);
+        return QI_ERR_ARG;
+    }
 
-}  // extern "C"
+    size_t qi_stx_multirate_workspace_bytes(int64_t C, int64_t N, const QiStxBand* bands, int B) {
+        if (C <= 0 || N < qi::STXMR_TILE * 2 || (N & (N - 1)) || B <= 0 || !bands) return 0;
+        return qi::stxmr_layout(C, N, bands, B).total;
+    }
+
+    int qi_stx_multirate(const void* sig, int64_t C, int64_t N, int64_t stride, const QiStxBand* bands, int B, void* out_tfr,
+                         void* out_power, void* ws, size_t ws_bytes, void* stream) {
+        if (!sig || !bands || !ws || C <= 0 || C > 65535 || N <= 0 || B <= 0 || stride < N || (!out_tfr && !out_power)) return QI_ERR_ARG;
+        if ((N & (N - 1)) || N < qi::STXMR_TILE * 2) return QI_ERR_ARG;
+        if (N > (1ll << 30)) return QI_ERR_UNSUPPORTED;
+        return qi::stx_multirate_impl(sig, C, N, stride, bands, B, out_tfr, out_power, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    }
+
+    int qi_stx_windows(const QiStxBand* bands, int B, int64_t N, int dtype, void* out, void* ws, size_t ws_bytes, void* stream) {
+        if (!bands || !out || !ws || B <= 0 || N <= 0) return QI_ERR_ARG;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (dtype == QI_F32) return qi::stx_windows_impl<float>(bands, B, N, out, ws, ws_bytes, st);
+        if (dtype == QI_F64) return qi::stx_windows_impl<double>(bands, B, N, out, ws, ws_bytes, st);
+        return QI_ERR_ARG;
+    }
+
+    }  // extern "C"
