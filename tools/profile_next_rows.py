@@ -28,5 +28,9 @@ if "stft" in which:
     styx_fft.stft_complex_pow2(x, FS, 1024, alpha=1.0, dtype="float32")
     obj = stf.get_stft_object_tukey(FS, 0.25, 1024, 512, dtype="float32")
     stf.istft_tukey(obj.stft(x), FS, 0.25, 1024, 512, dtype="float32")
+if "stxmr" in which:
+    from quantum_inferno_b200 import styx_stx
+    x = synth_batch_torch(torch, 1 << 18, list(range(16)), DEV)
+    styx_stx.stx_complex_any_scale_pow2(3, x, FS, dtype="float32", method="multirate")
 torch.cuda.synchronize()
 print("done")
