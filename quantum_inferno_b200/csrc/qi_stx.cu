@@ -188,7 +188,8 @@ __global__ void stxmr_coef_kernel(float* __restrict__ coef_all, unsigned need_ma
 __global__ void __launch_bounds__(256)
 stxmr_interp_kernel(const cplx<float>* __restrict__ dec, const int* __restrict__ ids, int n_channels, int n_bands, int logN,
                     int logD, const float* __restrict__ coef, cplx<float>* __restrict__ out_c, float* __restrict__ out_p) {
-    __shared__ cplx<float> seg[STXMR_SPAN * STXMR_TILE / 2 + STXMR_TAPS];
+    // one pad slot per 8 decimated samples: at small D the lanes of a warp start their windows 8 samples apart
+    __shared__ cplx<float> seg[(STXMR_SPAN * STXMR_TILE / 2 + STXMR_TAPS) * 9 / 8 + 2];
     const int D = 1 << logD, logK = logN - logD;
     const i64 K = 1ll << logK, N = 1ll << logN;
     const i64 span0 = (i64)blockIdx.x * (STXMR_SPAN * STXMR_TILE);
@@ -198,7 +199,7 @@ stxmr_interp_kernel(const cplx<float>* __restrict__ dec, const int* __restrict__
     const cplx<float>* src = dec + (((i64)bi * n_channels + chan) << logK);
     const i64 m_base = (span0 >> logD) - 7;
     const int nseg = ((ntile * STXMR_TILE) >> logD) + STXMR_TAPS;
-    for (int i = threadIdx.x; i < nseg; i += blockDim.x) seg[i] = src[(m_base + i) & (K - 1)];
+    for (int i = threadIdx.x; i < nseg; i += blockDim.x) seg[i + (i >> 3)] = src[(m_base + i) & (K - 1)];
     __syncthreads();
     const i64 row = ((i64)chan * n_bands + band) << logN;
     // Thread (p, g): phase p = tid mod D, and the 8 consecutive decimated positions m = 8 g .. 8 g + 7 (256 / D threads
@@ -219,7 +220,7 @@ stxmr_interp_kernel(const cplx<float>* __restrict__ dec, const int* __restrict__
         const int m0 = tl * (STXMR_TILE >> logD) + mg;
         const i64 tile0 = span0;
 #pragma unroll
-        for (int j = 0; j < PER + STXMR_TAPS - 1; ++j) win2[j] = *reinterpret_cast<const unsigned long long*>(&seg[m0 + j]);
+        for (int j = 0; j < PER + STXMR_TAPS - 1; ++j) win2[j] = *reinterpret_cast<const unsigned long long*>(&seg[m0 + j + ((m0 + j) >> 3)]);
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             unsigned long long acc;
@@ -242,7 +243,7 @@ stxmr_interp_kernel(const cplx<float>* __restrict__ dec, const int* __restrict__
         const i64 tile0 = span0;
         cplx<float> win[PER + STXMR_TAPS - 1];
 #pragma unroll
-        for (int j = 0; j < PER + STXMR_TAPS - 1; ++j) win[j] = seg[m0 + j];
+        for (int j = 0; j < PER + STXMR_TAPS - 1; ++j) win[j] = seg[m0 + j + ((m0 + j) >> 3)];
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             float re = 0.0f, im = 0.0f;
