@@ -70,43 +70,36 @@ def well_tempered_tone(frequency_sample_rate_hz: float = 800.0, frequency_center
     if add_noise_taper_aa:
         raise NotImplementedError("add_noise_taper_aa draws unseeded numpy.random noise in the reference "
                                   "(synth/synthetic_signals.py:169); only the deterministic tone is provided")
-    frequency_resolution_hz = 1.0 / time_fft_s
-    time_duration_nd = 2 ** (int(np.log2(time_duration_s * frequency_sample_rate_hz)))
-    time_fft_nd = 2 ** (int(np.log2(time_fft_s * frequency_sample_rate_hz)))
-    if time_duration_nd != time_duration_s * frequency_sample_rate_hz:
-        print(
-            f"Warning: The time duration {time_duration_s} s with given sample rate doesn't produce data points "
-            f"that are power of two, adjusting time duration to {time_duration_nd} s"
-        )
-    if time_fft_nd != time_fft_s * frequency_sample_rate_hz:
-        print(
-            f"Warning: fft duration {time_fft_s} s with given sample rate doesn't produce data points "
-            f"that are power of two, adjusting fft duration to {time_fft_nd} s"
-        )
-    frequency_fft_pos_hz = np.fft.rfftfreq(time_fft_nd, d=1 / frequency_sample_rate_hz)
-    fft_index = np.argmin(np.abs(frequency_fft_pos_hz - frequency_center_hz))
-    frequency_center_fft_hz = frequency_fft_pos_hz[fft_index]
-    frequency_resolution_fft_hz = frequency_sample_rate_hz / time_fft_nd
-    if use_fft_frequency:
-        f_c = frequency_center_fft_hz / frequency_sample_rate_hz
-    else:
-        f_c = frequency_center_hz / frequency_sample_rate_hz
+    fs = frequency_sample_rate_hz
+
+    def floor_pow2(seconds):
+        """Largest power of two not above seconds * fs (the reference truncates log2 with int())."""
+        return 2 ** (int(np.log2(seconds * fs)))
+
+    n_record, n_fft = floor_pow2(time_duration_s), floor_pow2(time_fft_s)
+    for what, asked, got in (("The time duration", time_duration_s, n_record), ("fft duration", time_fft_s, n_fft)):
+        if got != asked * fs:                                           # same wording as the reference's two warnings
+            print(f"Warning: {what} {asked} s with given sample rate doesn't produce data points "
+                  f"that are power of two, adjusting {what[4:] if what.startswith('The ') else what} to {got} s")
+    # the tone sits on a bin of the n_fft-point transform unless the caller asks for the nominal frequency
+    bins_hz = np.fft.rfftfreq(n_fft, d=1 / fs)
+    frequency_center_fft_hz = bins_hz[np.argmin(np.abs(bins_hz - frequency_center_hz))]
+    frequency_resolution_fft_hz = fs / n_fft
+    f_c = (frequency_center_fft_hz if use_fft_frequency else frequency_center_hz) / fs
     rt = get_runtime()
     dt = dtype_name(dtype)
     # mic_sig = cos(2.0 * pi * f_c * time_nd): the scalar product first, as Python evaluates it
-    sig = _driver.synth_chirp(time_duration_nd, dt, 2.0 * np.pi * f_c, rt=rt)
-    sig = rt.reshape(sig, (time_duration_nd,))
-    time_s = np.arange(time_duration_nd) / frequency_sample_rate_hz
+    sig = rt.reshape(_driver.synth_chirp(n_record, dt, 2.0 * np.pi * f_c, rt=rt), (n_record,))
+    time_s = np.arange(n_record) / fs
     if output_desc:
         print("WELL TEMPERED TONE SYNTHETIC")
-        print("Nyquist frequency:", frequency_sample_rate_hz / 2)
-        print("Nominal signal frequency, hz:", frequency_center_hz)
-        print("FFT signal frequency, hz:", frequency_center_fft_hz)
-        print("Nominal spectral resolution, hz", frequency_resolution_hz)
-        print("FFT spectral resolution, hz", frequency_resolution_fft_hz)
-        print("Number of signal points:", time_duration_nd)
-        print("log2(points):", np.log2(time_duration_nd))
-        print("Number of FFT points:", time_fft_nd)
-        print("log2(FFT points):", np.log2(time_fft_nd))
+        for label, value in (("Nyquist frequency:", fs / 2), ("Nominal signal frequency, hz:", frequency_center_hz),
+                             ("FFT signal frequency, hz:", frequency_center_fft_hz),
+                             ("Nominal spectral resolution, hz", 1.0 / time_fft_s),
+                             ("FFT spectral resolution, hz", frequency_resolution_fft_hz),
+                             ("Number of signal points:", n_record), ("log2(points):", np.log2(n_record)),
+                             ("Number of FFT points:", n_fft), ("log2(FFT points):", np.log2(n_fft))):
+            print(label, value)
+    time_fft_nd = n_fft
     mic_sig = sig if device_out else rt.to_numpy(sig)
     return mic_sig, time_s, time_fft_nd, frequency_sample_rate_hz, frequency_center_fft_hz, frequency_resolution_fft_hz
