@@ -166,6 +166,13 @@ def test_host_side_of_the_next_rows():
     assert lib.qi_filtfilt_workspace_bytes(1, 4096, 27, 17) == 0
     assert lib.qi_subsample(None, 1, 8, 8, 2, 1, 0, None, 4, None) == -1
     assert lib.qi_synth_chirp(1, 8, 8, 0, 0.0, 0.1, 0.0, 0.0, 0, 1, None, None, None) == -1
+    # multirate Stockwell planning (host side of qi_stx_multirate): workspace grows with the record, refuses short records
+    from quantum_inferno_b200 import _plan
+    f, sb = _plan.stx_bands(3, 1 << 16, 800.0)
+    sb = np.ascontiguousarray(sb, dtype=_lib.STX_BAND)
+    w16 = lib.qi_stx_multirate_workspace_bytes(2, 1 << 16, sb.ctypes.data, len(sb))
+    assert w16 > 2 * (1 << 16) * 8 * 2 and lib.qi_stx_multirate_workspace_bytes(2, 2048, sb.ctypes.data, len(sb)) == 0
+    assert lib.qi_stx_multirate(None, 2, 1 << 16, 1 << 16, sb.ctypes.data, len(sb), None, None, None, 0, None) == -1
     # factoring the reference's rounded taps: sections multiply back to the taps (float64 product of the sections is
     # good to 1e-9 for these designs; the exactness itself is asserted against the long-double recursion elsewhere)
     from scipy import signal
