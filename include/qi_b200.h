@@ -170,6 +170,7 @@ int qi_stx_multirate(const void* sig, int64_t n_channels, int64_t n_points, int6
                      int n_bands, void* out_tfr, void* out_power, void* workspace, size_t workspace_bytes, void* stream);
 
 /* windows_fft of tfr_stx_fft (styx_stx.py:179): out complex [n_bands, n_points], natural bin order */
+size_t qi_stx_windows_workspace_bytes(int n_bands);
 int qi_stx_windows(const QiStxBand* bands, int n_bands, int64_t n_points, int dtype, void* out,
                    void* workspace, size_t workspace_bytes, void* stream);
 

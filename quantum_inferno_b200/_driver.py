@@ -123,7 +123,7 @@ def stx_windows(bands, n_points, dt, rt=None):
     bands = np.ascontiguousarray(bands, dtype=_lib.STX_BAND)
     B = len(bands)
     out = rt.empty((B, n_points), COMPLEX_OF[dt])
-    nbytes = max(4096, 16 * B)
+    nbytes = max(4096, lib.qi_stx_windows_workspace_bytes(B))
     ws = rt.workspace(nbytes)
     rc = lib.qi_stx_windows(bands.ctypes.data, B, int(n_points), DTYPE_CODE[dt], rt.ptr(out), rt.ptr(ws), nbytes,
                             rt.stream())

@@ -67,6 +67,7 @@ SIGNATURES = {
     "qi_power_bits": (_c_int, [_c_vp, _c_i64, _c_i64, _c_int, _c_vp, _c_dbl, _c_vp, _c_vp]),
     "qi_tdr_marginal": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]),
     "qi_rfft": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
+    "qi_stx_windows_workspace_bytes": (_c_sz, [_c_int]),
     "qi_stx_windows": (_c_int, [_c_vp, _c_int, _c_i64, _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
     "qi_subsample": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_vp, _c_i64, _c_vp]),
     "qi_extrema": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_vp]),

@@ -28,8 +28,34 @@ def dtype_name(dtype, default="float64"):
     return s
 
 
+class _DeviceBoundLib:
+    """The bound C library with every ``qi_*`` call made while ``device`` is the current CUDA device: the kernels are
+    launched with ``<<<>>>`` on the stream handed in, so the device that owns that stream and the buffers has to be
+    current whatever the caller's ``torch.cuda.current_device()`` is."""
+
+    def __init__(self, lib, torch, device):
+        self._lib, self._torch, self._device = lib, torch, device
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw, guard, dev = getattr(self._lib, name), self._torch.cuda.device, self._device
+
+            def fn(*args):
+                with guard(dev):
+                    return raw(*args)
+
+            self._cache[name] = fn
+        return fn
+
+
 class CudaRuntime:
-    """torch-backed buffers on one CUDA device + the bound CUDA library."""
+    """torch-backed buffers on ONE CUDA device + the bound CUDA library.
+
+    One runtime exists per device (``get_runtime(like=tensor)`` picks the tensor's device).  Scratch memory is one
+    grow-only buffer per (device, stream): calls on the same stream are ordered, so they can share it; calls on
+    different streams get different buffers.  Host threads must not share a stream (plain CUDA stream semantics)."""
     name = "cuda"
 
     def __init__(self, device=None):
@@ -38,9 +64,11 @@ class CudaRuntime:
             raise RuntimeError("quantum_inferno_b200 needs a CUDA device (B200, sm_100a); none is visible and "
                                "there is no CPU fallback")
         self.torch = torch
-        self.lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self._ws = None
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.lib = _DeviceBoundLib(_lib.load(), torch, self.device)
+        self._ws = {}
 
     # ---- buffers
     def _tdtype(self, name):
@@ -70,11 +98,20 @@ class CudaRuntime:
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
     def workspace(self, nbytes):
-        """Grow-only scratch buffer (256-byte aligned by the caching allocator)."""
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = None
-            self._ws = self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
-        return self._ws
+        """Grow-only scratch buffer of the current stream (256-byte aligned by the caching allocator).  A buffer that
+        is outgrown goes back to the caching allocator, which keeps it alive until the stream has passed its last use."""
+        key = self.stream()
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            self._ws.pop(key, None)
+            with self.torch.cuda.device(self.device):
+                ws = self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    def release_workspace(self):
+        """Give every scratch buffer back to the caching allocator."""
+        self._ws.clear()
 
     def to_numpy(self, buf):
         return buf.detach().cpu().numpy()
@@ -83,14 +120,26 @@ class CudaRuntime:
         return buf.reshape(tuple(shape))
 
 
-_runtime = None
+_runtime = None          # override installed by use_runtime() (test-suite emulator); wins over the per-device table
+_cuda_runtimes = {}      # device index -> CudaRuntime
 
 
-def get_runtime():
-    global _runtime
-    if _runtime is None:
-        _runtime = CudaRuntime()
-    return _runtime
+def get_runtime(like=None):
+    """The runtime of the device that holds ``like`` (a CUDA tensor), else of torch's current CUDA device."""
+    if _runtime is not None:
+        return _runtime
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("quantum_inferno_b200 needs a CUDA device (B200, sm_100a); none is visible and there is "
+                           "no CPU fallback")
+    if isinstance(like, torch.Tensor) and like.is_cuda:
+        index = like.device.index
+    else:
+        index = torch.cuda.current_device()
+    rt = _cuda_runtimes.get(index)
+    if rt is None:
+        rt = _cuda_runtimes[index] = CudaRuntime(torch.device("cuda", index))
+    return rt
 
 
 @contextlib.contextmanager

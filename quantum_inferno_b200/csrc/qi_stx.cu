@@ -455,6 +455,8 @@ stxmr_interp_kernel(const cplx<float>* __restrict__ dec, const int* __restrict__
         return qi::stx_multirate_impl(sig, C, N, stride, bands, B, out_tfr, out_power, ws, ws_bytes, static_cast<cudaStream_t>(stream));
     }
 
+    size_t qi_stx_windows_workspace_bytes(int B) { return B > 0 ? sizeof(qi::DevStxBand) * (size_t)B : 0; }
+
     int qi_stx_windows(const QiStxBand* bands, int B, int64_t N, int dtype, void* out, void* ws, size_t ws_bytes, void* stream) {
         if (!bands || !out || !ws || B <= 0 || N <= 0) return QI_ERR_ARG;
         cudaStream_t st = static_cast<cudaStream_t>(stream);

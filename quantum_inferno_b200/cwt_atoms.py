@@ -183,7 +183,7 @@ def cwt_chirp_complex(band_order_nth: float, sig_wf, frequency_low_hz: float, fr
         raise NotImplementedError("cwt_type='morlet2' relied on scipy.signal.cwt, removed from SciPy")
     if cwt_type not in ("fft", "conv"):
         raise ValueError(f"Incorrect cwt_type: {cwt_type} specified in cwt_chirp_complex")
-    rt = get_runtime()
+    rt = get_runtime(sig_wf)
     dt = dtype_name(dtype)
     want_numpy = not rt.is_device_array(sig_wf)
     sig, was_1d = _driver._as_2d(rt, sig_wf, dt)

@@ -111,7 +111,7 @@ def cwt_power_entropy(band_order_nth: float, sig_wf, frequency_sample_rate_hz: f
                  channels in this many groups, copying group k+1 to the device on a second stream while group k is
                  being transformed (channels are independent, so the result is identical).
     """
-    rt = get_runtime()
+    rt = get_runtime(sig_wf)
     dt = dtype_name(dtype, default="float32")
     if host_chunks > 1 and getattr(rt, "name", "") == "cuda" and not getattr(sig_wf, "is_cuda", False) \
             and np.ndim(sig_wf) == 2 and np.shape(sig_wf)[0] > 1 and allreduce is None:

@@ -103,7 +103,7 @@ def cwt_complex_any_scale_pow2(band_order_nth: float, sig_wf, frequency_sample_r
     if cwt_type == "morlet2":
         # upstream calls scipy.signal.cwt here, which SciPy >= 1.15 no longer has (AttributeError)
         raise NotImplementedError("cwt_type='morlet2' relied on scipy.signal.cwt, removed from SciPy; use 'fft'")
-    rt = get_runtime()
+    rt = get_runtime(sig_wf)
     dt = dtype_name(dtype)
     want_numpy = not rt.is_device_array(sig_wf)
     sig, was_1d = _driver._as_2d(rt, sig_wf, dt)

@@ -41,7 +41,7 @@ def _spectral(sig_wf, fs, window, nperseg, noverlap, nfft, dtype, welch=False):
         raise ValueError("nfft must be greater than or equal to nperseg.")
     if not is_power_of_two(int(nfft)):
         raise ValueError(f"the STFT kernel needs nfft = 2^m, got {nfft}")
-    rt = get_runtime()
+    rt = get_runtime(sig_wf)
     dt = dtype_name(dtype)
     want_numpy = not rt.is_device_array(sig_wf)
     x = rt.asarray(sig_wf, dt)
@@ -125,7 +125,7 @@ def stft_from_sig(sig_wf, frequency_sample_rate_hz: float, band_order_nth: float
     if len(sig_wf) < time_fft_nd:
         raise ValueError(f"Signal length: {len(sig_wf)} is less than time_fft_nd: {time_fft_nd}")
     stft_scaling = 2 * np.sqrt(np.pi) / time_fft_nd
-    rt = get_runtime()
+    rt = get_runtime(sig_wf)
     want_numpy = not rt.is_device_array(sig_wf)
     frequency_stft_hz, time_stft_s, stft_complex = stft_complex_pow2(
         sig_wf=rt.asarray(sig_wf, dtype_name(dtype)), frequency_sample_rate_hz=frequency_sample_rate_hz,
@@ -138,7 +138,7 @@ def stft_from_sig(sig_wf, frequency_sample_rate_hz: float, band_order_nth: float
 # ----------------------------------------------------------------------------- Butterworth pre-filters (styx_fft.py:60-149)
 def _butter_filtfilt(sig_wf, b, a, tukey_alpha):
     """signal.filtfilt(b, a, sig * tukey(len(sig), alpha)) along the last axis (reference styx_fft.py:87-90)."""
-    rt = get_runtime()
+    rt = get_runtime(sig_wf)
     want_numpy = not rt.is_device_array(sig_wf)
     name = str(sig_wf.dtype).replace("torch.", "") if not want_numpy else np.asarray(sig_wf).dtype.name
     dt = name if name in ("float32", "float64") else "float64"

@@ -53,7 +53,7 @@ def tfr_stx_fft(sig_wf, time_sample_interval: float, scale_order_input: float = 
 
     :return: tfr_stx, psd_stx, frequency_stx, frequency_stx_fft, windows_fft
     """
-    rt = get_runtime()
+    rt = get_runtime(sig_wf)
     dt = dtype_name(dtype)
     want_numpy = not rt.is_device_array(sig_wf)
     host_sig = rt.to_numpy(sig_wf) if rt.is_device_array(sig_wf) else np.asarray(sig_wf)
@@ -116,7 +116,7 @@ def stx_complex_any_scale_pow2(band_order_nth: float, sig_wf, frequency_sample_r
 
     :return: frequency_stx_hz [B], time_stx_s [N], tfr_stx [B, N] (or [C, B, N] for 2-D input)
     """
-    rt = get_runtime()
+    rt = get_runtime(sig_wf)
     dt = dtype_name(dtype)
     want_numpy = not rt.is_device_array(sig_wf)
     sig, was_1d = _driver._as_2d(rt, sig_wf, dt)

@@ -53,7 +53,7 @@ class _Ctx:
     """Per-call context: runtime, dtype, and whether results go back to numpy."""
 
     def __init__(self, array_in, dtype):
-        self.rt = get_runtime()
+        self.rt = get_runtime(array_in)
         self.dt = dtype_name(dtype)
         self.want_numpy = not self.rt.is_device_array(array_in)
 

@@ -24,7 +24,7 @@ EXTRACTION_TYPE = ["sigmax", "sigmin", "sigabs", "log2", "log2max"]
 
 
 def _device_record(timeseries):
-    rt = get_runtime()
+    rt = get_runtime(timeseries)
     if rt.is_device_array(timeseries):
         name = str(timeseries.dtype).replace("torch.", "")
     else:

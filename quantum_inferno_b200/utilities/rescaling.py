@@ -17,7 +17,7 @@ def to_log2_with_epsilon(x: Union[np.ndarray, float, list]):
     if is_tensor or (isinstance(x, np.ndarray) and x.ndim >= 1 and x.size > 0):
         from .. import _driver
         from .._runtime import finish, get_runtime
-        rt = get_runtime()
+        rt = get_runtime(x)
         if is_tensor:
             is_complex = x.is_complex()
             dt = "float64" if x.dtype in (rt.torch.float64, rt.torch.complex128) else "float32"

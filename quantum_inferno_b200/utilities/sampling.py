@@ -50,7 +50,7 @@ def subsample(timeseries: np.ndarray, sample_rate_hz: float, subsample_factor: i
         return timeseries, sample_rate_hz
     new_sample_rate = sample_rate_hz / subsample_factor
     method = _checked_method(method)
-    rt = get_runtime()
+    rt = get_runtime(timeseries)
     dt = _dtype_of(rt, timeseries)
     want_numpy = not rt.is_device_array(timeseries)
     x = rt.asarray(timeseries, dt)
@@ -71,7 +71,7 @@ def subsample_2d(array: np.ndarray, subsample_factor: int, method: str = "nth") 
         print(f"Warning: subsample factor is less than 2, returning the original signal")
         return array
     method = _checked_method(method)
-    rt = get_runtime()
+    rt = get_runtime(array)
     dt = _dtype_of(rt, array)
     want_numpy = not rt.is_device_array(array)
     x = rt.asarray(array, dt)
@@ -102,7 +102,7 @@ def decimate_timeseries(timeseries: np.ndarray, decimation_factor: int) -> np.nd
 
     :return: decimated signal
     """
-    rt = get_runtime()
+    rt = get_runtime(timeseries)
     dt = _dtype_of(rt, timeseries)
     want_numpy = not rt.is_device_array(timeseries)
     x = rt.asarray(timeseries, dt)
@@ -118,7 +118,7 @@ def decimate_timeseries_collection(timeseries_collection: np.ndarray, decimation
 
     :return: decimated signals, [rows, ceil(n / q)]
     """
-    rt = get_runtime()
+    rt = get_runtime(timeseries_collection)
     dt = _dtype_of(rt, timeseries_collection)
     want_numpy = not rt.is_device_array(timeseries_collection)
     x = rt.asarray(timeseries_collection, dt)

@@ -78,7 +78,7 @@ class ShortTimeFFT(signal.ShortTimeFFT):
             raise NotImplementedError("k_offset != 0 is not supported")
         if padding not in padding_type:
             raise ValueError(f"Parameter {padding=} not in {tuple(padding_type)}!")
-        rt = get_runtime()
+        rt = get_runtime(x)
         want_numpy = not rt.is_device_array(x)
         if np.iscomplexobj(x) if want_numpy else x.is_complex():
             raise ValueError(f"Complex-valued `x` not allowed for {self.fft_mode=}'! "
@@ -106,7 +106,7 @@ class ShortTimeFFT(signal.ShortTimeFFT):
     def spectrogram(self, x, y=None, detr=None, *, p0=None, p1=None, k_offset=0, padding="zeros", axis=-1):
         if y is not None:
             raise NotImplementedError("cross-spectrograms (y is not None) are not supported")
-        rt = get_runtime()
+        rt = get_runtime(x)
         want_numpy = not rt.is_device_array(x)
         sx = self.stft_detrend(rt.asarray(x, self.compute_dtype), detr, p0, p1, k_offset=k_offset, padding=padding,
                                axis=axis)
@@ -115,7 +115,7 @@ class ShortTimeFFT(signal.ShortTimeFFT):
     # ---- inverse
     def istft(self, S, k0=0, k1=None, *, f_axis=-2, t_axis=-1):
         self._check_supported()
-        rt = get_runtime()
+        rt = get_runtime(S)
         want_numpy = not rt.is_device_array(S)
         nd = len(S.shape)
         if (f_axis % nd, t_axis % nd) != (nd - 2, nd - 1):
@@ -180,7 +180,7 @@ def stft_tukey(timeseries, sample_rate_hz: Union[float, int], tukey_alpha: float
         print(f"Warning: padding {padding} must be one of {padding_type}, using 'zeros' as the default value")
         padding = "zeros"
     stft_obj = get_stft_object_tukey(sample_rate_hz, tukey_alpha, segment_length, overlap_length, scaling, dtype=dtype)
-    rt = get_runtime()
+    rt = get_runtime(timeseries)
     want_numpy = not rt.is_device_array(timeseries)
     z = stft_obj.stft_detrend(rt.asarray(timeseries, stft_obj.compute_dtype), "constant", padding=padding)
     mag = finish(rt, _driver.abs_log2(z, stft_obj.compute_dtype, True, eps=0.0, square=2, rt=rt), want_numpy)

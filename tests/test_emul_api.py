@@ -90,6 +90,17 @@ def test_stx_general(golden, tag, kw):
     assert rel(win, g[f"gen_{tag}_win"]) < 1e-12
 
 
+def test_stx_general_many_bands():
+    """n_fft >= 512 on the default linear grid has more than 170 bands: the window workspace is sized by the library
+    (round-1 regression: the driver reserved 16 bytes per band, the kernel needs 24)."""
+    from oracle import qi_oracle as orc
+    x = np.random.default_rng(7).standard_normal(1024) + np.cos(2 * np.pi * 60 / FS * np.arange(1024))
+    tfr, psd, f, ffft, win = styx_stx.tfr_stx_fft(x, 1 / FS, scale_order_input=3.0, n_fft_in=1024)
+    tfr0, psd0, f0, ffft0, win0 = orc.tfr_stx_fft(x, 1 / FS, order=3.0, n_fft_in=1024)
+    assert len(f) > 170 and np.array_equal(f, f0) and np.array_equal(ffft, ffft0)
+    assert rel(tfr, tfr0) < 1e-10 and rel(psd, psd0) < 1e-10 and rel(win, win0) < 1e-12
+
+
 def test_stx_multirate():
     """Decimated voices + polyphase interpolation (float32 opt-in) against the oracle: north-star float32 tolerance
     1e-4 relative L2 per plane, and per band (no band may hide behind the strong ones)."""

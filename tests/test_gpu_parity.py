@@ -110,6 +110,20 @@ def test_stx_general_golden(torch_cuda, golden, tag, kw):
     assert rel(win, g[f"gen_{tag}_win"]) < 1e-12
 
 
+def test_stx_general_many_bands(torch_cuda):
+    """a9 at a multi-pass size: 4096-point record, default linear grid (~2000 bands), geometric and inferno grids."""
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import styx_stx
+    n = 4096
+    x = synth(n, chan=2)
+    for kw in (dict(), dict(is_geometric=True), dict(is_geometric=True, is_inferno=True)):
+        tfr, psd, f, ffft, win = styx_stx.tfr_stx_fft(x, 1 / FS, scale_order_input=3.0, n_fft_in=n, **kw)
+        tfr0, psd0, f0, ffft0, win0 = orc.tfr_stx_fft(x, 1 / FS, order=3.0, n_fft_in=n, **kw)
+        assert np.array_equal(f, f0) and np.array_equal(ffft, ffft0)
+        assert rel(tfr, tfr0) < TOL64 and rel(psd, psd0) < TOL64 and rel(win, win0) < 1e-12
+    assert len(styx_stx.tfr_stx_fft(x, 1 / FS, scale_order_input=3.0, n_fft_in=n)[2]) > 170
+
+
 def test_stft_golden(torch_cuda, golden):
     from quantum_inferno_b200 import styx_fft
     g = golden("stft")
