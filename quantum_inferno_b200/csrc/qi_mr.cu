@@ -23,6 +23,11 @@
 //                   both plane stores (256-bit) and the band / entropy sums.  Bands deeper than level 5 first get a
 //                   level-5 copy (MID mode, 1/32 of the cells).
 //   I  info rows    the level-0 rows' information plane (their power was written before S was known).
+//   R  edge rows    the reference cuts its atoms off at the record; for the record-long atoms of the lowest bands that
+//                   jump answers to every frequency of the record.  It is split off as a straight line over the atom's
+//                   support, whose contribution is a running sum + first moment of the record (mr_prefix_*_kernel and
+//                   a block scan inside E); the continuous remainder runs through T / A / E as an extra source band.
+//                   See MrDevBand in qi_mr_expand.cuh.
 //
 // Replaces (fp32 tolerance of the north star: power rel. L2 <= 1e-4) quantum_inferno/styx_cwt.py:147-198 + np.abs()**2.
 // tools/multirate_prototype.py is the numpy model the first version of this algorithm was validated with.
@@ -117,6 +122,7 @@ mr_table_kernel(const MrDevBand* __restrict__ bands, i64 n_points, int half_w_ca
             double s, c;
             sincos(b.omega * t, &s, &c);
             re = env * c; im = env * s;
+            if (b.flags & MR_FLAG_EDGE_SRC) { re -= step * b.edge_ar; im -= step * b.edge_beta * t; }
         }
         tile[p * 2] = mk<float>((float)re, (float)im);
     }
@@ -215,6 +221,50 @@ mr_level_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __r
     }
 }
 
+// ---------------------------------------------------------------- running sums of the record (edge rows, see MrDevBand)
+// blk[c][0][j + 1] = sum of x over block j, blk[c][1][j + 1] = sum of (k - (N-1)/2) x[k] over block j  (fp64)
+__global__ void __launch_bounds__(256)
+mr_prefix_sums_kernel(const float* __restrict__ x, i64 stride, i64 n_points, double* __restrict__ blk, i64 n_prefix) {
+    __shared__ double scratch[32];
+    const i64 c = blockIdx.y, j = blockIdx.x;
+    const float4* p = reinterpret_cast<const float4*>(x + c * stride + j * MR_EDGE_BLOCK) + 2 * threadIdx.x;
+    const float4 v0 = p[0], v1 = p[1];
+    const float z[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { a0 += z[r]; a1 = fmaf((float)r, z[r], a1); }
+    const double k0 = (double)(j * MR_EDGE_BLOCK + 8 * (i64)threadIdx.x) - 0.5 * (double)(n_points - 1);
+    double d0 = (double)a0, d1 = k0 * (double)a0 + (double)a1;
+    d0 = block_sum(d0, scratch);
+    d1 = block_sum(d1, scratch);
+    if (threadIdx.x == 0) {
+        double* row = blk + c * 2 * n_prefix;
+        row[j + 1] = d0;
+        row[n_prefix + j + 1] = d1;
+    }
+}
+
+// in-place inclusive scan of each of the 2 C rows (entry 0 = 0): row[j] = sum over the blocks before block j
+__global__ void __launch_bounds__(1024)
+mr_prefix_scan_kernel(double* __restrict__ blk, i64 n_prefix) {
+    __shared__ double part[1024];
+    double* row = blk + (i64)blockIdx.x * n_prefix;
+    const i64 per = (n_prefix + blockDim.x - 1) / blockDim.x;
+    const i64 i0 = (i64)threadIdx.x * per, i1 = i0 + per < n_prefix ? i0 + per : n_prefix;
+    double s = 0.0;
+    for (i64 i = i0; i < i1; ++i) s += i ? row[i] : 0.0;
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < (int)blockDim.x; o <<= 1) {           // Hillis-Steele over the per-thread sums
+        const double u = (int)threadIdx.x >= o ? part[threadIdx.x - o] : 0.0;
+        __syncthreads();
+        part[threadIdx.x] += u;
+        __syncthreads();
+    }
+    double run = part[threadIdx.x] - s;
+    for (i64 i = i0; i < i1; ++i) { run += i ? row[i] : 0.0; row[i] = run; }
+}
+
 // ---------------------------------------------------------------- host driver
 struct MrPlan {
     int cap;                         // deepest level
@@ -223,7 +273,9 @@ struct MrPlan {
     std::vector<int> expand_list;       // bands with level >= 1 (final expand launch)
     std::vector<int> deep_list;         // bands with level > MR_LMID (first brought to level MR_LMID)
     std::vector<MrLevelGeom> levels;
-    size_t off_bands, off_list, off_deep, off_tw, off_pyr, off_tables, off_w, off_mid, total;
+    int n_edge;                         // edge rows = the first n_edge bands; their source bands are B .. B + n_edge - 1
+    i64 n_prefix;
+    size_t off_bands, off_list, off_deep, off_tw, off_pyr, off_tables, off_w, off_mid, off_prefix, total;
     i64 pyr_per_chan, w_total, mid_total;
 };
 
@@ -259,8 +311,13 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl, bool all
         off += (pl.lvl_len[l] + 63) / 64 * 64;
     }
     pl.pyr_per_chan = off;
+    // edge rows: record-long atoms (they sit at the deepest level, at the low end of the table)
+    pl.n_edge = 0;
+    while (pl.n_edge < B && hb[pl.n_edge].level == pl.cap && (double)N / hb[pl.n_edge].scale < MR_EDGE_NS) ++pl.n_edge;
+    const int E = pl.n_edge;
+    pl.n_prefix = N / MR_EDGE_BLOCK + 1;
     // bands, tables, decimated outputs
-    pl.bands.resize(B);
+    pl.bands.resize(B + E);
     pl.expand_list.clear();
     pl.deep_list.clear();
     pl.levels.clear();
@@ -291,6 +348,7 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl, bool all
             if (g.wk > 3072) return QI_ERR_UNSUPPORTED;
         }
         g.TC = 1;
+        g.no_sums = 0;
         // Envelope decimation.  The band output y_b at level l is analytic with support |theta - omega_l| <= 4.8/s_l, so
         // its even samples are alias free, and times exp(-i omega_d q) they form a LOW-PASS signal at level l + 1 that
         // the real-coefficient interpolators of E handle like any other level-(l+1) band: half the inverse FFT, half the
@@ -314,31 +372,48 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl, bool all
         g.n_blocks = (g.n_out + V - 1) / V;
         pl.levels.push_back(g);
         const int lout = l + g.env;
-        for (int b = first; b < first + count; ++b) {
+        auto add_band = [&](int idx, int b, int flags) {
             MrDevBand d;
             d.omega = hb[b].omega; d.scale = hb[b].scale; d.amp = hb[b].amp; d.logF = g.logF;
+            d.edge_ar = 0.0; d.edge_beta = 0.0; d.out_row = b; d.flags = flags;
+            if (flags & MR_FLAG_EDGE_SRC) {
+                // last sample of the N-sample atom, g[N-1] = amp exp(-cc^2 / 2 s^2) exp(i omega cc), cc = (N-1)/2
+                const double cc = 0.5 * (double)(N - 1);
+                const double env = hb[b].amp * exp(-0.5 * (cc / hb[b].scale) * (cc / hb[b].scale));
+                d.edge_ar = env * cos(hb[b].omega * cc);
+                d.edge_beta = env * sin(hb[b].omega * cc) / cc;
+            }
             d.level = lout; d.conv_level = l; d.demod = g.env ? demod[b - first] : 0;
             d.table_off = toff; toff += (1ll << g.logF);
             d.w_off = 0; d.w_stride = 0; d.mid_off = 0; d.mid_stride = 0;
             if (l) {
                 d.w_stride = ((N >> lout) + 2 * MR_HALO + 63) / 64 * 64;
                 d.w_off = woff; woff += d.w_stride * C;
-                pl.expand_list.push_back(b);
+                if (!(flags & MR_FLAG_EDGE_EST)) pl.expand_list.push_back(idx);
             }
             if (lout > MR_LMID) {
                 d.mid_stride = ((N >> MR_LMID) + 2 * MR_HALO + 63) / 64 * 64;
                 d.mid_off = moff; moff += d.mid_stride * C;
-                pl.deep_list.push_back(b);
+                pl.deep_list.push_back(idx);
             }
-            pl.bands[b] = d;
+            pl.bands[idx] = d;
+        };
+        // the edge source bands first: both lists keep the bands of one launch group contiguous
+        if (l == pl.cap && E > 0) {
+            MrLevelGeom ge = g;
+            ge.band_first = B; ge.band_count = E; ge.no_sums = 1;
+            pl.levels.push_back(ge);
+            for (int b = 0; b < E; ++b) add_band(B + b, b, MR_FLAG_EDGE_SRC);
         }
+        for (int b = first; b < first + count; ++b) add_band(b, b, (l == pl.cap && b < E) ? MR_FLAG_EDGE_EST : 0);
     }
     pl.w_total = woff;
     pl.mid_total = moff;
     size_t o = 0;
-    pl.off_bands = o; o = align_up(o + sizeof(MrDevBand) * (size_t)B, 256);
-    pl.off_list = o; o = align_up(o + sizeof(int) * (size_t)(B + 1), 256);
-    pl.off_deep = o; o = align_up(o + sizeof(int) * (size_t)(B + 1), 256);
+    pl.off_bands = o; o = align_up(o + sizeof(MrDevBand) * (size_t)(B + E), 256);
+    pl.off_list = o; o = align_up(o + sizeof(int) * (size_t)(B + E + 1), 256);
+    pl.off_deep = o; o = align_up(o + sizeof(int) * (size_t)(B + E + 1), 256);
+    pl.off_prefix = o; o = align_up(o + sizeof(double) * 2 * (size_t)pl.n_prefix * (size_t)C * (E > 0 ? 1 : 0), 256);
     pl.off_tw = o; o = align_up(o + sizeof(float4) * (size_t)L2K_TW_TOTAL, 256);
     pl.off_pyr = o; o = align_up(o + sizeof(float) * (size_t)pl.pyr_per_chan * C, 256);
     pl.off_tables = o; o = align_up(o + sizeof(cplx<float>) * (size_t)toff, 256);
@@ -431,6 +506,8 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     MrDevBand* d_bands = reinterpret_cast<MrDevBand*>(base + pl.off_bands);
     int* d_list = reinterpret_cast<int*>(base + pl.off_list);
     int* d_deep = reinterpret_cast<int*>(base + pl.off_deep);
+    double* d_prefix = reinterpret_cast<double*>(base + pl.off_prefix);
+    const int E = pl.n_edge;
     cplx<float>* midbuf = reinterpret_cast<cplx<float>*>(base + pl.off_mid);
     float4* tw2k = reinterpret_cast<float4*>(base + pl.off_tw);
     float* pyr = reinterpret_cast<float*>(base + pl.off_pyr);
@@ -438,7 +515,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     cplx<float>* wbuf = reinterpret_cast<cplx<float>*>(base + pl.off_w);
     const HbTaps taps = make_taps();
 
-    stage_to_device(d_bands, pl.bands.data(), sizeof(MrDevBand) * (size_t)B, st);
+    stage_to_device(d_bands, pl.bands.data(), sizeof(MrDevBand) * (size_t)(B + E), st);
     if (!pl.expand_list.empty()) stage_to_device(d_list, pl.expand_list.data(), sizeof(int) * pl.expand_list.size(), st);
     if (!pl.deep_list.empty()) stage_to_device(d_deep, pl.deep_list.data(), sizeof(int) * pl.deep_list.size(), st);
     const bool do_front = phase != QI_MR_PHASE_EXPAND;      // tables, pyramid, level convolutions, estimates
@@ -456,8 +533,13 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
 #ifndef QI_EMUL
         cudaFuncSetAttribute(mr_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-        QI_LAUNCH(mr_table_kernel, dim3((unsigned)B), dim3(256), smem, st, (const MrDevBand*)d_bands, N, 2047, tables);
+        QI_LAUNCH(mr_table_kernel, dim3((unsigned)(B + E)), dim3(256), smem, st, (const MrDevBand*)d_bands, N, 2047, tables);
         QI_LAUNCH(mr_twiddle2k_kernel, dim3((L2K_TW_TOTAL + 255) / 256), dim3(256), 0, st, tw2k);
+        if (E > 0) {   // running sums of the record for the edge rows
+            QI_LAUNCH(mr_prefix_sums_kernel, dim3((unsigned)(pl.n_prefix - 1), (unsigned)C), dim3(256), 0, st, sig, stride, N,
+                      d_prefix, pl.n_prefix);
+            QI_LAUNCH(mr_prefix_scan_kernel, dim3((unsigned)(2 * C)), dim3(1024), 0, st, d_prefix, pl.n_prefix);
+        }
     }
     // P: pyramid
     for (int l = 1; do_front && l <= pl.cap; ++l) {
@@ -493,6 +575,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
         prof_set_category(g.level ? QI_CAT_INV_FIRST : QI_CAT_INV_MID);
         // level 0: exact band sums; levels 1..MR_LMID in the fused mode: raw sums for the power estimate
         double* sum_dst = g.level == 0 ? band_sum : ((fused && g.level + g.env <= MR_LMID) ? band_sum_est : nullptr);
+        if (g.no_sums) sum_dst = nullptr;
         if (g.logF == L2K_LOGF && g.band_count <= L2K_MAXB) {
             // 2048-point blocks: pairs of blocks per CTA, a few pairs in sequence so the twiddle copy is amortised
             const i64 pairs = (g.n_blocks + 1) / 2;
@@ -537,22 +620,29 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     ea.out_power = out_power; ea.out_complex = out_complex; ea.band_sum = band_sum;
     ea.out_info = out_info; ea.band_sum_est = band_sum_est; ea.entropy_sum = entropy_sum;
     ea.total_power = total_power; ea.eps = (float)eps;
+    ea.x = sig; ea.x_stride = stride; ea.prefix = d_prefix; ea.n_prefix = pl.n_prefix;
     // both lists are ordered deepest level first, so the bands sharing a polyphase factor 2^k are contiguous
     auto launch_groups = [&](const std::vector<int>& list, const int* d_idx, int dst_level, i64 n_dst, int mode) {
         size_t pos = 0;
         while (pos < list.size()) {
             const int lr0 = pl.bands[list[pos]].level - dst_level;
             const int k = lr0 < 3 ? lr0 : 3;
+            // edge source bands form their own group at the full rate (the running sums are added there)
+            const bool edge = mode != MR_MODE_MID && (pl.bands[list[pos]].flags & MR_FLAG_EDGE_SRC);
             size_t end = pos;
             while (end < list.size()) {
                 const int lr = pl.bands[list[end]].level - dst_level;
                 if ((lr < 3 ? lr : 3) != k) break;
+                if ((mode != MR_MODE_MID && (pl.bands[list[end]].flags & MR_FLAG_EDGE_SRC)) != edge) break;
                 ++end;
             }
             ea.band_list = d_idx + pos;
             const i64 tile = (i64)MR_SEGQ << 3;          // per CTA, for every k (see mr_expand_kernel)
             dim3 grid((unsigned)((n_dst + tile - 1) / tile), (unsigned)(end - pos), (unsigned)C);
-            if (k < 3) {
+            if (edge) {             // record-long atoms live at level >= 3: always the x8 interpolator
+                if (mode == MR_MODE_POWER) QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER, false, true>), grid, dim3(256), 0, st, ea, taps);
+                else QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER_INFO, false, true>), grid, dim3(256), 0, st, ea, taps);
+            } else if (k < 3) {
                 if (mode == MR_MODE_MID) QI_LAUNCH((mr_expand_kernel<MR_MODE_MID, true>), grid, dim3(256), 0, st, ea, taps);
                 else if (mode == MR_MODE_POWER) QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER, true>), grid, dim3(256), 0, st, ea, taps);
                 else QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER_INFO, true>), grid, dim3(256), 0, st, ea, taps);

@@ -75,6 +75,7 @@ struct MrLevelGeom {
     i64 x_stride, x_len;    // level signal: per-channel stride, stored length
     int x_halo;             // halo of the stored level signal (0 for level 0)
     int env;                // every band of this level is stored as a demodulated envelope at level + 1
+    int no_sums;            // edge source bands (indices >= n_bands): no row of their own in the sum arrays
 };
 
 // radix-8 stage on the two columns of a float4 tile; rows base + i*H live at tile[p0 + i*STRIDE]

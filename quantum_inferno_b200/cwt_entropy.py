@@ -104,9 +104,10 @@ def cwt_power_entropy(band_order_nth: float, sig_wf, frequency_sample_rate_hz: f
                  decimation pyramid + shared-memory overlap-save + half-band interpolation) or 'auto' (multirate
                  for float32 records of 2^m >= 8192 points, exact otherwise).
     truncated_bands : what the multirate method does with the lowest bands, whose atoms are cut off by the record
-                 (N/s < 10).  'multirate' keeps them on the fast path (whole-plane power L2 ~ 2e-6, but the
-                 out-of-band leakage the reference's hard truncation lets into those 2-4 bands, ~1e-3 of their
-                 peak, is not reproduced); 'exact' recomputes exactly those bands with the exact method.
+                 (N/s < 10).  'multirate' (default) keeps them on the fast path: the jump where the reference cuts
+                 the atom is carried by exact running sums of the record inside the fused expansion (qi_mr_expand.cuh),
+                 per-band power L2 against the fp64 reference 1e-5 .. 3e-5 like every other band; 'exact' recomputes
+                 those bands with the full-length FFT method instead.
     host_chunks : for records that live in host memory ([C, N] numpy / CPU tensor, ideally pinned): process the
                  channels in this many groups, copying group k+1 to the device on a second stream while group k is
                  being transformed (channels are independent, so the result is identical).

@@ -146,6 +146,11 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int d, int = 
     int src = lane + d > 31 ? lane : lane + d;
     return qi_emul::from_bits<T>(qi_emul::warp_exchange(qi_emul::to_bits(v), src));
 }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d, int = 32) {
+    int lane = qi_emul::cur->linear & 31;
+    int src = lane - d < 0 ? lane : lane - d;
+    return qi_emul::from_bits<T>(qi_emul::warp_exchange(qi_emul::to_bits(v), src));
+}
 template <class T> static inline T __ldg(const T* p) { return *p; }
 
 static inline unsigned __brev(unsigned v) {

@@ -210,23 +210,18 @@ def test_multirate_vs_oracle(torch_cuda, order, logn):
     n = 1 << logn
     x = np.stack([synth(n, chan=0), synth(n, chan=5)[::-1].copy()])
     r = cwt_entropy.cwt_power_entropy(order, x, FS, dtype="float32", method="multirate")
-    rx = cwt_entropy.cwt_power_entropy(order, x, FS, dtype="float32", method="multirate", truncated_bands="exact")
     for c in range(2):
         ref = orc.cwt_power_entropy(order, x[c], FS)
         p = r.power[c].double().cpu().numpy()
         assert l2(p, ref["power"]) < 2e-5                                         # tolerance is 1e-4
         assert abs(float(r.entropy_bits()[c]) - ref["entropy_bits"]) < 1e-4      # tolerance is 1e-3 bits
         assert abs(float(r.total_power[c]) - ref["total"]) / ref["total"] < 1e-5
+        # every band individually (tolerance 1e-4), the record-long truncated atoms of the lowest bands included
         per_band = np.linalg.norm(p - ref["power"], axis=1) / np.linalg.norm(ref["power"], axis=1)
-        n_trunc = int(np.sum(n / (orc.cycles_from_order(order) / (2 * np.pi * ref["freq"] / FS)) < 10.0))
-        assert per_band[n_trunc:].max() < TOL32_L2 and per_band.max() < 5e-3      # documented record-long-atom deviation
-        px = rx.power[c].double().cpu().numpy()
-        assert (np.linalg.norm(px - ref["power"], axis=1) / np.linalg.norm(ref["power"], axis=1)).max() < TOL32_L2
+        assert per_band.max() < 5e-5, per_band
         # per-cell information: the fp32 amplitude error (~3e-6 of the plane maximum) is amplified by 1/|cwt|
         strong = ref["power"] > 1e-2 * ref["power"].max()
-        strong[:n_trunc] = False                                                  # record-long atoms: see above
         assert np.abs(r.info[c].double().cpu().numpy() - ref["info"])[strong].max() < 1e-3
-        assert np.abs(rx.info[c].double().cpu().numpy() - ref["info"])[ref["power"] > 1e-2 * ref["power"].max()].max() < 1e-3
 
 
 def test_multirate_properties_north_star_size(torch_cuda):
@@ -249,9 +244,27 @@ def test_multirate_properties_north_star_size(torch_cuda):
     assert float((pa.double() - b.power[0].double()).norm() / b.power[0].double().norm()) < 2e-5
     assert abs(ent_a - float(b.entropy_bits()[0])) < 1e-4
     xf = np.fft.fft(x.cpu().numpy().astype(np.float64), 2 * n)
-    for band in (10, 35, 59):
+    for band in (0, 1, 10, 35, 59):                      # 0 and 1: record-long truncated atoms
         row = np.abs(orc.cwt_band(xf, 3, n, b.frequency_hz[band], FS)) ** 2
         assert l2(pa[band].double().cpu().numpy(), row) < TOL32_L2
+
+
+@pytest.mark.parametrize("order,logn,bands", [(6, 22, (0, 1, 2, 50, 101)), (12, 24, (0, 1, 4, 100, 214))])
+def test_multirate_config_sizes_vs_oracle(torch_cuda, order, logn, bands):
+    """BASELINE configs[3] (order 6, 2^22 samples, 102 bands) and the order-12 table at 2^24 samples: single bands of the
+    fused fp32 path against the fp64 oracle at full size, the record-long atoms of the lowest bands included."""
+    torch = torch_cuda
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import cwt_entropy
+    n = 1 << logn
+    xh = synth(n, chan=4)
+    r = cwt_entropy.cwt_power_entropy(order, torch.from_numpy(xh).cuda(), FS, dtype="float32")
+    assert r.power.shape[1] == len(orc.log_frequency_hz_from_fft_points(FS, n, order))
+    xf = np.fft.fft(xh, 2 * n)
+    for band in bands:
+        row = np.abs(orc.cwt_band(xf, order, n, r.frequency_hz[band], FS)) ** 2
+        assert l2(r.power[0, band].double().cpu().numpy(), row) < TOL32_L2, band
+        assert abs(float(r.band_power[0, band]) - row.sum()) / row.sum() < 1e-5
 
 
 def test_cwt_edge_cases(torch_cuda):
@@ -305,10 +318,9 @@ def test_cwt_properties_large(torch_cuda):
     # oracle on a slab: first band rows against the CPU restatement of one band
     from oracle import qi_oracle as orc
     xf = np.fft.fft(x[0].cpu().numpy(), 2 * n)
-    for b in (0, 5, 20, 47):
+    for b in (0, 1, 5, 20, 47):
         row = orc.cwt_band(xf, 3, n, r.frequency_hz[b], FS)
-        # band 0 is a record-long (truncated) atom: documented multirate deviation, see DESIGN.md section 3
-        assert l2(r.power[0, b].double().cpu().numpy(), np.abs(row) ** 2) < (5e-3 if b == 0 else TOL32_L2)
+        assert l2(r.power[0, b].double().cpu().numpy(), np.abs(row) ** 2) < TOL32_L2   # b = 0, 1: record-long atoms
 
 
 def test_stx_config3_slab(torch_cuda):
@@ -415,15 +427,14 @@ def test_multirate_vs_exact_other_orders(torch_cuda, order, logn):
     x = torch.from_numpy(np.stack([synth(n, chan=1), synth(n, chan=7)])).cuda()
     a = cwt_entropy.cwt_power_entropy(order, x, FS, dtype="float32", method="multirate")
     b = cwt_entropy.cwt_power_entropy(order, x, FS, dtype="float32", method="exact", want_info=True)
-    n_trunc = int(np.sum(n / (orc.cycles_from_order(order) / (2 * np.pi * a.frequency_hz / FS)) < 10.0))
     pa, pb = a.power.double(), b.power.double()
     per_band = ((pa - pb).norm(dim=-1) / pb.norm(dim=-1)).cpu().numpy()
-    assert per_band[:, n_trunc:].max() < TOL32_L2 and per_band.max() < 5e-3       # record-long atoms: documented deviation
+    assert per_band.max() < TOL32_L2, per_band.max()       # every band, the record-long atoms included
     assert float((pa - pb).norm() / pb.norm()) < 2e-5
     assert torch.allclose(a.entropy_bits(), b.entropy_bits(), atol=1e-4, rtol=0)
     assert torch.allclose(a.total_power, b.total_power, rtol=1e-5)
     xf = np.fft.fft(x[0].cpu().numpy().astype(np.float64), 2 * n)
-    for band in (n_trunc + 1, len(a.frequency_hz) // 2, len(a.frequency_hz) - 2):
+    for band in (0, 1, 3, len(a.frequency_hz) // 2, len(a.frequency_hz) - 2):
         row = np.abs(orc.cwt_band(xf, order, n, a.frequency_hz[band], FS)) ** 2
         assert l2(pa[0, band].cpu().numpy(), row) < TOL32_L2
 
