@@ -222,22 +222,40 @@ mr_level_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __r
 }
 
 // ---------------------------------------------------------------- running sums of the record (edge rows, see MrDevBand)
-// blk[c][0][j + 1] = sum of x over block j, blk[c][1][j + 1] = sum of (k - (N-1)/2) x[k] over block j  (fp64)
+// blk[c][0][j + 1] = sum of x over block j, blk[c][1][j + 1] = sum of (k - (N-1)/2) x[k] over block j  (fp64), and
+// grp[c][j * 256 + t] = (L0, L1) = (sum_{m < 8t} a[m], sum_{m < 8t} (m + 1) a[m]) with a[m] = x[2048 j + m]: the block-local
+// exclusive scans the edge expansion starts its 8 outputs from (see edge_add in qi_mr_expand.cuh)
 __global__ void __launch_bounds__(256)
-mr_prefix_sums_kernel(const float* __restrict__ x, i64 stride, i64 n_points, double* __restrict__ blk, i64 n_prefix) {
+mr_prefix_sums_kernel(const float* __restrict__ x, i64 stride, i64 n_points, double* __restrict__ blk, i64 n_prefix,
+                      float2* __restrict__ grp) {
     __shared__ double scratch[32];
+    __shared__ float wtot[2][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const i64 c = blockIdx.y, j = blockIdx.x;
-    const float4* p = reinterpret_cast<const float4*>(x + c * stride + j * MR_EDGE_BLOCK) + 2 * threadIdx.x;
+    const float4* p = reinterpret_cast<const float4*>(x + c * stride + j * MR_EDGE_BLOCK) + 2 * tid;
     const float4 v0 = p[0], v1 = p[1];
     const float z[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    float a0 = 0.0f, a1 = 0.0f;
+    float s0 = 0.0f, s1 = 0.0f;
+    const float fi0 = (float)(8 * tid);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) { a0 += z[r]; a1 = fmaf((float)r, z[r], a1); }
-    const double k0 = (double)(j * MR_EDGE_BLOCK + 8 * (i64)threadIdx.x) - 0.5 * (double)(n_points - 1);
-    double d0 = (double)a0, d1 = k0 * (double)a0 + (double)a1;
+    for (int r = 0; r < 8; ++r) { s0 += z[r]; s1 = fmaf(fi0 + (float)(r + 1), z[r], s1); }
+    float i0 = s0, i1 = s1;                              // inclusive scan of the thread totals over the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float u0 = __shfl_up_sync(0xffffffffu, i0, o), u1 = __shfl_up_sync(0xffffffffu, i1, o);
+        if (lane >= o) { i0 += u0; i1 += u1; }
+    }
+    if (lane == 31) { wtot[0][warp] = i0; wtot[1][warp] = i1; }
+    __syncthreads();
+    float off0 = i0 - s0, off1 = i1 - s1;
+    for (int w = 0; w < warp; ++w) { off0 += wtot[0][w]; off1 += wtot[1][w]; }
+    grp[c * (n_points >> 3) + j * (MR_EDGE_BLOCK / 8) + tid] = make_float2(off0, off1);
+    // block totals in fp64: sum a[m], sum (2048 j + m - cc) a[m] with sum (m + 1) a[m] = s1
+    const double k0 = (double)(j * MR_EDGE_BLOCK) - 1.0 - 0.5 * (double)(n_points - 1);
+    double d0 = (double)s0, d1 = k0 * (double)s0 + (double)s1;
     d0 = block_sum(d0, scratch);
     d1 = block_sum(d1, scratch);
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         double* row = blk + c * 2 * n_prefix;
         row[j + 1] = d0;
         row[n_prefix + j + 1] = d1;
@@ -275,7 +293,7 @@ struct MrPlan {
     std::vector<MrLevelGeom> levels;
     int n_edge;                         // edge rows = the first n_edge bands; their source bands are B .. B + n_edge - 1
     i64 n_prefix;
-    size_t off_bands, off_list, off_deep, off_tw, off_pyr, off_tables, off_w, off_mid, off_prefix, total;
+    size_t off_bands, off_list, off_deep, off_tw, off_pyr, off_tables, off_w, off_mid, off_prefix, off_group, total;
     i64 pyr_per_chan, w_total, mid_total;
 };
 
@@ -414,6 +432,7 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl, bool all
     pl.off_list = o; o = align_up(o + sizeof(int) * (size_t)(B + E + 1), 256);
     pl.off_deep = o; o = align_up(o + sizeof(int) * (size_t)(B + E + 1), 256);
     pl.off_prefix = o; o = align_up(o + sizeof(double) * 2 * (size_t)pl.n_prefix * (size_t)C * (E > 0 ? 1 : 0), 256);
+    pl.off_group = o; o = align_up(o + sizeof(float2) * (size_t)(N / 8) * (size_t)C * (E > 0 ? 1 : 0), 256);
     pl.off_tw = o; o = align_up(o + sizeof(float4) * (size_t)L2K_TW_TOTAL, 256);
     pl.off_pyr = o; o = align_up(o + sizeof(float) * (size_t)pl.pyr_per_chan * C, 256);
     pl.off_tables = o; o = align_up(o + sizeof(cplx<float>) * (size_t)toff, 256);
@@ -507,6 +526,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     int* d_list = reinterpret_cast<int*>(base + pl.off_list);
     int* d_deep = reinterpret_cast<int*>(base + pl.off_deep);
     double* d_prefix = reinterpret_cast<double*>(base + pl.off_prefix);
+    float2* d_group = reinterpret_cast<float2*>(base + pl.off_group);
     const int E = pl.n_edge;
     cplx<float>* midbuf = reinterpret_cast<cplx<float>*>(base + pl.off_mid);
     float4* tw2k = reinterpret_cast<float4*>(base + pl.off_tw);
@@ -537,7 +557,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
         QI_LAUNCH(mr_twiddle2k_kernel, dim3((L2K_TW_TOTAL + 255) / 256), dim3(256), 0, st, tw2k);
         if (E > 0) {   // running sums of the record for the edge rows
             QI_LAUNCH(mr_prefix_sums_kernel, dim3((unsigned)(pl.n_prefix - 1), (unsigned)C), dim3(256), 0, st, sig, stride, N,
-                      d_prefix, pl.n_prefix);
+                      d_prefix, pl.n_prefix, d_group);
             QI_LAUNCH(mr_prefix_scan_kernel, dim3((unsigned)(2 * C)), dim3(1024), 0, st, d_prefix, pl.n_prefix);
         }
     }
@@ -620,7 +640,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     ea.out_power = out_power; ea.out_complex = out_complex; ea.band_sum = band_sum;
     ea.out_info = out_info; ea.band_sum_est = band_sum_est; ea.entropy_sum = entropy_sum;
     ea.total_power = total_power; ea.eps = (float)eps;
-    ea.x = sig; ea.x_stride = stride; ea.prefix = d_prefix; ea.n_prefix = pl.n_prefix;
+    ea.x = sig; ea.x_stride = stride; ea.prefix = d_prefix; ea.n_prefix = pl.n_prefix; ea.group_prefix = d_group;
     // both lists are ordered deepest level first, so the bands sharing a polyphase factor 2^k are contiguous
     auto launch_groups = [&](const std::vector<int>& list, const int* d_idx, int dst_level, i64 n_dst, int mode) {
         size_t pos = 0;

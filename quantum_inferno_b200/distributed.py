@@ -48,15 +48,18 @@ def sum_allreduce(group=None):
     def _reduce(total):
         t = total if isinstance(total, torch.Tensor) else torch.from_numpy(total)    # shares memory with numpy
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        _reduce.calls += 1
         return total
 
+    _reduce.calls = 0            # collectives issued through this callable (bench.py reports it)
     return _reduce
 
 
 def cwt_power_entropy_band_sharded(band_order_nth, sig_wf, frequency_sample_rate_hz, rank=None, world=None,
-                                   group=None, **kwargs):
+                                   group=None, allreduce=None, **kwargs):
     """Band-sharded ``cwt_entropy.cwt_power_entropy``: every rank holds the whole record(s), computes its own band
-    range and joins the single total-power all-reduce.  Returns this rank's ``CwtEntropy`` (its bands only)."""
+    range and joins the single total-power all-reduce (``allreduce``: the callable to use, default
+    ``sum_allreduce(group)``).  Returns this rank's ``CwtEntropy`` (its bands only)."""
     import torch.distributed as dist
     from . import cwt_entropy, scales_dyadic as scales
     rank = dist.get_rank(group) if rank is None else rank
@@ -67,7 +70,8 @@ def cwt_power_entropy_band_sharded(band_order_nth, sig_wf, frequency_sample_rate
                                          band_slice=band_shard(len(freq), rank, world,
                                                                band_cost(band_order_nth, n_points, freq,
                                                                          frequency_sample_rate_hz, kwargs)),
-                                         allreduce=sum_allreduce(group), **kwargs)
+                                         allreduce=allreduce if allreduce is not None else sum_allreduce(group),
+                                         **kwargs)
 
 
 # measured cost of one band of the fused fp32 multirate path relative to a deep band (B200, 2^24 samples): the full
