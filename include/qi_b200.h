@@ -84,6 +84,11 @@ typedef struct {
 /* conv_mode */
 #define QI_CONV_LINEAR_SAME 0   /* out = fftconvolve(sig, conj(atom)[::-1], 'same')  (styx_cwt.py:195, cwt_atoms.py:435) */
 #define QI_CONV_CIRC_CORR 1     /* out = roll(ifft(fft(sig)*conj(fft(atom))), -n/2)  (cwt_atoms.py:406-421); n = 2^m */
+/* OR-ed into conv_mode: every band takes the plain route (three full-length passes).  By default the Gaussian atoms
+ * that have decayed inside the record take band-limited routes with the same result to the accuracy of the arithmetic
+ * type (csrc/qi_cwt_fast.cuh): short atoms an overlap-save convolution in shared memory, long atoms a short inverse
+ * transform of their baseband bins + Kaiser-windowed-sinc interpolation. */
+#define QI_CONV_PLAIN_ONLY 0x100
 
 size_t qi_cwt_workspace_bytes(int64_t n_channels, int64_t n_points, int n_bands, int n_table_bands,
                               int bands_per_group, int conv_mode, int dtype);

@@ -34,11 +34,14 @@ def _group_for(lib_fn_bytes, n_bands, target=WORKSPACE_TARGET_BYTES):
 
 
 def cwt_fft(sig, bands, fs, dt, conv_mode=_lib.QI_CONV_LINEAR_SAME, want_complex=True, want_power=False,
-            want_band_sum=False, rt=None, out_complex=None, out_power=None, band_sum=None):
+            want_band_sum=False, rt=None, out_complex=None, out_power=None, band_sum=None, plain_only=False):
     """Run qi_cwt_fft.  sig: device [C, N]; bands: numpy ATOM_BAND table.  Returns dict of device buffers
-    (complex [C,B,N], power [C,B,N], band_sum [C,B] float64)."""
+    (complex [C,B,N], power [C,B,N], band_sum [C,B] float64).  plain_only=True keeps every band on the three
+    full-length passes (the band-limited routes of csrc/qi_cwt_fast.cuh off: for comparisons)."""
     rt = rt or get_runtime()
     lib = rt.lib
+    if plain_only:
+        conv_mode |= _lib.QI_CONV_PLAIN_ONLY
     C, N = int(sig.shape[0]), int(sig.shape[1])
     bands = np.ascontiguousarray(bands, dtype=_lib.ATOM_BAND)
     B = len(bands)

@@ -12,6 +12,7 @@ import numpy as np
 
 QI_F32, QI_F64 = 0, 1
 QI_CONV_LINEAR_SAME, QI_CONV_CIRC_CORR = 0, 1
+QI_CONV_PLAIN_ONLY = 0x100
 SUBSAMPLE_METHOD_CODE = {"nth": 0, "average": 1, "median": 2, "max": 3, "min": 4}
 QI_ABI_VERSION = 3
 QI_N_CATEGORIES = 7

@@ -28,6 +28,8 @@ struct DevBand {
     long long table_off;   // element offset into the table buffer, -1 = analytic
     // time-domain atom (table bands)
     double omega, p_re, p_im, amp;
+    // decimated route (qi_cwt_fast.cuh): nearest bin of the band centre, bins kept either side of it
+    long long kc, dec_kmax;
 };
 
 // ---------------------------------------------------------------- on-the-fly Gabor response
@@ -134,9 +136,13 @@ __global__ void atoms_time_kernel(const DevBand* bands, int n_bands, i64 n_point
     out[(i64)b * n_points + i] = mk<T>((T)re, (T)im);
 }
 
+}  // namespace qi
+#include "qi_cwt_fast.cuh"
+namespace qi {
+
 struct CwtLayout {
     int logL; i64 L;
-    size_t off_bands, off_tabidx, off_spec, off_tables, off_work, total;
+    size_t off_bands, off_tabidx, off_spec, off_tables, off_work, off_bandsF, off_ids, off_coef, off_tabF, total;
     int group;
 };
 
@@ -155,6 +161,11 @@ static CwtLayout cwt_layout(i64 C, i64 N, int B, int n_tab, int group, int conv_
     lo.off_spec = o; o = align_up(o + sizeof(cplx<T>) * (size_t)C * lo.L, 256);
     lo.off_tables = o; o = align_up(o + sizeof(cplx<T>) * (size_t)n_tab * lo.L, 256);
     lo.off_work = o; o = align_up(o + sizeof(cplx<T>) * (size_t)group * C * lo.L, 256);
+    // band-limited routes (qi_cwt_fast.cuh): F-grid descriptors, id lists, interpolator and response tables
+    lo.off_bandsF = o; o = align_up(o + sizeof(DevBand) * (size_t)B, 256);
+    lo.off_ids = o; o = align_up(o + sizeof(int) * 2 * (size_t)B, 256);
+    lo.off_coef = o; o = align_up(o + sizeof(T) * CwtFastCfg<T>::TAPS * (size_t)(CWTF_MAX_LOGD + 1) * (1u << CWTF_MAX_LOGD), 256);
+    lo.off_tabF = o; o = align_up(o + sizeof(cplx<T>) * ((size_t)B << CWTF_OS_LOGF), 256);
     lo.total = o;
     return lo;
 }
@@ -167,6 +178,7 @@ static void fill_dev_bands(const QiAtomBand* hb, int B, int logL, int half_shift
     for (int b = 0; b < B; ++b) {
         DevBand d;
         d.omega = hb[b].omega; d.p_re = hb[b].p_re; d.p_im = hb[b].p_im; d.amp = hb[b].amp;
+        d.kc = 0; d.dec_kmax = 0;
         if (hb[b].analytic) {
             // centre frequency folded into [0, 2*pi): a centre beyond the sampling rate (orders below the 0.75
             // floor produce such bands upstream) aliases onto omega - 2*pi*m, with a sign (-1)^m from the
@@ -181,6 +193,7 @@ static void fill_dev_bands(const QiAtomBand* hb, int B, int logL, int half_shift
             d.kappa_int = (long long)ki;
             d.kappa_frac = kappa - ki;
             d.table_off = -1;
+            d.kc = (long long)llround(kappa) & ((1ll << logL) - 1);
         } else {
             d.gain = 1.0 / L; d.g = 0; d.kappa_frac = 0; d.kappa_int = 0;
             d.table_off = (long long)tab.size() << logL;
@@ -193,7 +206,7 @@ static void fill_dev_bands(const QiAtomBand* hb, int B, int logL, int half_shift
 template <typename T>
 static int cwt_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiAtomBand* hb, int B, double fs,
                         int conv_mode, void* out_c, void* out_p, double* band_sum, void* ws, size_t ws_bytes,
-                        int group, cudaStream_t st) {
+                        int group, cudaStream_t st, bool fast) {
     int n_tab = 0;
     for (int b = 0; b < B; ++b) {
         if (!hb[b].analytic) ++n_tab;
@@ -211,7 +224,13 @@ static int cwt_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiAtomB
     cplx<T>* work = reinterpret_cast<cplx<T>*>(base + lo.off_work);
 
     std::vector<DevBand> db; std::vector<int> tab;
-    fill_dev_bands(hb, B, lo.logL, (conv_mode == QI_CONV_LINEAR_SAME && (N % 2 == 0)) ? 1 : 0, db, tab);
+    const int half_shift = (conv_mode == QI_CONV_LINEAR_SAME && (N % 2 == 0)) ? 1 : 0;
+    fill_dev_bands(hb, B, lo.logL, half_shift, db, tab);
+    CwtFastPlan fp;
+    cwt_fast_plan<T>(hb, B, N, lo.logL, conv_mode, fast, fp);
+    for (int b = 0; b < B; ++b)
+        if (fp.route[b] == CWT_ROUTE_DEC)
+            db[b].dec_kmax = (long long)ceil(CwtFastCfg<T>::U_CUT / db[b].g) + 1;
     stage_to_device(d_bands, db.data(), sizeof(DevBand) * (size_t)B, st);
     if (n_tab) stage_to_device(d_tab, tab.data(), sizeof(int) * (size_t)n_tab, st);
 
@@ -219,24 +238,53 @@ static int cwt_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiAtomB
     geo.n_points = N; geo.n_channels = C; geo.n_bands = B; geo.logL = lo.logL;
     geo.conv_mode = conv_mode; geo.fs = fs;
     geo.centre_idx = (N - 1) / 2;
-    geo.half_shift = (conv_mode == QI_CONV_LINEAR_SAME && (N % 2 == 0)) ? 1 : 0;
+    geo.half_shift = half_shift;
     geo.d_min = -geo.centre_idx;
     geo.d_max = N - 1 - geo.centre_idx;
 
     const FftPlan plan = make_plan(lo.logL, (int)sizeof(cplx<T>));
     const int np = plan.npass;
     const T one = (T)1;
+    if (band_sum) cudaMemsetAsync(band_sum, 0, sizeof(double) * (size_t)C * B, st);
 
-    // record spectra
-    prof_set_category(QI_CAT_FFT_FWD);
-    for (int p = 0; p < np; ++p) {
-        DstComplex<T> d{spec, lo.L, one};
-        if (p == 0) {
-            SrcRealPad<T> s{static_cast<const T*>(sig), stride, N};
-            launch_pass<T, FFT_FWD>(plan, p, C, s, d, 0, st);
-        } else {
-            SrcComplex<T> s{spec, lo.L};
-            launch_pass<T, FFT_FWD>(plan, p, C, s, d, 0, st);
+    // ---- (S) short atoms: overlap-save in shared memory, straight from the record
+    if (!fp.os_ids.empty()) {
+        const int n_os = (int)fp.os_ids.size(), logF = CWTF_OS_LOGF;
+        DevBand* d_bandsF = reinterpret_cast<DevBand*>(base + lo.off_bandsF);
+        int* d_os = reinterpret_cast<int*>(base + lo.off_ids);
+        cplx<T>* tabF = reinterpret_cast<cplx<T>*>(base + lo.off_tabF);
+        std::vector<QiAtomBand> sel(n_os);
+        for (int i = 0; i < n_os; ++i) sel[i] = hb[fp.os_ids[i]];
+        std::vector<DevBand> dbF; std::vector<int> tabF_unused;
+        fill_dev_bands(sel.data(), n_os, logF, half_shift, dbF, tabF_unused);
+        stage_to_device(d_bandsF, dbF.data(), sizeof(DevBand) * (size_t)n_os, st);
+        stage_to_device(d_os, fp.os_ids.data(), sizeof(int) * (size_t)n_os, st);
+        prof_set_category(QI_CAT_FFT_FWD);
+        QI_LAUNCH((cwtf_os_table_kernel<T>), dim3((unsigned)((1 << logF) / 256), (unsigned)n_os), dim3(256), 0, st,
+                  (const DevBand*)d_bandsF, logF, half_shift, tabF);
+        const int V = (1 << logF) - 2 * fp.os_half;
+        const size_t smem = 3 * sizeof(cplx<T>) * ((size_t)1 << logF) + 256;
+#ifndef QI_EMUL
+        cudaFuncSetAttribute(cwtf_os_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+        prof_set_category(QI_CAT_INV_LAST);
+        QI_LAUNCH((cwtf_os_kernel<T>), dim3((unsigned)((N + V - 1) / V), (unsigned)C), dim3(512), smem, st,
+                  static_cast<const T*>(sig), stride, geo, (const int*)d_os, n_os, logF, fp.os_half, (const cplx<T>*)tabF,
+                  static_cast<cplx<T>*>(out_c), static_cast<T*>(out_p), band_sum);
+    }
+
+    // record spectra (the overlap-save route does not need them)
+    if (fp.n_plain > 0 || !fp.dec_ids.empty()) {
+        prof_set_category(QI_CAT_FFT_FWD);
+        for (int p = 0; p < np; ++p) {
+            DstComplex<T> d{spec, lo.L, one};
+            if (p == 0) {
+                SrcRealPad<T> s{static_cast<const T*>(sig), stride, N};
+                launch_pass<T, FFT_FWD>(plan, p, C, s, d, 0, st);
+            } else {
+                SrcComplex<T> s{spec, lo.L};
+                launch_pass<T, FFT_FWD>(plan, p, C, s, d, 0, st);
+            }
         }
     }
     // atom tables (one forward FFT per table band, shared by all channels)
@@ -252,10 +300,57 @@ static int cwt_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiAtomB
             }
         }
     }
-    if (band_sum) cudaMemsetAsync(band_sum, 0, sizeof(double) * (size_t)C * B, st);
 
-    for (int band0 = 0; band0 < B; band0 += lo.group) {
-        const int g = (B - band0 < lo.group) ? (B - band0) : lo.group;
+    // ---- (D) long decayed atoms: baseband bins -> short inverse transform -> Kaiser-sinc interpolation
+    if (!fp.dec_ids.empty()) {
+        typedef CwtFastCfg<T> Cfg;
+        int* d_dec = reinterpret_cast<int*>(base + lo.off_ids) + B;
+        T* coef = reinterpret_cast<T*>(base + lo.off_coef);
+        stage_to_device(d_dec, fp.dec_ids.data(), sizeof(int) * fp.dec_ids.size(), st);
+        unsigned need_mask = 0;
+        for (int b : fp.dec_ids) need_mask |= 1u << (lo.logL - fp.logK[b]);
+        prof_set_category(QI_CAT_OTHER);
+        QI_LAUNCH((cwtf_coef_kernel<T>), dim3((unsigned)((Cfg::TAPS << CWTF_MAX_LOGD) / 256 + 1), (unsigned)(CWTF_MAX_LOGD + 1)),
+                  dim3(256), 0, st, coef, need_mask, 1.0 / cwtf_bessel_i0(Cfg::BETA));
+        const size_t work_elems = (size_t)lo.group * C * lo.L;
+        size_t pos = 0;
+        while (pos < fp.dec_ids.size()) {
+            const int lk = fp.logK[fp.dec_ids[pos]];
+            size_t end = pos;
+            while (end < fp.dec_ids.size() && fp.logK[fp.dec_ids[end]] == lk) ++end;
+            const int logD = lo.logL - lk;
+            const T* cf = coef + (size_t)logD * Cfg::TAPS * (1u << CWTF_MAX_LOGD);
+            const FftPlan pk = make_plan(lk, (int)sizeof(cplx<T>));
+            const i64 K = 1ll << lk;
+            for (size_t sub = pos; sub < end;) {
+                i64 gs = (i64)(end - sub);
+                while (gs * C > 65535 || (size_t)gs * C * K > work_elems) --gs;
+                if (gs < 1) return QI_ERR_WORKSPACE;
+                const i64 nb = gs * C;
+                SrcCwtDec<T> s1{spec, d_bands, d_dec + sub, (int)C, lo.logL, lk, half_shift};
+                for (int p = pk.npass - 1; p >= 0; --p) {
+                    const bool first = (p == pk.npass - 1);
+                    SrcComplex<T> s2{work, K};
+                    DstComplex<T> dw{work, K, one};
+                    prof_set_category(first ? QI_CAT_INV_FIRST : QI_CAT_INV_MID);
+                    if (first) launch_pass<T, FFT_INV>(pk, p, nb, s1, dw, 0, st);
+                    else launch_pass<T, FFT_INV>(pk, p, nb, s2, dw, 0, st);
+                }
+                prof_set_category(QI_CAT_INV_LAST);
+                dim3 grid((unsigned)((N + CWTF_SPAN * CWTF_TILE - 1) / (CWTF_SPAN * CWTF_TILE)), (unsigned)gs, (unsigned)C);
+                QI_LAUNCH((cwtf_interp_kernel<T>), grid, dim3(256), 0, st, (const cplx<T>*)work, (const int*)(d_dec + sub),
+                          (const DevBand*)d_bands, geo, logD, cf, static_cast<cplx<T>*>(out_c), static_cast<T*>(out_p), band_sum);
+                sub += (size_t)gs;
+            }
+            pos = end;
+        }
+    }
+
+    // ---- plain route: maximal runs of consecutive bands that took no other route
+    for (int band0 = 0; band0 < B;) {
+        if (fp.route[band0] != CWT_ROUTE_PLAIN) { ++band0; continue; }
+        int g = 1;
+        while (band0 + g < B && g < lo.group && fp.route[band0 + g] == CWT_ROUTE_PLAIN) ++g;
         const i64 nb = (i64)g * C;
         for (int p = np - 1; p >= 0; --p) {
             const bool first = (p == np - 1), last = (p == 0);
@@ -269,6 +364,7 @@ static int cwt_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiAtomB
             else if (last) launch_pass<T, FFT_INV>(plan, p, nb, s2, d2, 256, st);
             else launch_pass<T, FFT_INV>(plan, p, nb, s2, d1, 0, st);
         }
+        band0 += g;
     }
     prof_set_category(QI_CAT_OTHER);
     return check_cuda("qi_cwt_fft");
@@ -295,6 +391,7 @@ extern "C" {
 
 size_t qi_cwt_workspace_bytes(int64_t C, int64_t N, int B, int n_tab, int group, int conv_mode, int dtype) {
     if (C <= 0 || N <= 0 || B <= 0) return 0;
+    conv_mode &= ~QI_CONV_PLAIN_ONLY;
     if (dtype == QI_F32) return qi::cwt_layout<float>(C, N, B, n_tab, group, conv_mode).total;
     return qi::cwt_layout<double>(C, N, B, n_tab, group, conv_mode).total;
 }
@@ -304,14 +401,16 @@ int qi_cwt_fft(const void* sig, int64_t C, int64_t N, int64_t stride, const QiAt
                int group, void* stream) {
     if (!sig || !bands || !ws || C <= 0 || N <= 0 || B <= 0 || stride < N) return QI_ERR_ARG;
     if (N > (1ll << 29)) return QI_ERR_UNSUPPORTED;
+    const bool fast = !(conv_mode & QI_CONV_PLAIN_ONLY);
+    conv_mode &= ~QI_CONV_PLAIN_ONLY;
     if (conv_mode != QI_CONV_LINEAR_SAME && conv_mode != QI_CONV_CIRC_CORR) return QI_ERR_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == QI_F32)
         return qi::cwt_fft_impl<float>(sig, C, N, stride, bands, B, fs, conv_mode, out_cwt, out_power, band_sum, ws,
-                                       ws_bytes, group, st);
+                                       ws_bytes, group, st, fast);
     if (dtype == QI_F64)
         return qi::cwt_fft_impl<double>(sig, C, N, stride, bands, B, fs, conv_mode, out_cwt, out_power, band_sum, ws,
-                                        ws_bytes, group, st);
+                                        ws_bytes, group, st, fast);
     return QI_ERR_ARG;
 }
 

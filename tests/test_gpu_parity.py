@@ -267,6 +267,35 @@ def test_multirate_config_sizes_vs_oracle(torch_cuda, order, logn, bands):
         assert abs(float(r.band_power[0, band]) - row.sum()) / row.sum() < TOL32_L2
 
 
+@pytest.mark.parametrize("dtype,tol", [("float64", TOL64), ("float32", 2e-5)])
+def test_cwt_band_limited_routes_large(torch_cuda, dtype, tol):
+    """The band-limited routes of the exact path (csrc/qi_cwt_fast.cuh: overlap-save for short atoms, decimated
+    transform + Kaiser interpolation for long ones) at 2^20 samples: against the plain three-pass route on every band
+    (complex TFR, power, band sums) and against the oracle on single bands of each route."""
+    torch = torch_cuda
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import _driver, _plan, _runtime, scales_dyadic as scales
+    rt = _runtime.get_runtime()
+    n = 1 << 20
+    xh = np.stack([synth(n, chan=2), synth(n, chan=9)])
+    x = rt.asarray(xh, dtype)
+    freq = scales.log_frequency_hz_from_fft_points(FS, n, 3)
+    bands, scale, _, _ = _plan.gabor_bands(3, n, freq, FS, "norm", dtype)
+    fast = _driver.cwt_fft(x, bands, FS, dtype, want_complex=True, want_power=True, want_band_sum=True, rt=rt)
+    plain = _driver.cwt_fft(x, bands, FS, dtype, want_complex=True, want_power=True, want_band_sum=True, rt=rt, plain_only=True)
+    cf, cp = torch.view_as_real(fast["complex"]).double(), torch.view_as_real(plain["complex"]).double()
+    per_band = ((cf - cp).abs().amax(dim=(2, 3)) / cp.abs().amax(dim=(2, 3))).cpu().numpy()
+    assert per_band.max() < tol, per_band
+    pf, pp = fast["power"].double(), plain["power"].double()
+    assert float(((pf - pp).abs().amax(dim=2) / pp.amax(dim=2)).max()) < 2 * tol
+    assert torch.allclose(fast["band_sum"], plain["band_sum"], rtol=2 * tol)
+    xf = np.fft.fft(xh[1], 2 * n)
+    for b in (0, 6, 20, 33, 40, 47):                       # table, decimated (x3), overlap-save (x2)
+        row = orc.cwt_band(xf, 3, n, freq[b], FS)
+        got = fast["complex"][1, b].cpu().numpy()
+        assert np.max(np.abs(got - row)) / np.max(np.abs(row)) < tol, b
+
+
 def test_cwt_edge_cases(torch_cuda):
     from oracle import qi_oracle as orc
     from quantum_inferno_b200 import styx_cwt
