@@ -116,6 +116,13 @@ def synth_batch_device(rt, n, chans, dtype="float32"):
     return out
 
 
+def synth_batch_torch(torch, n, chans, dev, dtype="float32"):
+    """Same records for the scripts under tools/ (which pass the torch module and a device)."""
+    from quantum_inferno_b200 import _runtime
+    with torch.cuda.device(dev):
+        return synth_batch_device(_runtime.get_runtime(), n, chans, dtype)
+
+
 # ----------------------------------------------------------------------------- CPU port (oracle) timing
 def cpu_baseline_single(log2n=None):
     """~10-30 s of single-threaded CPU work on a bounded sample of the same workload."""

@@ -130,10 +130,37 @@ def gabor_atom_centered(order, n_points, f_hz, fs, dictionary_type="norm"):
     return amp * gabor, scale, omega, amp
 
 
-def cwt_band(sig_fft_2n, order, n_points, f_hz, fs, dictionary_type="norm"):
+def gabor_atom_centered_arbiter(order, n_points, f_hz, fs, dictionary_type="norm"):
+    """ARBITER, not a restatement: the same atom as gabor_atom_centered with the time axis and the carrier phase carried
+    in 80-bit long double (the axis fs * (k / fs - t[-1] / 2) is exactly k - (n_points - 1) / 2 in exact arithmetic).
+    The reference's float64 axis and its float64 product omega * x carry a phase error of about eps64 * omega * N / 2
+    (1.4e-10 rad for the top band of a 2^20-sample record, 2.3e-9 at 2^24), which is above the 1e-10 fp64 tolerance;
+    tests on long records bound the distance to gabor_atom_centered by that figure and the distance to this arbiter by
+    the tolerance itself (the same device as the long-double arbiter of the IIR filters)."""
+    ld = np.longdouble
+    x = np.arange(n_points, dtype=ld) - ld(n_points - 1) / ld(2)
+    scale, omega = scale_from_frequency_hz(order, f_hz, fs)
+    two_pi = ld(2) * np.arctan2(ld(0), ld(-1))
+    phase = ld(omega) * x
+    phase -= two_pi * np.rint(phase / two_pi)
+    gabor = np.exp(-0.5 * (x / ld(scale)) ** 2) * (np.cos(phase) + 1j * np.sin(phase))
+    a_norm, a_spect = wavelet_amplitude(scale)
+    amp = a_spect if dictionary_type == "spect" else (1.0 if dictionary_type == "unit" else a_norm)
+    return (amp * gabor).astype(np.complex128), scale, omega, amp
+
+
+def reference_axis_phase_noise(order, n_points, f_hz, fs):
+    """Bound on the reference's own carrier-phase rounding for one band (see gabor_atom_centered_arbiter):
+    the float64 axis (three roundings at magnitude N/2 samples) times omega, plus the rounding of omega * x."""
+    _, omega = scale_from_frequency_hz(order, f_hz, fs)
+    return 4.0 * np.finfo(np.float64).eps * float(omega) * n_points / 2.0
+
+
+def cwt_band(sig_fft_2n, order, n_points, f_hz, fs, dictionary_type="norm", arbiter=False):
     """One row of styx_cwt.py:195-196: fftconvolve(sig, conj(fliplr(atom)), 'same'), i.e.
     ifft(fft(x,2N)*fft(h,2N))[(N-1)//2 : (N-1)//2+N] (scipy _freq_domain_conv + _centered)."""
-    atom, _, _, _ = gabor_atom_centered(order, n_points, f_hz, fs, dictionary_type)
+    make = gabor_atom_centered_arbiter if arbiter else gabor_atom_centered
+    atom, _, _, _ = make(order, n_points, f_hz, fs, dictionary_type)
     h = np.conj(atom[::-1])
     full = np.fft.ifft(sig_fft_2n * np.fft.fft(h, 2 * n_points))
     s = (n_points - 1) // 2

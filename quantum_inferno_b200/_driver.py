@@ -188,7 +188,8 @@ def shannon(power, dt, mode, norm, deg_free, eps=EPS64, planes=("info", "bits", 
     rt = rt or get_runtime()
     lib = rt.lib
     M, F, T = (int(s) for s in power.shape)
-    out = {k: (rt.empty((M, F, T), dt) if k in planes else None) for k in ("pdf", "info", "bits", "isnr", "esnr")}
+    out = {k: (rt.empty((M, F, T), dt) if (k in planes and not (k == "info" and out_info is not None)) else None)
+           for k in ("pdf", "info", "bits", "isnr", "esnr")}
     if out_info is not None:
         out["info"] = out_info
     es = rt.empty((M, F), "float64") if entropy_sum else None

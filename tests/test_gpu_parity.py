@@ -293,7 +293,13 @@ def test_cwt_band_limited_routes_large(torch_cuda, dtype, tol):
     for b in (0, 6, 20, 33, 40, 47):                       # table, decimated (x3), overlap-save (x2)
         row = orc.cwt_band(xf, 3, n, freq[b], FS)
         got = fast["complex"][1, b].cpu().numpy()
-        assert np.max(np.abs(got - row)) / np.max(np.abs(row)) < tol, b
+        # the reference's float64 time axis carries eps64 * omega * N / 2 of carrier-phase noise (4.5e-10 on the top band
+        # here): the distance to the restatement is bounded by tolerance + that, the distance to the long-double-axis
+        # arbiter of the same atom by the tolerance itself
+        noise = orc.reference_axis_phase_noise(3, n, freq[b], FS)
+        assert np.max(np.abs(got - row)) / np.max(np.abs(row)) < tol + noise, b
+        arb = orc.cwt_band(xf, 3, n, freq[b], FS, arbiter=True)
+        assert np.max(np.abs(got - arb)) / np.max(np.abs(arb)) < tol, b
 
 
 def test_cwt_edge_cases(torch_cuda):
