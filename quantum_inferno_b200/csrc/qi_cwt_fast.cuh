@@ -173,19 +173,19 @@ cwtf_os_kernel(const T* __restrict__ sig, i64 stride, CwtGeom geo, const int* __
     const i64 chan = blockIdx.y, N = geo.n_points;
     const i64 n0 = (i64)blockIdx.x * V;
     const T* xs = sig + chan * stride;
-    fill_twiddles<T>(tw, logF);
+    fill_stage_twiddles<T>(tw, logF);
     for (int p = threadIdx.x; p < F; p += blockDim.x) {
         const i64 k = n0 - half + p;
         tile_x[p] = mk<T>((k >= 0 && k < N) ? xs[k] : (T)0, (T)0);
     }
     __syncthreads();
-    tile_fft<T, FFT_FWD>(tile_x, tw, logF, 1, 1);
+    tile_fft<T, FFT_FWD, true>(tile_x, tw, logF, 1, 1);
     for (int i = 0; i < n_os; ++i) {
         const int band = ids[i];
         const cplx<T>* H = tabF + ((size_t)i << logF);
         for (int r = threadIdx.x; r < F; r += blockDim.x) tile_y[r] = tile_x[r] * H[r];
         __syncthreads();
-        tile_fft<T, FFT_INV>(tile_y, tw, logF, 1, 1);
+        tile_fft<T, FFT_INV, true>(tile_y, tw, logF, 1, 1);
         const i64 row = (chan * geo.n_bands + band) * N;
         double acc = 0.0;
         for (int v = threadIdx.x; v < V; v += blockDim.x) {

@@ -92,7 +92,14 @@ QI_HD int brev2(int f) { return ((f & 1) << 1) | ((f >> 1) & 1); }
 // ---------------------------------------------------------------- one radix-2^STEP stage on a tile
 // tile[r*TP + c], R = 2^logR rows, TC columns; tw[m] = exp(-2*pi*i*m/R), m in [0,R).
 // Block size 2^logB, sub-stride h = 2^(logB-STEP).
-template <typename T, int DIR, int STEP>
+// STW = true: `tw` is the per-stage table of fill_stage_twiddles (single-column tiles, lanes along j: the strided
+// tw[(j * f) << twshift] of the plain table is an 8-way bank conflict per quarter warp there).
+QI_HD int stage_tw_off(int logR, int logB) {     // radix-8 stages sit at logB = logR - 3k
+    int off = 0;
+    for (int lb = logR; lb > logB; lb -= 3) off += 7 << (lb - 3);
+    return off;
+}
+template <typename T, int DIR, int STEP, bool STW = false>
 QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int TC, int TP) {
     constexpr int Q = 1 << STEP;
     const int logH = logB - STEP;
@@ -100,6 +107,7 @@ QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int
     const int ntask = (1 << (logR - STEP)) * TC;
     const int logTC = 31 - __clz(TC);
     const int twshift = logR - logB;
+    const cplx<T>* tws = STW ? tw + stage_tw_off(logR, logB) - h : tw;      // slot s of block offset j: tws[s * h + j]
     for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
         const int c = task & (TC - 1);              // TC is a power of two
         const int u = task >> logTC;
@@ -116,7 +124,8 @@ QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int
             for (int s = 0; s < Q; ++s) {
                 const int f = STEP == 3 ? brev3(s) : (STEP == 2 ? brev2(s) : s);
                 cplx<T> v = a[s];
-                if (f != 0) v = v * tw[(j * f) << twshift];
+                if (STW) { if (s != 0 && STEP == 3 && logH > 0) v = v * tws[s * h + j]; }
+                else if (f != 0) v = v * tw[(j * f) << twshift];
                 p[s * stride] = v;
             }
         } else {
@@ -124,7 +133,8 @@ QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int
             for (int s = 0; s < Q; ++s) {
                 const int f = STEP == 3 ? brev3(s) : (STEP == 2 ? brev2(s) : s);
                 cplx<T> v = p[s * stride];
-                if (f != 0) v = mul_conj(v, tw[(j * f) << twshift]);
+                if (STW) { if (s != 0 && STEP == 3 && logH > 0) v = mul_conj(v, tws[s * h + j]); }
+                else if (f != 0) v = mul_conj(v, tw[(j * f) << twshift]);
                 a[s] = v;
             }
             if (STEP == 3) dit8<T, DIR>(a); else if (STEP == 2) dit4<T, DIR>(a); else dit2<T, DIR>(a);
@@ -135,27 +145,41 @@ QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int
 }
 
 // Full tile FFT.  All threads of the CTA must call it; it ends with a __syncthreads().
-template <typename T, int DIR>
+template <typename T, int DIR, bool STW = false>
 QI_DEV void tile_fft(cplx<T>* tile, const cplx<T>* tw, int logR, int TC, int TP) {
     if (logR == 0) { __syncthreads(); return; }
     const int rem = logR % 3;            // the odd-sized stage sits at the small-block end
     if (DIR == FFT_FWD) {
         int logB = logR;
         while (logB >= 3 && logB - 3 >= rem) {
-            tile_stage<T, DIR, 3>(tile, tw, logR, logB, TC, TP);
+            tile_stage<T, DIR, 3, STW>(tile, tw, logR, logB, TC, TP);
             __syncthreads();
             logB -= 3;
         }
-        if (logB == 2) { tile_stage<T, DIR, 2>(tile, tw, logR, 2, TC, TP); __syncthreads(); }
-        else if (logB == 1) { tile_stage<T, DIR, 1>(tile, tw, logR, 1, TC, TP); __syncthreads(); }
+        if (logB == 2) { tile_stage<T, DIR, 2, STW>(tile, tw, logR, 2, TC, TP); __syncthreads(); }
+        else if (logB == 1) { tile_stage<T, DIR, 1, STW>(tile, tw, logR, 1, TC, TP); __syncthreads(); }
     } else {
         int logB = rem;
-        if (rem == 2) { tile_stage<T, DIR, 2>(tile, tw, logR, 2, TC, TP); __syncthreads(); }
-        else if (rem == 1) { tile_stage<T, DIR, 1>(tile, tw, logR, 1, TC, TP); __syncthreads(); }
+        if (rem == 2) { tile_stage<T, DIR, 2, STW>(tile, tw, logR, 2, TC, TP); __syncthreads(); }
+        else if (rem == 1) { tile_stage<T, DIR, 1, STW>(tile, tw, logR, 1, TC, TP); __syncthreads(); }
         while (logB < logR) {
             logB += 3;
-            tile_stage<T, DIR, 3>(tile, tw, logR, logB, TC, TP);
+            tile_stage<T, DIR, 3, STW>(tile, tw, logR, logB, TC, TP);
             __syncthreads();
+        }
+    }
+}
+
+// per-stage twiddles of the radix-8 stages, contiguous in the block offset j: entry stage_tw_off(logR, logB) + (s - 1) h + j
+// = exp(-2 pi i j brev3(s) / 2^logB), h = 2^(logB - 3).  Fewer than 2^logR entries in total.  (The radix-4 / radix-2
+// stage of lengths that are not a power of 8 sits at the small-block end, where every twiddle is 1.)
+template <typename T> QI_DEV void fill_stage_twiddles(cplx<T>* tw, int logR) {
+    for (int logB = logR; logB >= 3 && logB - 3 >= logR % 3; logB -= 3) {
+        const int logH = logB - 3, h = 1 << logH;
+        cplx<T>* dst = tw + stage_tw_off(logR, logB);
+        for (int e = threadIdx.x; e < 7 * h; e += blockDim.x) {
+            const int s = (e >> logH) + 1, j = e & (h - 1);
+            dst[e] = conj(unit_root<T>((unsigned long long)(j * brev3(s)), logB));
         }
     }
 }
@@ -164,6 +188,17 @@ QI_DEV void tile_fft(cplx<T>* tile, const cplx<T>* tw, int logR, int TC, int TP)
 template <typename T> QI_DEV void fill_twiddles(cplx<T>* tw, int logR) {
     const int R = 1 << logR;
     for (int m = threadIdx.x; m < R; m += blockDim.x) tw[m] = conj(unit_root<T>((unsigned long long)m, logR));
+}
+// The same table from 2 sqrt(R) exact roots and one complex product per entry (a sincospi per entry was a tenth of a
+// pass's instructions in float64).  `scratch` holds 2^lo + 2^(logR-lo) entries and must not overlap tw; two barriers inside.
+template <typename T> QI_DEV void fill_twiddles_fast(cplx<T>* tw, int logR, cplx<T>* scratch) {
+    if (logR < 6) { fill_twiddles<T>(tw, logR); return; }
+    const int lo = logR >> 1, nlo = 1 << lo, nhi = 1 << (logR - lo);
+    for (int j = threadIdx.x; j < nlo + nhi; j += blockDim.x)
+        scratch[j] = conj(unit_root<T>(j < nlo ? (unsigned long long)j : ((unsigned long long)(j - nlo) << lo), logR));
+    __syncthreads();
+    for (int m = threadIdx.x; m < (1 << logR); m += blockDim.x) tw[m] = scratch[m & (nlo - 1)] * scratch[nlo + (m >> lo)];
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------- pass geometry
@@ -199,9 +234,30 @@ fft_pass_kernel(PassGeom g, Src src, Dst dst) {
     const int logTC = 31 - __clz(TC);
     const int twlog = g.logR + g.logS;           // modulus of the inter-pass twiddle
 
-    fill_twiddles<T>(tw, g.logR);
+    fill_twiddles_fast<T>(tw, g.logR, tile);
 
     const bool row_major = (g.logS == 0);        // rows contiguous in memory -> lanes along r
+    // Cooley-Tukey twiddle between the passes, W^(inner * k) with W = exp(2 pi i / 2^twlog), k = brev(r).  A thread keeps
+    // its column (256 is a multiple of TC) and visits the rows r0 + i * RPI, so k = k_hi(r0) + k_lo(i) and the twiddle
+    // factors into a per-thread constant W^(inner k_hi) and a CTA-wide table xtw[i][c] = W^(inner_c k_lo(i)): one shared
+    // load and one complex product per element instead of a sincospi (a third of a float32 pass, half of a float64 one).
+    cplx<T>* xtw = tw + R;
+    const int lr0 = 8 - logTC;                                   // log2 of the rows per 256-thread sweep
+    const bool fact = !row_major && (int)blockDim.x == 256 && g.logR >= lr0;
+    const int logNI = g.logR - lr0, NI = fact ? 1 << logNI : 0;
+    cplx<T> tw_thread = mk<T>((T)1, (T)0);
+    if (fact) {
+        for (int e = threadIdx.x; e < TC * NI; e += blockDim.x) {
+            const int c = e & (TC - 1), i = e >> logTC;           // [i][c]: the lanes of a warp read consecutive entries
+            const unsigned long long inner = (unsigned long long)((col0 + c) & ((1ll << g.logS) - 1));
+            xtw[e] = unit_root<T>(inner * brev_bits((unsigned)i, logNI), twlog);
+        }
+        const int c = threadIdx.x & (TC - 1), r0 = threadIdx.x >> logTC;
+        const unsigned long long inner = (unsigned long long)((col0 + c) & ((1ll << g.logS) - 1));
+        const unsigned long long k_hi = (unsigned long long)brev_bits((unsigned)r0, lr0) << logNI;
+        tw_thread = unit_root<T>((inner * k_hi) & ((1ull << twlog) - 1ull), twlog);
+        __syncthreads();
+    }
     constexpr int LU = QI_FFT_LOADS_IN_FLIGHT;
     for (int base = threadIdx.x; base < nelem; base += blockDim.x * LU) {
         cplx<T> v[LU];
@@ -225,9 +281,13 @@ fft_pass_kernel(PassGeom g, Src src, Dst dst) {
                 const i64 col = col0 + c;
                 cplx<T> w = v[u];
                 if (DIR == FFT_INV && g.logS > 0) {
-                    const unsigned long long inner = (unsigned long long)(col & ((1ll << g.logS) - 1));
-                    const unsigned k = brev_bits((unsigned)r, g.logR);
-                    if (inner * k) w = mul_conj(w, conj(unit_root<T>(inner * k, twlog)));
+                    if (fact) {
+                        w = w * (xtw[((idx >> 8) << logTC) + c] * tw_thread);
+                    } else {
+                        const unsigned long long inner = (unsigned long long)(col & ((1ll << g.logS) - 1));
+                        const unsigned k = brev_bits((unsigned)r, g.logR);
+                        if (inner * k) w = mul_conj(w, conj(unit_root<T>(inner * k, twlog)));
+                    }
                 }
                 tile[r * TP + c] = w;
             }
@@ -243,13 +303,17 @@ fft_pass_kernel(PassGeom g, Src src, Dst dst) {
         const i64 e = pass_elem(g, r, col);
         cplx<T> v = tile[r * TP + c];
         if (DIR == FFT_FWD && g.logS > 0) {
-            const unsigned long long inner = (unsigned long long)(col & ((1ll << g.logS) - 1));
-            const unsigned k = brev_bits((unsigned)r, g.logR);
-            if (inner * k) v = mul_conj(v, unit_root<T>(inner * k, twlog));
+            if (fact) {
+                v = mul_conj(v, xtw[((idx >> 8) << logTC) + c] * tw_thread);
+            } else {
+                const unsigned long long inner = (unsigned long long)(col & ((1ll << g.logS) - 1));
+                const unsigned k = brev_bits((unsigned)r, g.logR);
+                if (inner * k) v = mul_conj(v, unit_root<T>(inner * k, twlog));
+            }
         }
         dst.store(batch, e, v);
     }
-    dst.finish(batch, reinterpret_cast<unsigned char*>(tw + R));
+    dst.finish(batch, reinterpret_cast<unsigned char*>(xtw + TC * NI));
 }
 
 // ---------------------------------------------------------------- host-side plan
@@ -290,7 +354,9 @@ inline FftPlan make_plan(int logL, int elem_bytes /* sizeof(cplx<T>) */) {
 }
 
 template <typename T> inline size_t pass_smem_bytes(int logR, int TC, size_t dst_scratch) {
-    return ((size_t)(1 << logR) * (TC + 1) + (size_t)(1 << logR)) * sizeof(cplx<T>) + dst_scratch;
+    // tile + stage twiddles + the inter-pass twiddle table xtw[TC][R * TC / 256] of fft_pass_kernel
+    const size_t xtw = ((size_t)(1 << logR) * TC * TC + 255) / 256;
+    return ((size_t)(1 << logR) * (TC + 1) + (size_t)(1 << logR) + xtw) * sizeof(cplx<T>) + dst_scratch;
 }
 
 // Launch one pass.  `pass` indexes the FORWARD order; an inverse transform runs passes npass-1 .. 0.

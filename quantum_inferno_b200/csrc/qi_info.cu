@@ -132,6 +132,37 @@ info_plane_f32_kernel(const float4* __restrict__ p, const double* __restrict__ n
     }
 }
 
+// The float64 counterpart (the information pass of the exact float64 CWT path): 128-bit loads / stores, two in flight,
+// one reciprocal per row instead of a division per cell (P / S and P * (1 / S) differ by one ulp).
+__global__ void __launch_bounds__(256)
+info_plane_f64_kernel(const double2* __restrict__ p, const double* __restrict__ norm, i64 F, i64 T2, double eps,
+                      double2* __restrict__ o_info, double* __restrict__ ent_sum) {
+    __shared__ double scratch[32];
+    const i64 m = blockIdx.z, f = blockIdx.y;
+    const i64 row = (m * F + f) * T2;
+    const double inv = 1.0 / norm[m];
+    const i64 chunk = (T2 + gridDim.x - 1) / gridDim.x;
+    const i64 t0 = (i64)blockIdx.x * chunk;
+    const i64 t1 = t0 + chunk < T2 ? t0 + chunk : T2;
+    double acc = 0.0;
+    auto one = [&](const double2 v, i64 t) {
+        const double d0 = v.x * inv, d1 = v.y * inv;
+        const double i0 = -log2(d0 + eps), i1 = -log2(d1 + eps);
+        o_info[row + t] = make_double2(i0, i1);
+        acc += d0 * i0 + d1 * i1;
+    };
+    i64 t = t0 + threadIdx.x;
+    for (; t + (i64)blockDim.x < t1; t += 2 * (i64)blockDim.x) {
+        const double2 v0 = p[row + t], v1 = p[row + t + blockDim.x];
+        one(v0, t); one(v1, t + blockDim.x);
+    }
+    for (; t < t1; t += blockDim.x) one(p[row + t], t);
+    if (ent_sum) {
+        acc = block_sum(acc, scratch);
+        if (threadIdx.x == 0) atomicAdd(&ent_sum[m * F + f], acc);
+    }
+}
+
 // bits = log2(P + eps) - log2(max[m] + eps)   (tfr_info.py:73-79)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -236,6 +267,12 @@ static int shannon_impl(const void* p, i64 M, i64 F, i64 Tn, int mode, const dou
         ((uintptr_t)p % 16) == 0 && ((uintptr_t)o_info % 16) == 0) {
         QI_LAUNCH(info_plane_f32_kernel, grid, dim3(256), 0, st, static_cast<const float4*>(p), norm, F, Tn / 4,
                   (float)eps, static_cast<float4*>(o_info), ent_sum);
+        return check_cuda("qi_shannon");
+    }
+    if (sizeof(T) == 8 && mode == 0 && o_info && !o_pdf && !o_bits && !o_isnr && !o_esnr && (Tn % 2) == 0 &&
+        ((uintptr_t)p % 16) == 0 && ((uintptr_t)o_info % 16) == 0) {
+        QI_LAUNCH(info_plane_f64_kernel, grid, dim3(256), 0, st, static_cast<const double2*>(p), norm, F, Tn / 2, eps,
+                  static_cast<double2*>(o_info), ent_sum);
         return check_cuda("qi_shannon");
     }
     QI_LAUNCH((shannon_kernel<T>), grid, dim3(256), 0, st, static_cast<const T*>(p), norm, a, static_cast<T*>(o_pdf), static_cast<T*>(o_info),

@@ -321,3 +321,24 @@ def test_synth_and_decimate(golden, capsys):
     from tests import _synth_checks as sc
     sc.check_synth_golden(golden, capsys)
     sc.check_decimate_golden(golden)
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-10), ("float32", 2e-5)])
+def test_cwt_band_limited_routes(dtype, tol):
+    """2^13 samples is the smallest record that takes the band-limited routes of the exact path (csrc/qi_cwt_fast.cuh:
+    overlap-save blocks with the per-stage twiddle tables, decimated transforms + Kaiser interpolation) and a two-pass
+    FFT with the factorised inter-pass twiddles: every band against the oracle."""
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import _driver, _plan, scales_dyadic as scales
+    rt = _runtime.get_runtime()
+    n = 1 << 13
+    xh = np.cos(2 * np.pi * 60 / FS * np.arange(n)) + 0.3 * np.random.default_rng(3).standard_normal(n)
+    freq = scales.log_frequency_hz_from_fft_points(FS, n, 3)
+    bands, _, _, _ = _plan.gabor_bands(3, n, freq, FS, "norm", dtype)
+    out = _driver.cwt_fft(rt.asarray(xh[None, :], dtype), bands, FS, dtype, want_complex=True, want_power=True,
+                          want_band_sum=True, rt=rt)
+    _, _, ref = orc.cwt_complex_any_scale_pow2(3, xh, FS)
+    c = np.asarray(out["complex"][0])
+    assert (np.max(np.abs(c - ref), axis=1) / np.max(np.abs(ref), axis=1)).max() < tol
+    p = np.asarray(out["power"][0], dtype=np.float64)
+    assert np.allclose(np.asarray(out["band_sum"][0]), p.sum(axis=1), rtol=1e-6 if dtype == "float32" else 1e-12)
