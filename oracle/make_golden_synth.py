@@ -11,7 +11,7 @@ import numpy as np
 
 REF = os.environ.get("QI_REFERENCE", "/root/reference")
 sys.path.insert(0, REF)
-from quantum_inferno.synth import benchmark_signals  # noqa: E402
+from quantum_inferno.synth import benchmark_signals, synthetic_signals  # noqa: E402
 from quantum_inferno.utilities import sampling  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
@@ -36,6 +36,10 @@ def main():
         d[f"dec_{q}"] = sampling.decimate_timeseries(x, q)
     coll = np.random.default_rng(1).standard_normal((3, 3000))
     d["coll"], d["coll_dec_4"] = coll, sampling.decimate_timeseries_collection(coll, 4)
+    # the noisy generators with the noise switched off (normal(0, std / 2**inf) = 0): their deterministic part
+    d["chirp16_default"] = synthetic_signals.chirp_noise_16bit(noise_std_loss_bits=np.inf)
+    d["chirp16_fc"] = synthetic_signals.chirp_noise_16bit(2 ** 13, 800.0, np.inf, frequency_center_hz=20.0)
+    d["chirp_lin"], d["chirp_lin_t"] = synthetic_signals.chirp_linear_in_noise(np.inf, 800.0, 2.0, 10.0, 100.0, 0.25, 0.5)
     np.savez_compressed(os.path.join(OUT, "synth.npz"), **d)
     print("synth.npz", os.path.getsize(os.path.join(OUT, "synth.npz")) // 1024, "KiB")
 

@@ -225,10 +225,47 @@ def tdr_marginal(sig, dt, rt=None):
     return sn, mg, ss
 
 
+def fft_c2c(buf, dt, inverse=False, rt=None):
+    """qi_fft_c2c over the rows of a complex [M, 2^m] device buffer: forward = natural in, bit-reversed out; inverse =
+    bit-reversed in, natural out, scaled by 1 / n."""
+    rt = rt or get_runtime()
+    M, n = int(buf.shape[0]), int(buf.shape[1])
+    out = rt.empty((M, n), COMPLEX_OF[dt])
+    rc = rt.lib.qi_fft_c2c(rt.ptr(buf), rt.ptr(out), M, n.bit_length() - 1, int(bool(inverse)), DTYPE_CODE[dt], rt.stream())
+    _lib.check(rt.lib, rc, "qi_fft_c2c")
+    return out
+
+
+def _rfft_bluestein(sig, dt, rt):
+    """One-sided DFT of records whose length n is not a power of two (scipy.fft.rfft takes any n, reference
+    tfr_info.py:177): Bluestein's chirp-z identity  X[k] = c[k] * sum_m (x[m] c[m]) conj(c)[k - m],  c[m] = exp(-pi i m^2 / n),
+    as one circular convolution of length 2^p >= 2n - 1 through qi_fft_c2c (both spectra in bit-reversed order, so their
+    product is too).  The chirp is a host table with the phase reduced in integers (m^2 mod 2n), like the STFT windows."""
+    M, n = int(sig.shape[0]), int(sig.shape[1])
+    m = np.arange(n, dtype=np.int64)
+    ph = ((m * m) % (2 * n)).astype(np.float64) / n
+    c_host = np.cos(np.pi * ph) - 1j * np.sin(np.pi * ph)
+    F = 1 << (2 * n - 2).bit_length()
+    b_host = np.zeros(F, dtype=np.complex128)
+    b_host[:n] = np.conj(c_host)
+    b_host[F - n + 1:] = np.conj(c_host[1:][::-1])
+    cdt = COMPLEX_OF[dt]
+    c = rt.asarray(c_host, cdt)
+    a = rt.zeros((M, F), cdt)
+    a[:, :n] = sig * c
+    A = fft_c2c(a, dt, rt=rt)
+    B = fft_c2c(rt.asarray(b_host[None, :], cdt), dt, rt=rt)
+    y = fft_c2c(A * B, dt, inverse=True, rt=rt)
+    k = n // 2 + 1
+    return y[:, :k] * c[:k]
+
+
 def rfft(sig, dt, rt=None):
     rt = rt or get_runtime()
     lib = rt.lib
     M, n = int(sig.shape[0]), int(sig.shape[1])
+    if n & (n - 1):
+        return _rfft_bluestein(sig, dt, rt)
     out = rt.empty((M, n // 2 + 1), COMPLEX_OF[dt])
     nbytes = M * n * (8 if dt == "float32" else 16)
     ws = rt.workspace(nbytes)

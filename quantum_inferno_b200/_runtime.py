@@ -116,6 +116,15 @@ class CudaRuntime:
     def to_numpy(self, buf):
         return buf.detach().cpu().numpy()
 
+    def randn(self, shape, dtype, seed=None):
+        """Standard normal samples from the device generator; ``seed=None`` draws fresh entropy."""
+        gen = self.torch.Generator(device=self.device)
+        if seed is None:
+            gen.seed()
+        else:
+            gen.manual_seed(int(seed))
+        return self.torch.randn(tuple(int(s) for s in shape), dtype=self._tdtype(dtype), device=self.device, generator=gen)
+
     def reshape(self, buf, shape):
         return buf.reshape(tuple(shape))
 

@@ -263,7 +263,7 @@ static int cwt_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiAtomB
         QI_LAUNCH((cwtf_os_table_kernel<T>), dim3((unsigned)((1 << logF) / 256), (unsigned)n_os), dim3(256), 0, st,
                   (const DevBand*)d_bandsF, logF, half_shift, tabF);
         const int V = (1 << logF) - 2 * fp.os_half;
-        const size_t smem = 3 * sizeof(cplx<T>) * ((size_t)1 << logF) + 256;
+        const size_t smem = sizeof(cplx<T>) * (2 * (size_t)pad8(1 << logF) + ((size_t)1 << logF)) + 256;
 #ifndef QI_EMUL
         cudaFuncSetAttribute(cwtf_os_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif

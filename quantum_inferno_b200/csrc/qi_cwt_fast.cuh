@@ -158,7 +158,7 @@ __global__ void cwtf_os_table_kernel(const DevBand* __restrict__ bandsF, int log
     tabF[((size_t)blockIdx.y << logF) + e] = gabor_response<T>(bandsF[blockIdx.y], k, logF, half_shift);
 }
 
-// grid: (ceil(N / V), channels); one block of F samples, all n_os bands.  dyn smem: 3 F complex + 256 B
+// grid: (ceil(N / V), channels); one block of F samples, all n_os bands.  dyn smem: (2 pad8(F) + F) complex + 256 B
 template <typename T>
 __global__ void __launch_bounds__(512)
 cwtf_os_kernel(const T* __restrict__ sig, i64 stride, CwtGeom geo, const int* __restrict__ ids, int n_os, int logF,
@@ -166,9 +166,10 @@ cwtf_os_kernel(const T* __restrict__ sig, i64 stride, CwtGeom geo, const int* __
                double* __restrict__ band_sum) {
     QI_DYN_SMEM(smem_raw);
     const int F = 1 << logF, V = F - 2 * half;
+    const int FP = pad8(F);                                   // tiles in the padded single-column layout of tile_fft<.., true>
     cplx<T>* tile_x = reinterpret_cast<cplx<T>*>(smem_raw);
-    cplx<T>* tile_y = tile_x + F;
-    cplx<T>* tw = tile_y + F;
+    cplx<T>* tile_y = tile_x + FP;
+    cplx<T>* tw = tile_y + FP;
     double* scratch = reinterpret_cast<double*>(tw + F);
     const i64 chan = blockIdx.y, N = geo.n_points;
     const i64 n0 = (i64)blockIdx.x * V;
@@ -176,14 +177,14 @@ cwtf_os_kernel(const T* __restrict__ sig, i64 stride, CwtGeom geo, const int* __
     fill_stage_twiddles<T>(tw, logF);
     for (int p = threadIdx.x; p < F; p += blockDim.x) {
         const i64 k = n0 - half + p;
-        tile_x[p] = mk<T>((k >= 0 && k < N) ? xs[k] : (T)0, (T)0);
+        tile_x[pad8(p)] = mk<T>((k >= 0 && k < N) ? xs[k] : (T)0, (T)0);
     }
     __syncthreads();
     tile_fft<T, FFT_FWD, true>(tile_x, tw, logF, 1, 1);
     for (int i = 0; i < n_os; ++i) {
         const int band = ids[i];
         const cplx<T>* H = tabF + ((size_t)i << logF);
-        for (int r = threadIdx.x; r < F; r += blockDim.x) tile_y[r] = tile_x[r] * H[r];
+        for (int r = threadIdx.x; r < F; r += blockDim.x) tile_y[pad8(r)] = tile_x[pad8(r)] * H[r];
         __syncthreads();
         tile_fft<T, FFT_INV, true>(tile_y, tw, logF, 1, 1);
         const i64 row = (chan * geo.n_bands + band) * N;
@@ -191,7 +192,7 @@ cwtf_os_kernel(const T* __restrict__ sig, i64 stride, CwtGeom geo, const int* __
         for (int v = threadIdx.x; v < V; v += blockDim.x) {
             const i64 n = n0 + v;
             if (n < N) {
-                const cplx<T> y = tile_y[half + v];
+                const cplx<T> y = tile_y[pad8(half + v)];
                 const T pw = norm2(y);
                 if (out_c) out_c[row + n] = y;
                 if (out_p) out_p[row + n] = pw;

@@ -23,6 +23,9 @@
 #ifndef QI_FFT_LOADS_IN_FLIGHT
 #define QI_FFT_LOADS_IN_FLIGHT 1
 #endif
+#ifndef QI_FFT_TILE_BUDGET_KB
+#define QI_FFT_TILE_BUDGET_KB 96
+#endif
 
 namespace qi {
 
@@ -92,13 +95,17 @@ QI_HD int brev2(int f) { return ((f & 1) << 1) | ((f >> 1) & 1); }
 // ---------------------------------------------------------------- one radix-2^STEP stage on a tile
 // tile[r*TP + c], R = 2^logR rows, TC columns; tw[m] = exp(-2*pi*i*m/R), m in [0,R).
 // Block size 2^logB, sub-stride h = 2^(logB-STEP).
-// STW = true: `tw` is the per-stage table of fill_stage_twiddles (single-column tiles, lanes along j: the strided
-// tw[(j * f) << twshift] of the plain table is an 8-way bank conflict per quarter warp there).
+// STW = true (single-column tiles only, TC = 1): `tw` is the per-stage table of fill_stage_twiddles (lanes run along j:
+// the strided tw[(j * f) << twshift] of the plain table is an 8-way bank conflict per quarter warp there).
 QI_HD int stage_tw_off(int logR, int logB) {     // radix-8 stages sit at logB = logR - 3k
     int off = 0;
     for (int lb = logR; lb > logB; lb -= 3) off += 7 << (lb - 3);
     return off;
 }
+// STW also selects the single-column tile layout phys(r) = r + (r >> 3) (pad8): with lanes along the block offset j the
+// plain layout puts the 32 / h blocks a warp touches in stages with h < 32 a multiple of 512 B apart -- an 8-way conflict
+// on 16-byte elements; with one padding slot per 8 rows every stage of a 2^m-point transform is conflict free.
+QI_HD int pad8(int r) { return r + (r >> 3); }
 template <typename T, int DIR, int STEP, bool STW = false>
 QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int TC, int TP) {
     constexpr int Q = 1 << STEP;
@@ -113,6 +120,32 @@ QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int
         const int u = task >> logTC;
         const int j = u & (h - 1);
         const int g = u >> logH;
+        if (STW) {                                   // single column, padded rows, per-stage twiddle tables
+            const int r0 = (g << logB) + j;
+            cplx<T> a[Q];
+            if (DIR == FFT_FWD) {
+#pragma unroll
+                for (int i = 0; i < Q; ++i) a[i] = tile[pad8(r0 + i * h)];
+                if (STEP == 3) dif8<T, DIR>(a); else if (STEP == 2) dif4<T, DIR>(a); else dif2<T, DIR>(a);
+#pragma unroll
+                for (int s = 0; s < Q; ++s) {
+                    cplx<T> v = a[s];
+                    if (s != 0 && STEP == 3 && logH > 0) v = v * tws[s * h + j];
+                    tile[pad8(r0 + s * h)] = v;
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < Q; ++s) {
+                    cplx<T> v = tile[pad8(r0 + s * h)];
+                    if (s != 0 && STEP == 3 && logH > 0) v = mul_conj(v, tws[s * h + j]);
+                    a[s] = v;
+                }
+                if (STEP == 3) dit8<T, DIR>(a); else if (STEP == 2) dit4<T, DIR>(a); else dit2<T, DIR>(a);
+#pragma unroll
+                for (int i = 0; i < Q; ++i) tile[pad8(r0 + i * h)] = a[i];
+            }
+            continue;
+        }
         cplx<T>* p = tile + (size_t)(((g << logB) + j) * TP + c);
         const int stride = h * TP;
         cplx<T> a[Q];
@@ -124,8 +157,7 @@ QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int
             for (int s = 0; s < Q; ++s) {
                 const int f = STEP == 3 ? brev3(s) : (STEP == 2 ? brev2(s) : s);
                 cplx<T> v = a[s];
-                if (STW) { if (s != 0 && STEP == 3 && logH > 0) v = v * tws[s * h + j]; }
-                else if (f != 0) v = v * tw[(j * f) << twshift];
+                if (f != 0) v = v * tw[(j * f) << twshift];
                 p[s * stride] = v;
             }
         } else {
@@ -133,8 +165,7 @@ QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int
             for (int s = 0; s < Q; ++s) {
                 const int f = STEP == 3 ? brev3(s) : (STEP == 2 ? brev2(s) : s);
                 cplx<T> v = p[s * stride];
-                if (STW) { if (s != 0 && STEP == 3 && logH > 0) v = mul_conj(v, tws[s * h + j]); }
-                else if (f != 0) v = mul_conj(v, tw[(j * f) << twshift]);
+                if (f != 0) v = mul_conj(v, tw[(j * f) << twshift]);
                 a[s] = v;
             }
             if (STEP == 3) dit8<T, DIR>(a); else if (STEP == 2) dit4<T, DIR>(a); else dit2<T, DIR>(a);
@@ -342,7 +373,7 @@ inline FftPlan make_plan(int logL, int elem_bytes /* sizeof(cplx<T>) */) {
         p.logS[i] = below;
         rem -= lr;
         // tile columns: target ~96 KB tile, power of two, between 1 and 32
-        long budget = 96 * 1024 / elem_bytes;
+        long budget = QI_FFT_TILE_BUDGET_KB * 1024 / elem_bytes;
         int tc = 1;
         while (tc < 32 && (long)(1 << lr) * (2 * tc + 1) <= budget) tc *= 2;
         long ncols = 1l << (logL - lr);

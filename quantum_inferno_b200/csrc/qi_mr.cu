@@ -643,54 +643,34 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     ea.x = sig; ea.x_stride = stride; ea.prefix = d_prefix; ea.n_prefix = pl.n_prefix; ea.group_prefix = d_group;
     // both lists are ordered deepest level first, so the bands sharing a polyphase factor 2^k are contiguous
     auto launch_groups = [&](const std::vector<int>& list, const int* d_idx, int dst_level, i64 n_dst, int mode) {
-        const bool mid = mode == MR_MODE_MID;
-        auto key = [&](int idx) {
-            const MrDevBand& bd = pl.bands[idx];
-            const int lr = bd.level - dst_level;
-            const int k = lr < 3 ? lr : 3;
-            const int edge = (!mid && (bd.flags & MR_FLAG_EDGE_SRC)) ? 1 : 0;   // edge source bands: the running sums are added
-            return (k << 8) | edge;
-        };
         size_t pos = 0;
         while (pos < list.size()) {
-            const int ky = key(list[pos]);
-            const int k = ky >> 8;
-            const bool edge = ky & 1;
+            const int lr0 = pl.bands[list[pos]].level - dst_level;
+            const int k = lr0 < 3 ? lr0 : 3;
+            // edge source bands form their own group at the full rate (the running sums are added there)
+            const bool edge = mode != MR_MODE_MID && (pl.bands[list[pos]].flags & MR_FLAG_EDGE_SRC);
             size_t end = pos;
-            std::vector<int> levels;
-            while (end < list.size() && key(list[end]) == ky) { levels.push_back(pl.bands[list[end]].level); ++end; }
-            ea.band_list = d_idx + pos;
-            const size_t smem = mr_expand_smem(levels.data(), (int)levels.size(), dst_level, mid, taps);
-            // a CTA walks up to 8 x8-tiles (the same number of destination samples for the smaller factors) of one row,
-            // fewer when that would leave less than ~8 waves of CTAs
-            const i64 n_tiles = (n_dst + ((i64)MR_SEGQ << k) - 1) / ((i64)MR_SEGQ << k);
-            i64 tpc = n_tiles * (i64)(end - pos) * C / (148 * 4 * 8);
-            const i64 tpc_max = (i64)8 << (3 - k);
-            tpc = tpc < 1 ? 1 : (tpc > tpc_max ? tpc_max : tpc);
-            ea.tiles_per_cta = (int)tpc;
-            dim3 grid((unsigned)((n_tiles + tpc - 1) / tpc), (unsigned)(end - pos), (unsigned)C);
-#ifdef QI_EMUL
-#define QI_EXPAND_LAUNCH(...) QI_LAUNCH((mr_expand_kernel<__VA_ARGS__>), grid, dim3(256), smem, st, ea, taps)
-#else
-#define QI_EXPAND_LAUNCH(...)                                                                                            \
-    do {                                                                                                                 \
-        cudaFuncSetAttribute(mr_expand_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-        QI_LAUNCH((mr_expand_kernel<__VA_ARGS__>), grid, dim3(256), smem, st, ea, taps);                                 \
-    } while (0)
-#endif
-            if (edge) {             // record-long atoms live at level >= 3: always the x8 interpolator
-                if (mode == MR_MODE_POWER) QI_EXPAND_LAUNCH(MR_MODE_POWER, false, true);
-                else QI_EXPAND_LAUNCH(MR_MODE_POWER_INFO, false, true);
-            } else if (k < 3) {
-                if (mode == MR_MODE_MID) QI_EXPAND_LAUNCH(MR_MODE_MID, true);
-                else if (mode == MR_MODE_POWER) QI_EXPAND_LAUNCH(MR_MODE_POWER, true);
-                else QI_EXPAND_LAUNCH(MR_MODE_POWER_INFO, true);
-            } else {
-                if (mode == MR_MODE_MID) QI_EXPAND_LAUNCH(MR_MODE_MID, false);
-                else if (mode == MR_MODE_POWER) QI_EXPAND_LAUNCH(MR_MODE_POWER, false);
-                else QI_EXPAND_LAUNCH(MR_MODE_POWER_INFO, false);
+            while (end < list.size()) {
+                const int lr = pl.bands[list[end]].level - dst_level;
+                if ((lr < 3 ? lr : 3) != k) break;
+                if ((mode != MR_MODE_MID && (pl.bands[list[end]].flags & MR_FLAG_EDGE_SRC)) != edge) break;
+                ++end;
             }
-#undef QI_EXPAND_LAUNCH
+            ea.band_list = d_idx + pos;
+            const i64 tile = (i64)MR_SEGQ << 3;          // per CTA, for every k (see mr_expand_kernel)
+            dim3 grid((unsigned)((n_dst + tile - 1) / tile), (unsigned)(end - pos), (unsigned)C);
+            if (edge) {             // record-long atoms live at level >= 3: always the x8 interpolator
+                if (mode == MR_MODE_POWER) QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER, false, true>), grid, dim3(256), 0, st, ea, taps);
+                else QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER_INFO, false, true>), grid, dim3(256), 0, st, ea, taps);
+            } else if (k < 3) {
+                if (mode == MR_MODE_MID) QI_LAUNCH((mr_expand_kernel<MR_MODE_MID, true>), grid, dim3(256), 0, st, ea, taps);
+                else if (mode == MR_MODE_POWER) QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER, true>), grid, dim3(256), 0, st, ea, taps);
+                else QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER_INFO, true>), grid, dim3(256), 0, st, ea, taps);
+            } else {
+                if (mode == MR_MODE_MID) QI_LAUNCH((mr_expand_kernel<MR_MODE_MID, false>), grid, dim3(256), 0, st, ea, taps);
+                else if (mode == MR_MODE_POWER) QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER, false>), grid, dim3(256), 0, st, ea, taps);
+                else QI_LAUNCH((mr_expand_kernel<MR_MODE_POWER_INFO, false>), grid, dim3(256), 0, st, ea, taps);
+            }
             pos = end;
         }
     };

@@ -16,6 +16,8 @@ record are the blocked parallel scan of csrc/qi_iir.cu (fp64 arithmetic; 2-D [ch
 """
 from typing import Tuple
 
+import warnings
+
 import numpy as np
 
 from . import _driver, _iir, _plan
@@ -48,7 +50,13 @@ def _spectral(sig_wf, fs, window, nperseg, noverlap, nfft, dtype, welch=False):
     lead = tuple(int(s) for s in x.shape[:-1])
     n_points = int(x.shape[-1])
     if nperseg > n_points:
-        raise ValueError(f"nperseg = {nperseg} is greater than the record length {n_points}")
+        # scipy.signal._spectral_py._triage_segments: warn, shorten the segment to the record, rebuild the window;
+        # noverlap and nfft stay as given (reference styx_fft.py:175-187 hands them to scipy.signal.stft unchanged)
+        warnings.warn(f"nperseg = {nperseg:d} is greater than input length  = {n_points:d}, using nperseg = {n_points:d}",
+                      stacklevel=3)
+        nperseg = n_points
+        if noverlap >= nperseg:
+            raise ValueError("noverlap must be less than nperseg.")
     x2 = rt.reshape(x, (int(np.prod(lead)) if lead else 1, n_points))
     win = _plan.periodic_window(window[0], window[1], nperseg)
     n_frames, pad_left, ext = _plan.stft_frames(n_points, nperseg, noverlap, boundary_zeros=not welch,

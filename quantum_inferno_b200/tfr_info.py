@@ -159,16 +159,14 @@ class ShannonTDR(Shannon):
 
 
 class ShannonFFT(Shannon):
-    """Spectral Shannon information: marginal = |rfft(x)|^2 / sum (reference tfr_info.py:163-190).
-    The record length must be a power of two on this implementation."""
+    """Spectral Shannon information: marginal = |rfft(x)|^2 / sum (reference tfr_info.py:163-190).  Any record length
+    (lengths that are not a power of two go through Bluestein's identity, see _driver._rfft_bluestein)."""
 
     def __init__(self, sig_in_real, *, dtype=None):
         c = _Ctx(sig_in_real, dtype)
         rt, dt = c.rt, c.dt
         x = rt.asarray(sig_in_real, dt)
         n = int(x.shape[-1])
-        if n & (n - 1):
-            raise ValueError("ShannonFFT on the B200 path needs a power-of-two record length")
         k = n // 2 + 1
         z = _driver.rfft(rt.reshape(x, (1, n)), dt, rt=rt)
         p3 = rt.reshape(_driver.abs_log2(z, dt, True, eps=0.0, square=True, rt=rt), (1, 1, k))     # |z|^2

@@ -1,0 +1,81 @@
+"""Shared assertions for the thinly covered rows of SURVEY 8(a) -- a5 atoms, a9 general Stockwell transform, a14 1-D
+Shannon classes, and the reference's ValueError paths -- run through the CPU emulator (tests/test_emul_api.py) and on the
+B200 (tests/test_gpu_parity.py) against tests/golden/extra.npz (oracle/make_golden_extra.py)."""
+import numpy as np
+import pytest
+
+FS = 800.0
+ATOM_CASES = [(3, 512, "norm"), (3, 1000, "spect"), (6, 2048, "unit"), (12, 1000, "norm"), (6, 512, "spect"), (3, 2048, "unit")]
+ATOM_FREQS = np.array([2.5, 40.0, 310.0])
+INFO_LENGTHS = [1000, 777, 1 << 13]
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - b)) / np.max(np.abs(b)))
+
+
+def check_atoms_all_dictionaries(golden):
+    """a5: styx_cwt.wavelet_centered_4cwt (reference styx_cwt.py:113-144), three dictionaries x three sizes x three orders."""
+    from quantum_inferno_b200 import styx_cwt
+    g = golden("extra")
+    for i, (order, n, dic) in enumerate(ATOM_CASES):
+        atoms, t_s, scale, omega, amp = styx_cwt.wavelet_centered_4cwt(order, n, ATOM_FREQS, FS, dic)
+        assert atoms.shape == (3, n) and atoms.dtype == np.complex128
+        assert rel(atoms, g[f"atoms{i}"]) < 1e-12, (order, n, dic)
+        assert np.array_equal(t_s, g[f"atoms{i}_t"])
+        assert np.array_equal(scale[:, 0], g[f"atoms{i}_scale"]) and np.array_equal(omega[:, 0], g[f"atoms{i}_omega"])
+        assert np.array_equal(amp[:, 0], g[f"atoms{i}_amp"])
+        a32 = styx_cwt.wavelet_centered_4cwt(order, n, ATOM_FREQS, FS, dic, dtype="float32")[0]
+        assert a32.dtype == np.complex64 and rel(a32, g[f"atoms{i}"]) < 2e-6
+
+
+def check_stx_general_multipass(golden):
+    """a9: styx_stx.tfr_stx_fft (reference styx_stx.py:52-192) at 2048 samples = two FFT passes, and its error paths."""
+    from quantum_inferno_b200 import styx_stx
+    g = golden("extra")
+    x = g["stx_x"]
+    for tag, kw in [("lin", dict(frequency_min=10.0, frequency_max=100.0, frequency_step=5.0)),
+                    ("geo", dict(frequency_min=10.0, frequency_max=100.0, is_geometric=True, scale_order_input=3.0))]:
+        tfr, psd, f, f_fft, win = styx_stx.tfr_stx_fft(x, 1 / FS, n_fft_in=2048, **kw)
+        assert np.array_equal(f, g[f"stx_{tag}_f"]) and np.array_equal(f_fft, g[f"stx_{tag}_ffft"])
+        assert tfr.shape == g[f"stx_{tag}_tfr"].shape and rel(tfr, g[f"stx_{tag}_tfr"]) < 1e-10, tag
+        assert rel(psd, g[f"stx_{tag}_psd"]) < 1e-10 and rel(win[::4], g[f"stx_{tag}_win0"]) < 1e-12
+    # reference styx_stx.py:30-31: a transform shorter than the record is an error
+    with pytest.raises(ValueError):
+        styx_stx.sig_pad_up_to_pow2(x, 1024)
+    with pytest.raises(ValueError):
+        styx_stx.tfr_stx_fft(x, 1 / FS, n_fft_in=1024)
+
+
+def check_shannon_1d_all_attributes(golden):
+    """a14: ShannonTDR / ShannonFFT (reference tfr_info.py:106-200): every attribute, record lengths that are not powers
+    of two included (scipy's rfft takes any length)."""
+    from quantum_inferno_b200 import tfr_info
+    g = golden("extra")
+    for n in INFO_LENGTHS:
+        tdr, ff = tfr_info.shannon_tdr_fft(g[f"info{n}_x"])
+        for tag, obj in (("tdr", tdr), ("fft", ff)):
+            assert rel(obj.sig, g[f"info{n}_{tag}_sig"]) < 1e-10, (n, tag)
+            assert rel(obj.marginal, g[f"info{n}_{tag}_marginal"]) < 1e-10
+            # information of near-empty cells: log2 of (marginal + eps32) with marginal ~ eps64 * peak
+            assert np.max(np.abs(obj.info - g[f"info{n}_{tag}_info"])) < 1e-9, (n, tag)
+            assert rel(obj.entropy, g[f"info{n}_{tag}_entropy"]) < 1e-10
+            assert np.max(np.abs(obj.isnr - g[f"info{n}_{tag}_isnr"])) < 1e-9
+            assert rel(obj.esnr, g[f"info{n}_{tag}_esnr"]) < 1e-10
+            assert abs(obj.ref_entropy - float(g[f"info{n}_{tag}_ref"])) < 1e-15
+        assert np.array_equal(ff.frequency, g[f"info{n}_fft_freq"])
+        # the unwrapped phase is only defined where the spectrum is not numerically zero
+        strong = np.abs(g[f"info{n}_fft_sig"]) > 1e-6 * np.abs(g[f"info{n}_fft_sig"]).max()
+        d = (ff.angle_rads - g[f"info{n}_fft_angle"])[strong]
+        assert np.max(np.abs(d - 2 * np.pi * np.round(d / (2 * np.pi)))) < 1e-8
+
+
+def check_reference_error_paths():
+    """ValueError conventions of the reference on the live runtime: styx_fft.py:42-45 (record shorter than the FFT window),
+    cwt_atoms.py:436-437 (unknown cwt_type)."""
+    from quantum_inferno_b200 import cwt_atoms, styx_fft
+    x = np.cos(2 * np.pi * 60.0 / FS * np.arange(256))
+    with pytest.raises(ValueError):
+        styx_fft.stft_from_sig(x, FS, 3, center_frequency_hz=0.5)       # needs a window far longer than 256 samples
+    with pytest.raises(ValueError):
+        cwt_atoms.cwt_chirp_complex(3, x, 10.0, FS, cwt_type="nope")

@@ -43,3 +43,32 @@ def check_decimate_golden(golden):
     assert y.shape == g["coll_dec_4"].shape and peak_rel(y, g["coll_dec_4"]) < 1e-11
     with pytest.raises(ValueError):
         sampling.decimate_timeseries(g["x"][:27], 2)                           # the reference needs 28 samples or more
+
+
+def check_noise_generators_golden(golden):
+    """chirp_noise_16bit / chirp_linear_in_noise / white_noise_fbits (reference synth/synthetic_signals.py:53-81, :127-169):
+    the deterministic part against the reference with the noise switched off, the noise by its seed and its statistics."""
+    from quantum_inferno_b200.synth import synthetic_signals as ss
+    g = golden("synth")
+    y = ss.chirp_noise_16bit(noise_std_loss_bits=np.inf)
+    assert y.dtype == np.float16 and y.shape == g["chirp16_default"].shape
+    # float16 output: one half-precision ulp where a float64 value sits on a rounding boundary
+    assert np.max(np.abs(y.astype(np.float64) - g["chirp16_default"].astype(np.float64))) <= 2.0 ** -10
+    assert np.mean(y == g["chirp16_default"]) > 0.999
+    y = ss.chirp_noise_16bit(2 ** 13, 800.0, np.inf, frequency_center_hz=20.0)
+    assert np.max(np.abs(y.astype(np.float64) - g["chirp16_fc"].astype(np.float64))) <= 2.0 ** -10
+    w, t = ss.chirp_linear_in_noise(np.inf, 800.0, 2.0, 10.0, 100.0, 0.25, 0.5)
+    assert w.dtype == np.float64 and np.array_equal(t, g["chirp_lin_t"])
+    assert np.max(np.abs(w - g["chirp_lin"])) < 1e-11
+    # seeded noise: repeatable, of the requested level, uncorrelated with the sweep
+    a, _ = ss.chirp_linear_in_noise(3.0, 800.0, 2.0, 10.0, 100.0, 0.25, 0.5, seed=7)
+    b, _ = ss.chirp_linear_in_noise(3.0, 800.0, 2.0, 10.0, 100.0, 0.25, 0.5, seed=7)
+    c, _ = ss.chirp_linear_in_noise(3.0, 800.0, 2.0, 10.0, 100.0, 0.25, 0.5, seed=8)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    noise = a - g["chirp_lin"]
+    want = np.std(g["chirp_lin"]) / 2.0 ** 3
+    assert abs(np.std(noise) / want - 1.0) < 0.05 and abs(np.mean(noise)) < 4 * want / np.sqrt(noise.size)
+    assert abs(np.corrcoef(noise, g["chirp_lin"])[0, 1]) < 0.1
+    n = ss.white_noise_fbits(g["x"], 2.0, seed=1)
+    assert n.shape == (g["x"].size,) and abs(np.std(n) / (np.std(g["x"]) / 4.0) - 1.0) < 0.05
+    assert np.array_equal(n, ss.white_noise_fbits(g["x"], 2.0, seed=1))

@@ -54,5 +54,8 @@ class EmulRuntime:
     def to_numpy(self, buf):
         return np.asarray(buf)
 
+    def randn(self, shape, dtype, seed=None):
+        return np.random.default_rng(seed).standard_normal(tuple(int(s) for s in shape)).astype(dtype)
+
     def reshape(self, buf, shape):
         return buf.reshape(tuple(shape))

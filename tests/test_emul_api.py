@@ -321,6 +321,7 @@ def test_synth_and_decimate(golden, capsys):
     from tests import _synth_checks as sc
     sc.check_synth_golden(golden, capsys)
     sc.check_decimate_golden(golden)
+    sc.check_noise_generators_golden(golden)
 
 
 @pytest.mark.parametrize("dtype,tol", [("float64", 1e-10), ("float32", 2e-5)])
@@ -342,3 +343,43 @@ def test_cwt_band_limited_routes(dtype, tol):
     assert (np.max(np.abs(c - ref), axis=1) / np.max(np.abs(ref), axis=1)).max() < tol
     p = np.asarray(out["power"][0], dtype=np.float64)
     assert np.allclose(np.asarray(out["band_sum"][0]), p.sum(axis=1), rtol=1e-6 if dtype == "float32" else 1e-12)
+
+
+def test_stft_segment_longer_than_record():
+    """scipy.signal.stft (reference styx_fft.py:175) warns and shortens nperseg to the record; noverlap / nfft stay."""
+    import warnings
+    import scipy.signal
+    x = np.random.default_rng(0).standard_normal(100)
+    with warnings.catch_warnings(record=True) as wref:
+        warnings.simplefilter("always")
+        fr, tr, zr = scipy.signal.stft(x, FS, nperseg=128, noverlap=64, nfft=128, window=("tukey", 0.25),
+                                       detrend="constant", boundary="zeros", padded=True)
+    with warnings.catch_warnings(record=True) as wour:
+        warnings.simplefilter("always")
+        f, t, z = styx_fft.stft_complex_pow2(x, FS, 128)
+    assert [str(m.message) for m in wour] == [str(m.message) for m in wref] and len(wour) == 1
+    assert z.shape == zr.shape == (65, 4) and np.array_equal(f, fr) and np.allclose(t, tr)
+    assert rel(z, zr) < 1e-12
+    with pytest.raises(ValueError, match="noverlap must be less than nperseg"):
+        styx_fft.stft_complex_pow2(x[:60], FS, 128)
+
+
+# ----------------------------------------------------------------------------- thinly covered rows (a5, a9, a14, errors)
+def test_atoms_all_dictionaries(golden):
+    from tests import _extra_checks as ec
+    ec.check_atoms_all_dictionaries(golden)
+
+
+def test_stx_general_multipass(golden):
+    from tests import _extra_checks as ec
+    ec.check_stx_general_multipass(golden)
+
+
+def test_shannon_1d_all_attributes(golden):
+    from tests import _extra_checks as ec
+    ec.check_shannon_1d_all_attributes(golden)
+
+
+def test_reference_error_paths():
+    from tests import _extra_checks as ec
+    ec.check_reference_error_paths()

@@ -563,6 +563,7 @@ def test_synth_and_decimate_gpu(torch_cuda, golden, capsys):
     from tests import _synth_checks as sc
     sc.check_synth_golden(golden, capsys)
     sc.check_decimate_golden(golden)
+    sc.check_noise_generators_golden(golden)
     # bench-size tone made on the device: 2^24 samples, stays a tensor, equals the closed form at probe points
     from quantum_inferno_b200.synth import benchmark_signals as bs
     sig, t, nfft, fs, fc, df = bs.well_tempered_tone(800.0, 60.0, (1 << 24) / 800.0, 0.64, dtype="float32", device_out=True)
@@ -604,3 +605,24 @@ def test_stx_multirate_vs_oracle(torch_cuda, order, logn, chans):
         assert np.linalg.norm(c[ch] - c0) / np.linalg.norm(c0) < TOL32_L2 / 10
         assert max(np.linalg.norm(c[ch, b] - c0[b]) / np.linalg.norm(c0[b]) for b in range(len(f))) < TOL32_L2 / 5
         assert l2(p[ch], np.abs(c0) ** 2) < TOL32_L2 / 5
+
+
+# ----------------------------------------------------------------------------- thinly covered rows (a5, a9, a14, errors)
+def test_atoms_all_dictionaries(torch_cuda, golden):
+    from tests import _extra_checks as ec
+    ec.check_atoms_all_dictionaries(golden)
+
+
+def test_stx_general_multipass(torch_cuda, golden):
+    from tests import _extra_checks as ec
+    ec.check_stx_general_multipass(golden)
+
+
+def test_shannon_1d_all_attributes(torch_cuda, golden):
+    from tests import _extra_checks as ec
+    ec.check_shannon_1d_all_attributes(golden)
+
+
+def test_reference_error_paths(torch_cuda):
+    from tests import _extra_checks as ec
+    ec.check_reference_error_paths()
