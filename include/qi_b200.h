@@ -161,7 +161,11 @@ typedef struct {
 
 size_t qi_stx_workspace_bytes(int64_t n_channels, int64_t n_points, int n_bands, int bands_per_group, int dtype);
 
-/* out_tfr complex [C,B,N] or NULL; out_power real [C,B,N] or NULL; band_sum double [C,B] or NULL */
+/* out_tfr complex [C,B,N] or NULL; out_power real [C,B,N] or NULL; band_sum double [C,B] or NULL.
+ * Records of 2^13 samples or more: a voice whose Gaussian window fits K <= n / 4 bins is inverse-transformed at length K
+ * and interpolated to the full rate (Kaiser-windowed sinc; float64 24 taps / -231 dB, float32 16 taps / -110 dB), the
+ * others take full-length passes.  A NEGATIVE bands_per_group keeps every band on the full-length passes (|value| bands
+ * per launch): the arbiter the band-limited route is tested against. */
 int qi_stx_fft(const void* sig, int64_t n_channels, int64_t n_points, int64_t sig_stride,
                const QiStxBand* bands, int n_bands, int dtype,
                void* out_tfr, void* out_power, double* band_sum,

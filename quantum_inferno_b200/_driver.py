@@ -83,8 +83,9 @@ def atoms_time(bands, n_points, fs, dt, xtime=None, rt=None):
 
 
 def stx_fft(sig, bands, dt, want_complex=True, want_power=False, want_band_sum=False, rt=None, method="exact"):
-    """Run qi_stx_fft (method="exact") or qi_stx_multirate (method="multirate": float32, records of 2^m >= 4096
-    samples, decimated voices + polyphase interpolation)."""
+    """Run qi_stx_fft (method="exact": band-limited voices where the window allows, full-length passes otherwise;
+    method="plain": full-length passes for every band) or qi_stx_multirate (method="multirate": float32, records of
+    2^m >= 4096 samples, decimated voices + packed polyphase interpolation)."""
     rt = rt or get_runtime()
     lib = rt.lib
     C, N = int(sig.shape[0]), int(sig.shape[1])
@@ -102,8 +103,8 @@ def stx_fft(sig, bands, dt, want_complex=True, want_power=False, want_band_sum=F
                                   nbytes, rt.stream())
         _lib.check(lib, rc, "qi_stx_multirate")
         return {"complex": out_c, "power": out_p, "band_sum": None}
-    if method != "exact":
-        raise ValueError("method must be 'exact' or 'multirate'")
+    if method not in ("exact", "plain"):
+        raise ValueError("method must be 'exact', 'plain' or 'multirate'")
 
     def ws_bytes(group):
         return lib.qi_stx_workspace_bytes(C, N, B, group, code)
@@ -115,7 +116,7 @@ def stx_fft(sig, bands, dt, want_complex=True, want_power=False, want_band_sum=F
     out_p = rt.empty((C, B, N), dt) if want_power else None
     bsum = rt.empty((C, B), "float64") if want_band_sum else None
     rc = lib.qi_stx_fft(rt.ptr(sig), C, N, N, bands.ctypes.data, B, code, rt.ptr(out_c), rt.ptr(out_p), rt.ptr(bsum),
-                        rt.ptr(ws), nbytes, group, rt.stream())
+                        rt.ptr(ws), nbytes, -group if method == "plain" else group, rt.stream())
     _lib.check(lib, rc, "qi_stx_fft")
     return {"complex": out_c, "power": out_p, "band_sum": bsum}
 

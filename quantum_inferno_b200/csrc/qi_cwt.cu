@@ -339,7 +339,8 @@ static int cwt_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiAtomB
                 prof_set_category(QI_CAT_INV_LAST);
                 dim3 grid((unsigned)((N + CWTF_SPAN * CWTF_TILE - 1) / (CWTF_SPAN * CWTF_TILE)), (unsigned)gs, (unsigned)C);
                 QI_LAUNCH((cwtf_interp_kernel<T>), grid, dim3(256), 0, st, (const cplx<T>*)work, (const int*)(d_dec + sub),
-                          (const DevBand*)d_bands, geo, logD, cf, static_cast<cplx<T>*>(out_c), static_cast<T*>(out_p), band_sum);
+                          (const long long*)&d_bands[0].kc, (int)(sizeof(DevBand) / sizeof(long long)), geo, logD, cf,
+                          static_cast<cplx<T>*>(out_c), static_cast<T*>(out_p), band_sum);
                 sub += (size_t)gs;
             }
             pos = end;

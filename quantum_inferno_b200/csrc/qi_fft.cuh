@@ -17,14 +17,22 @@
 #pragma once
 #include "qi_platform.cuh"
 
-// loads requested per thread before the first is consumed in the load phase of a pass.  Measured on B200 (Stockwell
-// 16 x 2^18 and the exact CWT bench): 1 -> 3.11 ms / 412 ms, 2 -> 3.32 / 446, 4 -> 3.21 / 422: the passes are
-// instruction-bound, not latency-bound, so the simple loop stays (make EXTRA=-DQI_FFT_LOADS_IN_FLIGHT=n to repeat).
+// Loads requested per thread before the first is consumed in the load phase of a pass, and the shared-memory budget that
+// sets the tile width.  Measured on B200 once the per-element sincospi of the inter-pass twiddles was gone (before that
+// the passes were instruction-bound and neither knob mattered), forward / inverse ms of tools/fft_probe.py:
+//   (loads, KB)      8 x 2^25 f32     8 x 2^25 f64     672 x 2^18 f32   336 x 2^18 f64
+//   (1, 96)          9.19 / 9.08      11.94 / 11.79    4.08 / 3.99      2.60 / 2.58
+//   (8, 96)          5.24 / 5.06      11.93 / 11.80    2.27 / 2.15      2.60 / 2.58
+//   (4, 48)          5.57 / 5.23       9.59 /  9.42    2.53 / 2.28      2.38 / 2.32
+//   (8, 48)          4.23 / 3.97       7.57 /  7.43    2.52 / 2.28      2.04 / 1.98      <- default
+//   (8, 32)          6.54 / 6.18      10.24 / 10.62    2.10 / 2.11      3.01 / 3.02
+// (gpurun_out r2j, summarised in profiles/r02_fft_pass_tuning.md): the passes are latency-bound -- two ~80 KB CTAs per SM
+// with one load in flight per thread kept 8 KB per SM in flight where HBM needs ~20 KB.
 #ifndef QI_FFT_LOADS_IN_FLIGHT
-#define QI_FFT_LOADS_IN_FLIGHT 1
+#define QI_FFT_LOADS_IN_FLIGHT 8
 #endif
 #ifndef QI_FFT_TILE_BUDGET_KB
-#define QI_FFT_TILE_BUDGET_KB 96
+#define QI_FFT_TILE_BUDGET_KB 48
 #endif
 
 namespace qi {
@@ -95,8 +103,8 @@ QI_HD int brev2(int f) { return ((f & 1) << 1) | ((f >> 1) & 1); }
 // ---------------------------------------------------------------- one radix-2^STEP stage on a tile
 // tile[r*TP + c], R = 2^logR rows, TC columns; tw[m] = exp(-2*pi*i*m/R), m in [0,R).
 // Block size 2^logB, sub-stride h = 2^(logB-STEP).
-// STW = true (single-column tiles only, TC = 1): `tw` is the per-stage table of fill_stage_twiddles (lanes run along j:
-// the strided tw[(j * f) << twshift] of the plain table is an 8-way bank conflict per quarter warp there).
+// STW = true: TC independent single-column tiles, TP elements apart; `tw` is the per-stage table of fill_stage_twiddles
+// (lanes run along j: the strided tw[(j * f) << twshift] of the plain table is an 8-way bank conflict per quarter warp).
 QI_HD int stage_tw_off(int logR, int logB) {     // radix-8 stages sit at logB = logR - 3k
     int off = 0;
     for (int lb = logR; lb > logB; lb -= 3) off += 7 << (lb - 3);
@@ -120,29 +128,35 @@ QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int
         const int u = task >> logTC;
         const int j = u & (h - 1);
         const int g = u >> logH;
-        if (STW) {                                   // single column, padded rows, per-stage twiddle tables
-            const int r0 = (g << logB) + j;
+        if (STW) {
+            // TC independent single-column tiles TP elements apart, padded rows, per-stage twiddle tables; the lanes of a
+            // warp run along the butterflies of ONE tile (task = tile * butterflies + butterfly)
+            const int logPer = logR - STEP;
+            const int uu = task & ((1 << logPer) - 1);
+            cplx<T>* tl = tile + (size_t)(task >> logPer) * TP;
+            const int jj = uu & (h - 1);
+            const int r0 = ((uu >> logH) << logB) + jj;
             cplx<T> a[Q];
             if (DIR == FFT_FWD) {
 #pragma unroll
-                for (int i = 0; i < Q; ++i) a[i] = tile[pad8(r0 + i * h)];
+                for (int i = 0; i < Q; ++i) a[i] = tl[pad8(r0 + i * h)];
                 if (STEP == 3) dif8<T, DIR>(a); else if (STEP == 2) dif4<T, DIR>(a); else dif2<T, DIR>(a);
 #pragma unroll
                 for (int s = 0; s < Q; ++s) {
                     cplx<T> v = a[s];
-                    if (s != 0 && STEP == 3 && logH > 0) v = v * tws[s * h + j];
-                    tile[pad8(r0 + s * h)] = v;
+                    if (s != 0 && STEP == 3 && logH > 0) v = v * tws[s * h + jj];
+                    tl[pad8(r0 + s * h)] = v;
                 }
             } else {
 #pragma unroll
                 for (int s = 0; s < Q; ++s) {
-                    cplx<T> v = tile[pad8(r0 + s * h)];
-                    if (s != 0 && STEP == 3 && logH > 0) v = mul_conj(v, tws[s * h + j]);
+                    cplx<T> v = tl[pad8(r0 + s * h)];
+                    if (s != 0 && STEP == 3 && logH > 0) v = mul_conj(v, tws[s * h + jj]);
                     a[s] = v;
                 }
                 if (STEP == 3) dit8<T, DIR>(a); else if (STEP == 2) dit4<T, DIR>(a); else dit2<T, DIR>(a);
 #pragma unroll
-                for (int i = 0; i < Q; ++i) tile[pad8(r0 + i * h)] = a[i];
+                for (int i = 0; i < Q; ++i) tl[pad8(r0 + i * h)] = a[i];
             }
             continue;
         }

@@ -1,0 +1,124 @@
+// qi_interp.cuh -- the Kaiser-windowed-sinc interpolator of the band-limited routes (Gabor CWT: qi_cwt_fast.cuh,
+// Stockwell: qi_stx.cu), float32 and float64.
+//
+// A band whose spectrum is negligible outside K = 2^m bins around its centre is known exactly from the K-point inverse
+// transform of those bins: every D = L / K-th sample of its L-point (circular) output, demodulated by the centre bin.  A
+// TAPS-per-phase interpolator brings it to the full rate, puts the carrier back (exact integer phase, stepped inside a
+// thread) and fuses the output slice, |.|^2 and the fp64 band sums.
+//     float32: RHO = 2 (oversampling of the decimated samples), 16 taps, beta 11.2 (stop band -110 dB)
+//     float64: RHO = 4, 24 taps, beta 24.5 (-231 dB)
+#pragma once
+#include "qi_tfr.cuh"
+
+namespace qi {
+
+constexpr int CWTF_MAX_LOGD = 8;
+constexpr int CWTF_TILE = 2048;
+constexpr int CWTF_SPAN = 4;                 // tiles per CTA of the interpolator
+constexpr int CWTF_OS_LOGF = 11;             // overlap-save block length 2048
+constexpr int CWTF_OS_MAX_HALF = 384;        // longest kernel half-support taken by the overlap-save route
+
+template <typename T> struct CwtFastCfg;
+template <> struct CwtFastCfg<float> {
+    static constexpr int TAPS = 16, RHO = 2, PER = 8;
+    static constexpr double U_CUT = 5.6, BETA = 11.2;
+};
+template <> struct CwtFastCfg<double> {
+    static constexpr int TAPS = 24, RHO = 4, PER = 4;
+    static constexpr double U_CUT = 7.7, BETA = 24.5;
+};
+
+// modified Bessel function I0 by its power series (converged to 1e-19 of the sum for x <= 23 after 64 terms)
+QI_HD double cwtf_bessel_i0(double x) {
+    double s = 1.0, term = 1.0;
+    const double hh = 0.25 * x * x;
+    for (int k = 1; k <= 64; ++k) { term *= hh / (double)(k * k); s += term; }
+    return s;
+}
+
+// coef[logD][j * D + p] = h(p - (j - (TAPS/2 - 1)) D),  h(t) = sinc(t / D) kaiser(t / (TAPS/2 D); beta)
+template <typename T>
+__global__ void cwtf_coef_kernel(T* __restrict__ coef_all, unsigned need_mask, double inv_i0_beta) {
+    constexpr int TAPS = CwtFastCfg<T>::TAPS;
+    const int logD = blockIdx.y;
+    if (!((need_mask >> logD) & 1u)) return;
+    T* coef = coef_all + (size_t)logD * TAPS * (1u << CWTF_MAX_LOGD);
+    const int D = 1 << logD;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= TAPS * D) return;
+    const int j = idx >> logD, p = idx & (D - 1);
+    const double t = (double)(p - (j - (TAPS / 2 - 1)) * D);
+    const double x = t / (0.5 * TAPS * D);
+    const double arg = 1.0 - x * x;
+    const double w = cwtf_bessel_i0(CwtFastCfg<T>::BETA * sqrt(arg > 0.0 ? arg : 0.0)) * inv_i0_beta;
+    const double y = t / (double)D;
+    const double sinc = t == 0.0 ? 1.0 : sinpi(y) / (M_PI * y);
+    coef[idx] = (T)(sinc * w);
+}
+
+// grid: (ceil(N / (SPAN * TILE)), bands of the group, channels);  dec: [band_in_group][chan][K]
+template <typename T>
+__global__ void __launch_bounds__(256)
+cwtf_interp_kernel(const cplx<T>* __restrict__ dec, const int* __restrict__ ids, const long long* __restrict__ kc_of_band,
+                   int kc_stride, CwtGeom geo, int logD, const T* __restrict__ coef, cplx<T>* __restrict__ out_c, T* __restrict__ out_p,
+                   double* __restrict__ band_sum) {
+    constexpr int TAPS = CwtFastCfg<T>::TAPS, PER = CwtFastCfg<T>::PER, NSUB = 8 / PER, J0 = TAPS / 2 - 1;
+    // one pad slot per 8 decimated samples: at small D the lanes of a warp start their windows PER samples apart
+    __shared__ cplx<T> seg[(CWTF_SPAN * CWTF_TILE / 4 + TAPS) * 9 / 8 + 2];
+    __shared__ double scratch[32];
+    const int D = 1 << logD, logK = geo.logL - logD;
+    const i64 K = 1ll << logK, N = geo.n_points;
+    const i64 span0 = (i64)blockIdx.x * (CWTF_SPAN * CWTF_TILE);
+    const i64 left = (N - span0 + CWTF_TILE - 1) / CWTF_TILE;
+    const int ntile = left < CWTF_SPAN ? (int)left : CWTF_SPAN;
+    const int bi = blockIdx.y, chan = blockIdx.z, band = ids[bi];
+    // carrier bin of the band (0 without a table: the decimated samples are the output's own baseband)
+    const unsigned long long kc = kc_of_band ? (unsigned long long)kc_of_band[(size_t)band * kc_stride] : 0ull;
+    const cplx<T>* src = dec + (((i64)bi * geo.n_channels + chan) << logK);
+    const i64 m_base = (span0 >> logD) - J0;
+    const int nseg = ((ntile * CWTF_TILE) >> logD) + TAPS;
+    for (int i = threadIdx.x; i < nseg; i += blockDim.x) seg[i + (i >> 3)] = src[(m_base + i) & (K - 1)];
+    __syncthreads();
+    const i64 row = ((i64)chan * geo.n_bands + band) * N;
+    const int p = threadIdx.x & (D - 1);
+    const int MT = CWTF_TILE >> logD;                       // decimated samples per tile
+    T cf[TAPS];
+#pragma unroll
+    for (int j = 0; j < TAPS; ++j) cf[j] = coef[(j << logD) + p];
+    // carrier exp(2 pi i k_c n / L) at n = m D + p: exact at the first sample of a run, stepped by exp(2 pi i k_c D / L)
+    const unsigned long long Lmask = (1ull << geo.logL) - 1ull;
+    const cplx<T> step = unit_root<T>((kc << logD) & Lmask, geo.logL);
+    double acc = 0.0;
+    for (int tl = 0; tl < ntile; ++tl) {
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) {
+            const int m0 = tl * MT + sub * (MT / NSUB) + (threadIdx.x >> logD) * PER;
+            cplx<T> win[PER + TAPS - 1];
+#pragma unroll
+            for (int j = 0; j < PER + TAPS - 1; ++j) win[j] = seg[m0 + j + ((m0 + j) >> 3)];
+            const i64 n0 = span0 + ((i64)m0 << logD) + p;
+            cplx<T> car = mk<T>((T)1, (T)0);
+            if (out_c) car = unit_root<T>((kc * (unsigned long long)n0) & Lmask, geo.logL);
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                T re = (T)0, im = (T)0;
+#pragma unroll
+                for (int j = 0; j < TAPS; ++j) { re += cf[j] * win[i + j].re; im += cf[j] * win[i + j].im; }
+                const i64 n = n0 + ((i64)i << logD);
+                if (n < N) {
+                    const T pw = re * re + im * im;
+                    if (out_c) out_c[row + n] = mk<T>(re, im) * car;
+                    if (out_p) out_p[row + n] = pw;
+                    acc += (double)pw;
+                }
+                if (out_c) car = car * step;
+            }
+        }
+    }
+    if (band_sum) {
+        acc = block_sum(acc, scratch);
+        if (threadIdx.x == 0) atomicAdd(&band_sum[(i64)chan * geo.n_bands + band], acc);
+    }
+}
+
+}  // namespace qi

@@ -27,23 +27,28 @@ template <typename T> struct StftLaunch {
     static constexpr int min_ctas = sizeof(T) == 8 ? 1 : 2;
     static constexpr size_t budget = sizeof(T) == 8 ? 200 * 1024 : 100 * 1024;
 };
+// pitch (elements) between the single-column tiles of the STFT kernels: the padded tile, made odd so that the lanes of the
+// Hermitian split (which run along the tiles) start in different banks
+QI_HD int stft_tile_pitch(int R) { return pad8(R) | 1; }
+
 template <typename T>
 __global__ void __launch_bounds__(StftLaunch<T>::threads, StftLaunch<T>::min_ctas)
 stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g, cplx<T>* __restrict__ out,
             double* __restrict__ psd_acc) {
     QI_DYN_SMEM(smem_raw);
     const int R = 1 << g.logF;
-    const int TC = g.TC, TP = TC + 1;
+    // TC single-column tiles (two real frames each) in the padded layout of tile_fft<.., true>, PT elements apart
+    const int TC = g.TC, PT = stft_tile_pitch(R);
     const int logTC = 31 - __clz(TC);
     cplx<T>* tile = reinterpret_cast<cplx<T>*>(smem_raw);
-    cplx<T>* tw = tile + (size_t)R * TP;
+    cplx<T>* tw = tile + (size_t)TC * PT;
     T* means = reinterpret_cast<T*>(tw + R);              // 2*TC means
     double* bsum = reinterpret_cast<double*>(means + 2 * TC);   // 2*TC + 16 hop-block sums (fused path)
     const i64 chan = blockIdx.y;
     const i64 frame0 = (i64)blockIdx.x * (2 * TC);
     const T* x = sig + chan * g.sig_stride;
 
-    fill_twiddles<T>(tw, g.logF);
+    fill_stage_twiddles<T>(tw, g.logF);
     // gather (lanes along the sample axis -> coalesced global reads)
     // interior CTAs (every frame exists and lies inside the record) take the path without bounds checks
     const i64 first = frame0 * g.hop - g.pad_left;
@@ -109,7 +114,7 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
                         v.re = (v.re - means[2 * c]) * w;
                         v.im = (v.im - means[2 * c + 1]) * w;
                     }
-                    tile[r * TP + c] = v;
+                    tile[c * PT + pad8(r)] = v;
                 }
             }
         }
@@ -124,7 +129,7 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
                 if (fa < g.n_frames && pa >= 0 && pa < g.n_points) va = x[pa];
                 if (fb < g.n_frames && pb >= 0 && pb < g.n_points) vb = x[pb];
             }
-            tile[r * TP + c] = mk<T>(va, vb);
+            tile[c * PT + pad8(r)] = mk<T>(va, vb);
         }
     }
     __syncthreads();
@@ -136,7 +141,7 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
             if (g.detrend) {
                 const int c = col >> 1;
                 for (int r = lane; r < g.nperseg; r += 32) {
-                    const cplx<T> v = tile[r * TP + c];
+                    const cplx<T> v = tile[c * PT + pad8(r)];
                     s += (double)((col & 1) ? v.im : v.re);
                 }
             }
@@ -144,18 +149,19 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
             if (lane == 0) means[col] = (T)(s / (double)g.nperseg);
         }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < g.nperseg * TC; idx += blockDim.x) {
-            const int c = idx & (TC - 1);                   // TC is a power of two
-            const int r = idx >> logTC;
-            const T w = window[r];
-            cplx<T> v = tile[r * TP + c];
-            v.re = (v.re - means[2 * c]) * w;
-            v.im = (v.im - means[2 * c + 1]) * w;
-            tile[r * TP + c] = v;
+        for (int c = 0; c < TC; ++c) {                      // lanes along the samples of one tile
+            const T m0 = means[2 * c], m1 = means[2 * c + 1];
+            for (int r = threadIdx.x; r < g.nperseg; r += blockDim.x) {
+                const T w = window[r];
+                cplx<T> v = tile[c * PT + pad8(r)];
+                v.re = (v.re - m0) * w;
+                v.im = (v.im - m1) * w;
+                tile[c * PT + pad8(r)] = v;
+            }
         }
         __syncthreads();
     }
-    tile_fft<T, FFT_FWD>(tile, tw, g.logF, TC, TP);
+    tile_fft<T, FFT_FWD, true>(tile, tw, g.logF, TC, PT);
     // Hermitian split + store, lanes along frames (time is the fastest output axis)
     const int K = (R >> 1) + 1;
     const T sc = (T)g.scale;
@@ -165,8 +171,8 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
         const bool active = idx < total;
         const int c = idx & (TC - 1);
         const int k = active ? idx >> logTC : 0;
-        const cplx<T> z1 = tile[(int)brev_bits((unsigned)k, g.logF) * TP + c];
-        const cplx<T> z2 = tile[(int)brev_bits((unsigned)((R - k) & (R - 1)), g.logF) * TP + c];
+        const cplx<T> z1 = tile[c * PT + pad8((int)brev_bits((unsigned)k, g.logF))];
+        const cplx<T> z2 = tile[c * PT + pad8((int)brev_bits((unsigned)((R - k) & (R - 1)), g.logF))];
         cplx<T> xa = mk<T>((T)0.5 * (z1.re + z2.re), (T)0.5 * (z1.im - z2.im));
         cplx<T> xb = mk<T>((T)0.5 * (z1.im + z2.im), (T)-0.5 * (z1.re - z2.re));
         if (g.roll) {               // segment rotated left by roll samples: bin k times exp(+2 pi i k roll / nfft)
@@ -203,7 +209,7 @@ static int stft_impl(const void* sig, i64 C, i64 n_points, i64 stride, const voi
     // <= ~100 KB per CTA so that two CTAs (2 x 512 threads) share an SM; fall back to one big CTA for long FFTs
     size_t budget = StftLaunch<T>::budget;
     int TC = 16;
-    auto need = [&](int tc) { return ((size_t)nfft * (tc + 2)) * sizeof(cplx<T>) + 2 * tc * sizeof(T) + (2 * tc + 16) * sizeof(double) + 64; };
+    auto need = [&](int tc) { return ((size_t)stft_tile_pitch(nfft) * tc + nfft) * sizeof(cplx<T>) + 2 * tc * sizeof(T) + (2 * tc + 16) * sizeof(double) + 64; };
     while (TC > 2 && need(TC) > budget) TC >>= 1;
     if (need(TC) > budget) { budget = 200 * 1024; while (TC > 1 && need(TC) > budget) TC >>= 1; }
     if (need(TC) > budget) return QI_ERR_UNSUPPORTED;

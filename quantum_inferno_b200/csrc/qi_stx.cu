@@ -7,12 +7,14 @@
 #include "qi_fft.cuh"
 #include "qi_host.h"
 #include "qi_tfr.cuh"
+#include "qi_interp.cuh"
 
 #include <vector>
 
 namespace qi {
 
-struct DevStxBand { double q; long long shift; long long kmax; };   // q = sigma*2*pi/n; |k| > kmax: the window underflows to 0
+// q = sigma*2*pi/n; |k| > kmax: the window underflows to 0; |k| > dec_kmax: below the cut of the band-limited route
+struct DevStxBand { double q; long long shift; long long kmax; long long dec_kmax; };
 
 template <typename T> struct SrcStxSpec {
     const cplx<T>* spec; const DevStxBand* bands; int band0; CwtGeom geo;
@@ -32,6 +34,26 @@ template <typename T> struct SrcStxSpec {
     }
 };
 
+// Band-limited route (both dtypes; the float32-only method="multirate" further down predates it and keeps its packed
+// interpolator).  A Stockwell voice is a BASEBAND signal: X[k + shift] exp(-0.5 (q k)^2) is below exp(-0.5 U^2) of its peak
+// beyond |k| > kmax = U / q.  The K = 2^m >= RHO (2 kmax + 4) bins around zero, inverse-transformed at length K, are the
+// voice at every D = n / K-th sample exactly; qi_interp.cuh brings it to the full rate (no carrier to put back).
+template <typename T> struct SrcStxDecT {
+    const cplx<T>* spec; const DevStxBand* bands; const int* ids; int n_channels, logN, logK;
+    QI_DEV cplx<T> load(i64 batch, i64 e) const {
+        const i64 chan = batch % n_channels;
+        const DevStxBand b = bands[ids[batch / n_channels]];
+        const i64 K = 1ll << logK, n = 1ll << logN;
+        const i64 k = (i64)brev_bits((unsigned)e, logK);
+        const i64 ks = (k < (K >> 1)) ? k : k - K;
+        if (ks > b.dec_kmax || -ks > b.dec_kmax) return mk<T>((T)0, (T)0);
+        const i64 ksrc = (ks + b.shift) & (n - 1);
+        const cplx<T> X = spec[(chan << logN) + (i64)brev_bits((unsigned)ksrc, logN)];
+        const T u = (T)b.q * (T)ks;
+        return X * (exp((T)-0.5 * u * u) * (T)(1.0 / (double)n));
+    }
+};
+
 template <typename T>
 __global__ void stx_windows_kernel(const DevStxBand* bands, i64 n, cplx<T>* out) {
     const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -42,7 +64,7 @@ __global__ void stx_windows_kernel(const DevStxBand* bands, i64 n, cplx<T>* out)
     out[(i64)blockIdx.y * n + k] = mk<T>(exp((T)-0.5 * u * u), (T)0);
 }
 
-struct StxLayout { int logL; i64 L; size_t off_bands, off_spec, off_work, total; int group; };
+struct StxLayout { int logL; i64 L; size_t off_bands, off_spec, off_work, off_ids, off_coef, total; int group; };
 
 template <typename T> static StxLayout stx_layout(i64 C, i64 N, int B, int group) {
     StxLayout lo;
@@ -56,13 +78,16 @@ template <typename T> static StxLayout stx_layout(i64 C, i64 N, int B, int group
     lo.off_bands = o; o = align_up(o + sizeof(DevStxBand) * (size_t)B, 256);
     lo.off_spec = o; o = align_up(o + sizeof(cplx<T>) * (size_t)C * lo.L, 256);
     lo.off_work = o; o = align_up(o + sizeof(cplx<T>) * (size_t)group * C * lo.L, 256);
+    lo.off_ids = o; o = align_up(o + sizeof(int) * (size_t)B, 256);
+    lo.off_coef = o; o = align_up(o + sizeof(T) * CwtFastCfg<T>::TAPS * (size_t)(CWTF_MAX_LOGD + 1) * (1u << CWTF_MAX_LOGD), 256);
     lo.total = o;
     return lo;
 }
 
 // u_zero: |u| from which exp(-0.5 u^2) is exactly 0 in the arithmetic type (below the smallest subnormal, with margin:
 // float32 exp(-104) = 6.8e-46 < 2^-150; float64 exp(-746) < 2^-1075)
-static void upload_stx_bands(const QiStxBand* hb, int B, i64 N, double u_zero, DevStxBand* d_bands, cudaStream_t st) {
+static void upload_stx_bands(const QiStxBand* hb, int B, i64 N, double u_zero, DevStxBand* d_bands, cudaStream_t st,
+                             double u_cut = 0.0) {
     std::vector<DevStxBand> db(B);
     for (int b = 0; b < B; ++b) {
         db[b].q = hb[b].sigma * 2.0 * M_PI / (double)N;
@@ -70,13 +95,16 @@ static void upload_stx_bands(const QiStxBand* hb, int B, i64 N, double u_zero, D
         const double aq = fabs(db[b].q);
         const double km = aq > 0.0 ? ceil(u_zero / aq) + 2.0 : (double)N;
         db[b].kmax = km < (double)N ? (long long)km : (long long)N;
+        const double kd = (aq > 0.0 && u_cut > 0.0) ? ceil(u_cut / aq) + 1.0 : (double)N;
+        db[b].dec_kmax = kd < (double)N ? (long long)kd : (long long)N;
     }
     stage_to_device(d_bands, db.data(), sizeof(DevStxBand) * (size_t)B, st);
 }
 
 template <typename T>
 static int stx_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiStxBand* hb, int B, void* out_c,
-                        void* out_p, double* band_sum, void* ws, size_t ws_bytes, int group, cudaStream_t st) {
+                        void* out_p, double* band_sum, void* ws, size_t ws_bytes, int group, cudaStream_t st, bool fast) {
+    typedef CwtFastCfg<T> Cfg;
     const StxLayout lo = stx_layout<T>(C, N, B, group);
     if (ws_bytes < lo.total) return QI_ERR_WORKSPACE;
     if (C > 65535) return QI_ERR_UNSUPPORTED;
@@ -84,7 +112,7 @@ static int stx_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiStxBa
     DevStxBand* d_bands = reinterpret_cast<DevStxBand*>(base + lo.off_bands);
     cplx<T>* spec = reinterpret_cast<cplx<T>*>(base + lo.off_spec);
     cplx<T>* work = reinterpret_cast<cplx<T>*>(base + lo.off_work);
-    upload_stx_bands(hb, B, N, sizeof(T) == 4 ? 14.5 : 38.7, d_bands, st);
+    upload_stx_bands(hb, B, N, sizeof(T) == 4 ? 14.5 : 38.7, d_bands, st, Cfg::U_CUT);
 
     CwtGeom geo;
     geo.n_points = N; geo.n_channels = C; geo.n_bands = B; geo.logL = lo.logL;
@@ -105,8 +133,69 @@ static int stx_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiStxBa
         }
     }
     if (band_sum) cudaMemsetAsync(band_sum, 0, sizeof(double) * (size_t)C * B, st);
-    for (int band0 = 0; band0 < B; band0 += lo.group) {
-        const int g = (B - band0 < lo.group) ? (B - band0) : lo.group;
+    // ---- band-limited route: bands whose window fits K <= n / 4 bins, grouped by K
+    std::vector<int> logK(B, lo.logL), dec_ids;
+    if (fast && lo.logL >= 13) {
+        for (int b = 0; b < B; ++b) {
+            const double aq = fabs(hb[b].sigma * 2.0 * M_PI / (double)N);
+            if (!(aq > 0.0)) continue;
+            const double need = Cfg::RHO * (2.0 * (ceil(Cfg::U_CUT / aq) + 1.0) + 4.0);
+            int lk = lo.logL - CWTF_MAX_LOGD;
+            if (lk < 6) lk = 6;
+            while (lk < lo.logL && (double)(1ll << lk) < need) ++lk;
+            if (lk <= lo.logL - 2) logK[b] = lk;
+        }
+        for (int lk = 0; lk < lo.logL; ++lk)
+            for (int b = 0; b < B; ++b) if (logK[b] == lk) dec_ids.push_back(b);
+    }
+    if (!dec_ids.empty()) {
+        int* d_ids = reinterpret_cast<int*>(base + lo.off_ids);
+        T* coef = reinterpret_cast<T*>(base + lo.off_coef);
+        stage_to_device(d_ids, dec_ids.data(), sizeof(int) * dec_ids.size(), st);
+        unsigned need_mask = 0;
+        for (int b : dec_ids) need_mask |= 1u << (lo.logL - logK[b]);
+        prof_set_category(QI_CAT_OTHER);
+        QI_LAUNCH((cwtf_coef_kernel<T>), dim3((unsigned)((Cfg::TAPS << CWTF_MAX_LOGD) / 256 + 1), (unsigned)(CWTF_MAX_LOGD + 1)),
+                  dim3(256), 0, st, coef, need_mask, 1.0 / cwtf_bessel_i0(Cfg::BETA));
+        const size_t work_elems = (size_t)lo.group * C * lo.L;
+        size_t pos = 0;
+        while (pos < dec_ids.size()) {
+            const int lk = logK[dec_ids[pos]];
+            size_t end = pos;
+            while (end < dec_ids.size() && logK[dec_ids[end]] == lk) ++end;
+            const int logD = lo.logL - lk;
+            const T* cf = coef + (size_t)logD * Cfg::TAPS * (1u << CWTF_MAX_LOGD);
+            const FftPlan pk = make_plan(lk, (int)sizeof(cplx<T>));
+            const i64 K = 1ll << lk;
+            for (size_t sub = pos; sub < end;) {
+                i64 gs = (i64)(end - sub);
+                while (gs > 1 && (gs * C > 65535 || (size_t)gs * C * K > work_elems)) --gs;
+                if (gs * C > 65535 || (size_t)gs * C * K > work_elems) return QI_ERR_WORKSPACE;
+                const i64 nbd = gs * C;
+                SrcStxDecT<T> s1{spec, d_bands, d_ids + sub, (int)C, lo.logL, lk};
+                for (int p = pk.npass - 1; p >= 0; --p) {
+                    const bool first = (p == pk.npass - 1);
+                    SrcComplex<T> s2{work, K};
+                    DstComplex<T> dw{work, K, one};
+                    prof_set_category(first ? QI_CAT_INV_FIRST : QI_CAT_INV_MID);
+                    if (first) launch_pass<T, FFT_INV>(pk, p, nbd, s1, dw, 0, st);
+                    else launch_pass<T, FFT_INV>(pk, p, nbd, s2, dw, 0, st);
+                }
+                prof_set_category(QI_CAT_INV_LAST);
+                dim3 grid((unsigned)((N + CWTF_SPAN * CWTF_TILE - 1) / (CWTF_SPAN * CWTF_TILE)), (unsigned)gs, (unsigned)C);
+                QI_LAUNCH((cwtf_interp_kernel<T>), grid, dim3(256), 0, st, (const cplx<T>*)work, (const int*)(d_ids + sub),
+                          (const long long*)nullptr, 0, geo, logD, cf, static_cast<cplx<T>*>(out_c), static_cast<T*>(out_p),
+                          band_sum);
+                sub += (size_t)gs;
+            }
+            pos = end;
+        }
+    }
+    // ---- full-length passes: maximal runs of consecutive bands that took no other route
+    for (int band0 = 0; band0 < B;) {
+        if (logK[band0] != lo.logL) { ++band0; continue; }
+        int g = 1;
+        while (band0 + g < B && g < lo.group && logK[band0 + g] == lo.logL) ++g;
         const i64 nb = (i64)g * C;
         for (int p = np - 1; p >= 0; --p) {
             const bool first = (p == np - 1), last = (p == 0);
@@ -120,6 +209,7 @@ static int stx_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiStxBa
             else if (last) launch_pass<T, FFT_INV>(plan, p, nb, s2, d2, 256, st);
             else launch_pass<T, FFT_INV>(plan, p, nb, s2, d1, 0, st);
         }
+        band0 += g;
     }
     prof_set_category(QI_CAT_OTHER);
     return check_cuda("qi_stx_fft");
@@ -428,6 +518,7 @@ stxmr_interp_kernel(const cplx<float>* __restrict__ dec, const int* __restrict__
 
     size_t qi_stx_workspace_bytes(int64_t C, int64_t N, int B, int group, int dtype) {
         if (C <= 0 || N <= 0 || B <= 0) return 0;
+        if (group < 0) group = -group;
         return dtype == QI_F32 ? qi::stx_layout<float>(C, N, B, group).total : qi::stx_layout<double>(C, N, B, group).total;
     }
 
@@ -437,8 +528,10 @@ stxmr_interp_kernel(const cplx<float>* __restrict__ dec, const int* __restrict__
         if (N & (N - 1)) return QI_ERR_ARG;
         if (N > (1ll << 30)) return QI_ERR_UNSUPPORTED;
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        if (dtype == QI_F32) return qi::stx_fft_impl<float>(sig, C, N, stride, bands, B, out_tfr, out_power, band_sum, ws, ws_bytes, group, st);
-        if (dtype == QI_F64) return qi::stx_fft_impl<double>(sig, C, N, stride, bands, B, out_tfr, out_power, band_sum, ws, ws_bytes, group, st);
+        const bool fast = group >= 0;                  // a negative bands_per_group keeps every band on the full-length passes
+        if (group < 0) group = -group;
+        if (dtype == QI_F32) return qi::stx_fft_impl<float>(sig, C, N, stride, bands, B, out_tfr, out_power, band_sum, ws, ws_bytes, group, st, fast);
+        if (dtype == QI_F64) return qi::stx_fft_impl<double>(sig, C, N, stride, bands, B, out_tfr, out_power, band_sum, ws, ws_bytes, group, st, fast);
         return QI_ERR_ARG;
     }
 

@@ -79,3 +79,25 @@ def check_reference_error_paths():
         styx_fft.stft_from_sig(x, FS, 3, center_frequency_hz=0.5)       # needs a window far longer than 256 samples
     with pytest.raises(ValueError):
         cwt_atoms.cwt_chirp_complex(3, x, 10.0, FS, cwt_type="nope")
+
+
+def check_stx_band_limited_routes(log2n, channels=1):
+    """styx_stx.stx_complex_any_scale_pow2 (reference styx_stx.py:195-236) on records long enough for the band-limited
+    route of csrc/qi_stx.cu (decimated voices + Kaiser interpolation): against the full-length passes and the oracle."""
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import styx_stx
+    n = 1 << log2n
+    k = np.arange(n)
+    x = np.stack([np.cos(2 * np.pi * (40.0 + 7 * c) / FS * k) + 0.3 * np.random.default_rng(c).standard_normal(n)
+                  for c in range(channels)])
+    _, _, ref = orc.stx_complex_any_scale_pow2(3, x[-1], FS)
+    for dtype, tol in (("float64", 1e-10), ("float32", 2e-5)):
+        f, _, c = styx_stx.stx_complex_any_scale_pow2(3, x, FS, dtype=dtype)
+        _, _, cp = styx_stx.stx_complex_any_scale_pow2(3, x, FS, dtype=dtype, method="plain")
+        per_band = np.max(np.abs(c - cp), axis=-1) / np.max(np.abs(cp), axis=-1)
+        assert per_band.max() < tol, (dtype, per_band)
+        assert np.any(per_band > 0)                               # some bands did take another route
+        err = np.max(np.abs(c[-1] - ref), axis=-1) / np.max(np.abs(ref), axis=-1)
+        assert err.max() < tol, (dtype, err)
+        _, _, p = styx_stx.stx_complex_any_scale_pow2(3, x, FS, dtype=dtype, outputs="power")
+        assert np.max(np.abs(p[-1] - np.abs(ref) ** 2)) / np.max(np.abs(ref) ** 2) < 4 * tol

@@ -383,3 +383,8 @@ def test_shannon_1d_all_attributes(golden):
 def test_reference_error_paths():
     from tests import _extra_checks as ec
     ec.check_reference_error_paths()
+
+
+def test_stx_band_limited_routes():
+    from tests import _extra_checks as ec
+    ec.check_stx_band_limited_routes(13, channels=2)

@@ -626,3 +626,8 @@ def test_shannon_1d_all_attributes(torch_cuda, golden):
 def test_reference_error_paths(torch_cuda):
     from tests import _extra_checks as ec
     ec.check_reference_error_paths()
+
+
+def test_stx_band_limited_routes(torch_cuda):
+    from tests import _extra_checks as ec
+    ec.check_stx_band_limited_routes(18, channels=3)

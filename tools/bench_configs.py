@@ -1,6 +1,7 @@
 """
 Secondary measurements for the other BASELINE.json configs (the headline line is bench.py).  One GPU, the per-GPU
-share of each config, CUDA-event timing, inputs resident in HBM, 3 warm-ups.  Prints one JSON object per config.
+share of each config, CUDA-event timing, inputs resident in HBM, 3 warm-ups.  Prints one JSON object per config, with
+the SM clocks / throttle reasons nvidia-smi reported while it ran (``clocks``, as in bench.py).
 
     python tools/bench_configs.py [cfg1 cfg2 cfg3 cfg4 cfg5]
 """
@@ -14,7 +15,7 @@ import torch
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
-from bench import FS, synth_batch_torch  # noqa: E402
+from bench import FS, ClockSampler, synth_batch_torch  # noqa: E402
 from quantum_inferno_b200 import cwt_entropy, styx_cwt, styx_fft, styx_stx  # noqa: E402
 
 DEV = torch.device("cuda", 0)
@@ -194,7 +195,10 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg1", "cfg2", "cfg3", "cfg4"]
     for name in which:
         t0 = time.time()
+        sampler = ClockSampler(0)                 # SM clock and throttle reasons while this configuration runs
+        sampler.start()
         res = globals()[name]()
+        res["clocks"] = sampler.stop()
         res["wall_s"] = time.time() - t0
         print(json.dumps(res), flush=True)
         torch.cuda.empty_cache()
