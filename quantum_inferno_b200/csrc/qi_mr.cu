@@ -38,7 +38,6 @@
 #include "qi_halfband_coeffs.h"
 #include "qi_mr_expand.cuh"
 #include "qi_mr_level2k.cuh"
-#include "qi_mr_autocorr.cuh"
 
 #include <vector>
 #include <math.h>
@@ -294,8 +293,7 @@ struct MrPlan {
     std::vector<MrLevelGeom> levels;
     int n_edge;                         // edge rows = the first n_edge bands; their source bands are B .. B + n_edge - 1
     i64 n_prefix;
-    size_t off_bands, off_list, off_deep, off_tw, off_pyr, off_tables, off_w, off_mid, off_prefix, off_group, off_acorr, total;
-    int acorr_lags, acorr_stride;       // lags of the record's autocorrelation the level-0 bands need (0: none), row stride
+    size_t off_bands, off_list, off_deep, off_tw, off_pyr, off_tables, off_w, off_mid, off_prefix, off_group, total;
     i64 pyr_per_chan, w_total, mid_total;
 };
 
@@ -435,16 +433,6 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl, bool all
     pl.off_deep = o; o = align_up(o + sizeof(int) * (size_t)(B + E + 1), 256);
     pl.off_prefix = o; o = align_up(o + sizeof(double) * 2 * (size_t)pl.n_prefix * (size_t)C * (E > 0 ? 1 : 0), 256);
     pl.off_group = o; o = align_up(o + sizeof(float2) * (size_t)(N / 8) * (size_t)C * (E > 0 ? 1 : 0), 256);
-    // autocorrelation of the record for the level-0 band powers (qi_mr_autocorr.cuh)
-    pl.acorr_lags = 0;
-    for (int b = 0; b < B; ++b)
-        if (hb[b].level == 0) {
-            int h = (int)ceil(5.2 * hb[b].scale) + 1;
-            if (h > 2047) h = 2047;
-            if (2 * h + 1 > pl.acorr_lags) pl.acorr_lags = 2 * h + 1;
-        }
-    pl.acorr_stride = ((pl.acorr_lags + 15) / 16 / AC_TB + 1) * AC_LAGS + 32;
-    pl.off_acorr = o; o = align_up(o + sizeof(double) * (size_t)pl.acorr_stride * C * (pl.acorr_lags > 0 ? 1 : 0), 256);
     pl.off_tw = o; o = align_up(o + sizeof(float4) * (size_t)L2K_TW_TOTAL, 256);
     pl.off_pyr = o; o = align_up(o + sizeof(float) * (size_t)pl.pyr_per_chan * C, 256);
     pl.off_tables = o; o = align_up(o + sizeof(cplx<float>) * (size_t)toff, 256);
@@ -460,12 +448,11 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl, bool all
 // band-limited below that level's Nyquist rate,
 //     sum_{n<N} P(n) ~= h * sum_q P(h q) + (h-1)/2 (P(N) - P(0)) - (h^2-1)/12 (P'(N) - P'(0))      (Euler-Maclaurin,
 // P' by central differences; deep bands use their level-MR_LMID copy: smaller h => smaller remainder).
-// Level-0 bands enter with their exact sums, or with the prediction of qi_mr_autocorr.cuh when their convolution runs
-// after this kernel (fused information mode).  total[c] = sum over bands.
+// Level-0 bands enter with their exact sums.  total[c] = sum over bands.
 __global__ void mr_total_kernel(const MrDevBand* __restrict__ bands, int B, i64 n_points,
                                 const cplx<float>* __restrict__ wbuf, const cplx<float>* __restrict__ midbuf,
                                 const double* __restrict__ band_sum, double* __restrict__ band_sum_est,
-                                double* __restrict__ total, int level0_predicted) {
+                                double* __restrict__ total) {
     __shared__ double scratch[32];
     const i64 c = blockIdx.x;
     double s = 0.0;
@@ -473,8 +460,7 @@ __global__ void mr_total_kernel(const MrDevBand* __restrict__ bands, int B, i64 
         const MrDevBand band = bands[b];
         double est;
         if (band.level == 0) {
-            // exact sum left by the convolution, or (the convolution has not run yet) the autocorrelation prediction
-            est = level0_predicted ? band_sum_est[c * B + b] : band_sum[c * B + b];
+            est = band_sum[c * B + b];
         } else {
             const int lvl = band.level > MR_LMID ? MR_LMID : band.level;
             const i64 m = n_points >> lvl;
@@ -575,25 +561,6 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
             QI_LAUNCH(mr_prefix_scan_kernel, dim3((unsigned)(2 * C)), dim3(1024), 0, st, d_prefix, pl.n_prefix);
         }
     }
-    // level-0 band powers ahead of their convolution (fused information mode, 2048-point level-0 blocks): the level-0
-    // convolution then runs AFTER mr_total_kernel and writes the information plane itself
-    const MrLevelGeom* g_level0 = nullptr;
-    for (const MrLevelGeom& g0 : pl.levels) if (g0.level == 0) g_level0 = &g0;
-    const bool predict0 = fused && g_level0 && g_level0->logF == L2K_LOGF && g_level0->band_count <= L2K_MAXB &&
-                          pl.acorr_lags > 0 && (N % AC_TS) == 0;
-    if (predict0 && do_front) {
-        double* d_acorr = reinterpret_cast<double*>(base + pl.off_acorr);
-        cudaMemsetAsync(d_acorr, 0, sizeof(double) * (size_t)pl.acorr_stride * C, st);
-        const int passes = (pl.acorr_lags + 15) / 16 / AC_TB + 1;
-        i64 per_chan = (148 * 6 + C * passes - 1) / (C * passes);                // ~6 CTAs per SM in total
-        if (per_chan > N / AC_TS) per_chan = N / AC_TS;
-        QI_LAUNCH(mr_autocorr_kernel, dim3((unsigned)per_chan, (unsigned)C, (unsigned)passes), dim3(AC_THREADS), 0, st, sig,
-                  stride, N, d_acorr, pl.acorr_stride, pl.acorr_lags);
-        const size_t smem = sizeof(double2) * (size_t)pl.acorr_lags;
-        QI_LAUNCH(mr_level0_predict_kernel, dim3((unsigned)g_level0->band_count, (unsigned)C), dim3(256), smem, st,
-                  (const MrDevBand*)d_bands, g_level0->band_first, B, N, 2047, sig, stride, (const double*)d_acorr,
-                  pl.acorr_stride, band_sum_est);
-    }
     // P: pyramid
     for (int l = 1; do_front && l <= pl.cap; ++l) {
         const float* src = l == 1 ? sig : pyr + pl.lvl_off[l - 1];
@@ -618,11 +585,9 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
                   L2K_SMEM, st, multi, (const MrDevBand*)d_bands, (const cplx<float>*)tables, (const float4*)tw2k, wbuf);
         multi.n = 0;
     };
-    const MrInfoOut no_info = {nullptr, nullptr, nullptr, 0.0f};
     for (const MrLevelGeom& g0 : pl.levels) {
         if (g0.level == 0) { level0_first = g0.band_first; level0_count = g0.band_count; }
         if (!do_front) continue;
-        if (g0.level == 0 && predict0) continue;             // runs after mr_total_kernel, see below
         MrLevelGeom g = g0;
         const float* x = g.level ? pyr + pl.lvl_off[g.level] : sig;
         g.x_stride = g.level ? pl.pyr_per_chan : stride;
@@ -652,10 +617,10 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
 #endif
             if (g.env)
                 QI_LAUNCH((mr_level2k_kernel<true>), grid2, dim3(L2K_THREADS), L2K_SMEM, st, x, g, (const MrDevBand*)d_bands,
-                          (const cplx<float>*)tables, (const float4*)tw2k, wbuf, out_power, out_complex, sum_dst, (int)ppc, no_info);
+                          (const cplx<float>*)tables, (const float4*)tw2k, wbuf, out_power, out_complex, sum_dst, (int)ppc);
             else
                 QI_LAUNCH((mr_level2k_kernel<false>), grid2, dim3(L2K_THREADS), L2K_SMEM, st, x, g, (const MrDevBand*)d_bands,
-                          (const cplx<float>*)tables, (const float4*)tw2k, wbuf, out_power, out_complex, sum_dst, (int)ppc, no_info);
+                          (const cplx<float>*)tables, (const float4*)tw2k, wbuf, out_power, out_complex, sum_dst, (int)ppc);
             continue;
         }
         const i64 gx = (g.n_blocks + g.TC - 1) / g.TC;
@@ -716,31 +681,14 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
             // raw sums are in band_sum_est (level kernels / the MID pass); finish the estimates and the totals
             QI_LAUNCH(mr_total_kernel, dim3((unsigned)C), dim3(128), 0, st, (const MrDevBand*)d_bands, B, N,
                       (const cplx<float>*)wbuf, (const cplx<float>*)midbuf, (const double*)band_sum, band_sum_est,
-                      total_power, predict0 ? 1 : 0);
+                      total_power);
         }
-    }
-    if (do_back && predict0) {
-        // level-0 convolution with S known: power rows, information rows, exact band sums and entropy sums in one pass
-        MrLevelGeom g = *g_level0;
-        g.x_stride = stride;
-        const i64 pairs = (g.n_blocks + 1) / 2;
-        i64 ppc = pairs * C / (148 * 2 * 8);
-        ppc = ppc < 1 ? 1 : (ppc > 4 ? 4 : ppc);
-        const i64 ctas = (pairs + ppc - 1) / ppc;
-        const MrInfoOut io = {out_info, total_power, entropy_sum, (float)eps};
-        prof_set_category(QI_CAT_INV_MID);
-#ifndef QI_EMUL
-        cudaFuncSetAttribute(mr_level2k_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2K_SMEM);
-#endif
-        QI_LAUNCH((mr_level2k_kernel<false>), dim3((unsigned)ctas, (unsigned)C), dim3(L2K_THREADS), L2K_SMEM, st, sig, g,
-                  (const MrDevBand*)d_bands, (const cplx<float>*)tables, (const float4*)tw2k, wbuf, out_power, out_complex,
-                  band_sum, (int)ppc, io);
     }
     if (do_back) {
         prof_set_category(QI_CAT_INV_LAST);
         if (!pl.expand_list.empty())
             launch_groups(pl.expand_list, d_list, 0, N, fused ? MR_MODE_POWER_INFO : MR_MODE_POWER);
-        if (fused && level0_count > 0 && !predict0) {
+        if (fused && level0_count > 0) {
             prof_set_category(QI_CAT_INFO);
             const i64 T4 = N / 4;
             i64 splits = (148 * 8 * 16 + (i64)level0_count * C - 1) / ((i64)level0_count * C);

@@ -37,7 +37,7 @@ constexpr int L2K_DEMOD = 4 * L2K_TWJ;               // float4 index of the demo
 constexpr int L2K_TW_TOTAL = 4 * L2K_TWJ + 32;       // float4 elements in the whole table
 constexpr int L2K_MAXB = 64;                         // bands per level handled by this kernel
 constexpr int L2K_THREADS = 256;
-constexpr size_t L2K_SMEM = (size_t)(2 * L2K_TILE + L2K_TW_TOTAL) * 16 + 2 * (size_t)(L2K_THREADS / 32) * L2K_MAXB * 4;
+constexpr size_t L2K_SMEM = (size_t)(2 * L2K_TILE + L2K_TW_TOTAL) * 16 + (size_t)(L2K_THREADS / 32) * L2K_MAXB * 4;
 
 // tw[m * L2K_TWJ + row] = ( w_B^(j * brev3(2m)), w_B^(j * brev3(2m+1)) ),  w_B = exp(-2 pi i / B)
 __global__ void mr_twiddle2k_kernel(float4* __restrict__ tw) {
@@ -76,15 +76,6 @@ struct MrLevelGeom {
     int x_halo;             // halo of the stored level signal (0 for level 0)
     int env;                // every band of this level is stored as a demodulated envelope at level + 1
     int no_sums;            // edge source bands (indices >= n_bands): no row of their own in the sum arrays
-};
-
-// Level 0 with the record's total power known beforehand (qi_mr_autocorr.cuh): the convolution stores the information
-// plane -log2(P / S + eps) next to the power rows and accumulates the entropy sums itself.
-struct MrInfoOut {
-    float* out_info;             // nullptr: power only
-    const double* total_power;   // S per channel
-    double* entropy_sum;         // [C][n_bands] sum_t pdf * info
-    float eps;
 };
 
 // radix-8 stage on the two columns of a float4 tile; rows base + i*H live at tile[p0 + i*STRIDE]
@@ -135,15 +126,12 @@ template <bool ENV>
 QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const MrDevBand* __restrict__ bands,
                      const cplx<float>* __restrict__ tables, const float4* __restrict__ tw_g,
                      cplx<float>* __restrict__ wbuf, float* __restrict__ out_power, cplx<float>* __restrict__ out_complex,
-                     double* __restrict__ band_sum, int pairs_per_cta, int bx, const MrInfoOut io) {
+                     double* __restrict__ band_sum, int pairs_per_cta, int bx) {
     QI_DYN_SMEM(smem_raw);
     float4* tile0 = reinterpret_cast<float4*>(smem_raw);
     float4* tile1 = tile0 + L2K_TILE;
     float4* tw = tile1 + L2K_TILE;
     float* wsum = reinterpret_cast<float*>(tw + L2K_TW_TOTAL);         // [warps][L2K_MAXB]
-    float* went = wsum + (L2K_THREADS / 32) * L2K_MAXB;                // [warps][L2K_MAXB] entropy sums (level 0 + info)
-    const bool with_info = !ENV && io.out_info != nullptr;
-    const float inv_total = with_info ? (float)(1.0 / io.total_power[blockIdx.y]) : 0.0f;
     const int t = threadIdx.x;
     const int warp = t >> 5, lane = t & 31;
     const i64 chan = blockIdx.y;
@@ -152,7 +140,7 @@ QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const Mr
     const float* xs = x + chan * g.x_stride;
 
     for (int i = t; i < L2K_TW_TOTAL; i += L2K_THREADS) tw[i] = tw_g[i];
-    for (int i = t; i < 2 * (L2K_THREADS / 32) * L2K_MAXB; i += L2K_THREADS) wsum[i] = 0.0f;
+    for (int i = t; i < (L2K_THREADS / 32) * L2K_MAXB; i += L2K_THREADS) wsum[i] = 0.0f;
 
     // per-thread tile addresses (padded rows), fixed for the whole kernel
     const int pA = t + (t >> 3);                                           // stage B=2048: rows t + 256 i   -> + 288 i
@@ -401,7 +389,7 @@ QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const Mr
                 }
                 dit8<float, FFT_INV>(a); dit8<float, FFT_INV>(c);
             }
-            float acc = 0.0f, ent = 0.0f;
+            float acc = 0.0f;
 #pragma unroll
             for (int col = 0; col < 2; ++col) {
                 const i64 blk = blk0 + col;
@@ -418,12 +406,6 @@ QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const Mr
                             if (out_power) out_power[cell0 + t + 256 * i] = pw;
                             if (out_complex) out_complex[cell0 + t + 256 * i] = y[i];
                             acc += pw;
-                            if (with_info) {
-                                const float pdf = fmaf(pw, inv_total, io.eps);
-                                const float nf = -mr_fast_log2f(pdf);
-                                io.out_info[cell0 + t + 256 * i] = nf;
-                                ent = fmaf(pdf, nf, ent);          // eps inside the weight, as in the fused expansion
-                            }
                         }
                     }
                 } else {
@@ -444,19 +426,14 @@ QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const Mr
                 acc = warp_sum(acc);
                 if (lane == 0) wsum[warp * L2K_MAXB + bi] += acc;
             }
-            if (with_info) {
-                ent = warp_sum(ent);
-                if (lane == 0) went[warp * L2K_MAXB + bi] += ent;
-            }
         }
     }
-    if (band_sum || with_info) {
+    if (band_sum) {
         __syncthreads();
         if (t < g.band_count) {
-            double s = 0.0, e = 0.0;
-            for (int w = 0; w < L2K_THREADS / 32; ++w) { s += (double)wsum[w * L2K_MAXB + t]; e += (double)went[w * L2K_MAXB + t]; }
-            if (band_sum) atomicAdd(&band_sum[chan * g.n_bands + g.band_first + t], s);
-            if (with_info && io.entropy_sum) atomicAdd(&io.entropy_sum[chan * g.n_bands + g.band_first + t], e);
+            double s = 0.0;
+            for (int w = 0; w < L2K_THREADS / 32; ++w) s += (double)wsum[w * L2K_MAXB + t];
+            atomicAdd(&band_sum[chan * g.n_bands + g.band_first + t], s);
         }
     }
 }
@@ -466,8 +443,8 @@ __global__ void __launch_bounds__(L2K_THREADS, 2)
 mr_level2k_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __restrict__ bands,
                   const cplx<float>* __restrict__ tables, const float4* __restrict__ tw_g,
                   cplx<float>* __restrict__ wbuf, float* __restrict__ out_power, cplx<float>* __restrict__ out_complex,
-                  double* __restrict__ band_sum, int pairs_per_cta, MrInfoOut io) {
-    l2k_body<ENV>(x, g, bands, tables, tw_g, wbuf, out_power, out_complex, band_sum, pairs_per_cta, (int)blockIdx.x, io);
+                  double* __restrict__ band_sum, int pairs_per_cta) {
+    l2k_body<ENV>(x, g, bands, tables, tw_g, wbuf, out_power, out_complex, band_sum, pairs_per_cta, (int)blockIdx.x);
 }
 
 // The deep levels are a few CTAs each and independent of one another: one launch runs up to L2K_MULTI of them side by
@@ -489,8 +466,7 @@ mr_level2k_multi_kernel(MrMultiLevel m, const MrDevBand* __restrict__ bands, con
     while (li + 1 < m.n && (int)blockIdx.x >= m.cta_end[li]) ++li;
     const int bx = (int)blockIdx.x - (li ? m.cta_end[li - 1] : 0);
     const MrLevelGeom g = m.g[li];
-    const MrInfoOut no_info = {nullptr, nullptr, nullptr, 0.0f};
-    l2k_body<true>(m.x[li], g, bands, tables, tw_g, wbuf, nullptr, nullptr, m.sum[li], m.ppc[li], bx, no_info);
+    l2k_body<true>(m.x[li], g, bands, tables, tw_g, wbuf, nullptr, nullptr, m.sum[li], m.ppc[li], bx);
 }
 
 }  // namespace qi
