@@ -82,7 +82,8 @@ def atoms_time(bands, n_points, fs, dt, xtime=None, rt=None):
     return out
 
 
-def stx_fft(sig, bands, dt, want_complex=True, want_power=False, want_band_sum=False, rt=None, method="exact"):
+def stx_fft(sig, bands, dt, want_complex=True, want_power=False, want_band_sum=False, rt=None, method="exact",
+            out_power=None):
     """Run qi_stx_fft (method="exact": band-limited voices where the window allows, full-length passes otherwise;
     method="plain": full-length passes for every band) or qi_stx_multirate (method="multirate": float32, records of
     2^m >= 4096 samples, decimated voices + packed polyphase interpolation)."""
@@ -113,7 +114,7 @@ def stx_fft(sig, bands, dt, want_complex=True, want_power=False, want_band_sum=F
     nbytes = ws_bytes(group)
     ws = rt.workspace(nbytes)
     out_c = rt.empty((C, B, N), COMPLEX_OF[dt]) if want_complex else None
-    out_p = rt.empty((C, B, N), dt) if want_power else None
+    out_p = (out_power if out_power is not None else rt.empty((C, B, N), dt)) if want_power else None
     bsum = rt.empty((C, B), "float64") if want_band_sum else None
     rc = lib.qi_stx_fft(rt.ptr(sig), C, N, N, bands.ctypes.data, B, code, rt.ptr(out_c), rt.ptr(out_p), rt.ptr(bsum),
                         rt.ptr(ws), nbytes, -group if method == "plain" else group, rt.stream())

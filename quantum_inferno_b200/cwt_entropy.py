@@ -166,3 +166,36 @@ def cwt_power_entropy(band_order_nth: float, sig_wf, frequency_sample_rate_hz: f
         info, ent = sh["info"], sh["entropy_sum"]
     return CwtEntropy(freq, (b0, b1), len(freq_all), power, info, band_power, total, ent,
                       float(np.log2(deg_free) / deg_free))
+
+
+def stx_power_entropy(band_order_nth: float, sig_wf, frequency_sample_rate_hz: float, *, dtype="float32",
+                      want_info: bool = True, out_power=None, out_info=None) -> CwtEntropy:
+    """Power, information and entropy of the Stockwell transform on the standard order-N band table -- the composition
+
+        f, t, stx = styx_stx.stx_complex_any_scale_pow2(N, sig, fs)          # styx_stx.py:195-236
+        power     = np.abs(stx) ** 2
+        shannon   = tfr_info.shannon_stft_from_tfr_power(power)              # tfr_info.py:231-236
+
+    without the complex plane ever reaching HBM: the band-limited voices are interpolated straight to ``|.|^2`` with their
+    fp64 band sums (csrc/qi_interp.cuh), the wide voices leave the last inverse pass the same way, and one streaming pass
+    writes -log2(P / S + eps64) and the per-band entropy sums.  ``sig_wf``: [N] or [C, N], N = 2^m; float32 or float64.
+    """
+    rt = get_runtime(sig_wf)
+    dt = dtype_name(dtype, default="float32")
+    sig, _ = _driver._as_2d(rt, sig_wf, dt)
+    n_points = int(sig.shape[1])
+    if n_points & (n_points - 1):
+        raise ValueError("the Stockwell transform needs a record of 2^m points (reference styx_stx.py:16-48 pads to one)")
+    freq, bands = _plan.stx_bands(band_order_nth, n_points, frequency_sample_rate_hz)
+    res = _driver.stx_fft(sig, bands, dt, want_complex=False, want_power=True, want_band_sum=True, rt=rt,
+                          out_power=out_power)
+    power, band_power = res["power"], res["band_sum"]
+    total = band_power.sum(-1)
+    deg_free = len(freq) * n_points
+    info = ent = None
+    if want_info:
+        sh = _driver.shannon(power, dt, 0, total, deg_free, eps=_driver.EPS64, planes=("info",), entropy_sum=True, rt=rt,
+                             out_info=out_info)
+        info, ent = sh["info"], sh["entropy_sum"]
+    return CwtEntropy(freq, (0, len(freq)), len(freq), power, info, band_power, total, ent,
+                      float(np.log2(deg_free) / deg_free))

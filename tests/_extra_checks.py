@@ -101,3 +101,30 @@ def check_stx_band_limited_routes(log2n, channels=1):
         assert err.max() < tol, (dtype, err)
         _, _, p = styx_stx.stx_complex_any_scale_pow2(3, x, FS, dtype=dtype, outputs="power")
         assert np.max(np.abs(p[-1] - np.abs(ref) ** 2)) / np.max(np.abs(ref) ** 2) < 4 * tol
+
+
+def check_stx_power_entropy(log2n):
+    """cwt_entropy.stx_power_entropy: Stockwell power / information / entropy without the complex plane, against the
+    reference composition (styx_stx.py:195-236 + tfr_info.py:203-236) restated by the oracle."""
+    from oracle import qi_oracle as orc
+    from quantum_inferno_b200 import cwt_entropy
+    n = 1 << log2n
+    k = np.arange(n)
+    x = np.cos(2 * np.pi * 55.0 / FS * k) + 0.3 * np.random.default_rng(11).standard_normal(n)
+    _, _, ref = orc.stx_complex_any_scale_pow2(3, x, FS)
+    p_ref = np.abs(ref) ** 2
+    s_ref = p_ref.sum()
+    pdf = p_ref / s_ref
+    info_ref = -np.log2(pdf + np.finfo(np.float64).eps)
+    ent_ref = float(np.sum(pdf * info_ref))
+    for dtype, tol_p, tol_bits in (("float64", 1e-10, 1e-9), ("float32", 1e-4, 1e-3)):
+        r = cwt_entropy.stx_power_entropy(3, x, FS, dtype=dtype)
+        p = np.asarray(r.power[0].cpu() if hasattr(r.power, "cpu") else r.power[0], dtype=np.float64)
+        assert np.linalg.norm(p - p_ref) / np.linalg.norm(p_ref) < tol_p
+        tot = float(r.total_power[0])
+        assert abs(tot - s_ref) / s_ref < tol_p
+        ent = float(r.entropy_bits()[0])
+        assert abs(ent - ent_ref) < tol_bits, (dtype, ent, ent_ref)
+        info = np.asarray(r.info[0].cpu() if hasattr(r.info, "cpu") else r.info[0], dtype=np.float64)
+        strong = p_ref > 1e-3 * p_ref.max()
+        assert np.max(np.abs(info - info_ref)[strong]) < (1e-8 if dtype == "float64" else 1e-3)

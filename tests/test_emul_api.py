@@ -388,3 +388,8 @@ def test_reference_error_paths():
 def test_stx_band_limited_routes():
     from tests import _extra_checks as ec
     ec.check_stx_band_limited_routes(13, channels=2)
+
+
+def test_stx_power_entropy():
+    from tests import _extra_checks as ec
+    ec.check_stx_power_entropy(13)

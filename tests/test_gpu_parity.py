@@ -631,3 +631,8 @@ def test_reference_error_paths(torch_cuda):
 def test_stx_band_limited_routes(torch_cuda):
     from tests import _extra_checks as ec
     ec.check_stx_band_limited_routes(18, channels=3)
+
+
+def test_stx_power_entropy(torch_cuda):
+    from tests import _extra_checks as ec
+    ec.check_stx_power_entropy(16)
