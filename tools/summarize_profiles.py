@@ -81,7 +81,10 @@ FULL_METRICS = [
 
 
 def full(src, dst, traffic_json=None):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if src.endswith(".csv"):      # already exported on the GPU box (`ncu -i report --page raw --csv`): reports are too big to bring back
+        out = open(src).read()
+    else:
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
