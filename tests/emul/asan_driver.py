@@ -24,4 +24,13 @@ with _runtime.use_runtime(EmulRuntime()):
         f,t,mag = stf.stft_tukey(x, 800.0, 0.25, m, ov, padding=pad)
         o = stf.get_stft_object_tukey(800.0, 0.25, m, ov)
         ts, xr = stf.istft_tukey(o.stft(x), 800.0, 0.25, m, ov); print("tukey", mag.shape, xr.shape, flush=True)
+    # round 2: band-limited routes of the exact paths (overlap-save blocks, decimated transforms + interpolation,
+    # factorised inter-pass twiddles), both dtypes; Bluestein rfft; fused Stockwell entropy
+    from quantum_inferno_b200 import tfr_info
+    x = rng.standard_normal((2, 1 << 13))
+    for dt in ("float64", "float32"):
+        f,t,c = styx_cwt.cwt_complex_any_scale_pow2(3, x, 800.0, dtype=dt); print("exact band-limited", dt, c.shape, flush=True)
+        f,t,s = styx_stx.stx_complex_any_scale_pow2(3, x, 800.0, dtype=dt); print("stx band-limited", dt, s.shape, flush=True)
+        r = cwt_entropy.stx_power_entropy(3, x, 800.0, dtype=dt); print("stx entropy", dt, float(np.asarray(r.entropy_bits())[0]), flush=True)
+    ff = tfr_info.ShannonFFT(x[0, :777]); print("bluestein", ff.sig.shape, flush=True)
 print("asan run done")
