@@ -38,11 +38,9 @@
 #include "qi_halfband_coeffs.h"
 #include "qi_mr_expand.cuh"
 #include "qi_mr_level2k.cuh"
-#include "qi_mr_level2kp.cuh"
 
 #include <vector>
 #include <math.h>
-#include <stdlib.h>
 
 namespace qi {
 
@@ -102,8 +100,7 @@ mr_decimate_kernel(const float* __restrict__ src, i64 src_stride, i64 src_len, i
 // One CTA per band: sample kappa[d] = 2^l * amp * exp(-t^2/2s^2) * exp(i*omega*t), t = 2^l d - 1/2, on the circular
 // lag grid of F points, keep |d| <= half_w and |t| <= (N-1)/2, forward FFT in shared memory, store * 1/F.
 __global__ void __launch_bounds__(256)
-mr_table_kernel(const MrDevBand* __restrict__ bands, i64 n_points, int half_w_cap, cplx<float>* __restrict__ tables,
-                float4* __restrict__ tables_dup) {
+mr_table_kernel(const MrDevBand* __restrict__ bands, i64 n_points, int half_w_cap, cplx<float>* __restrict__ tables) {
     QI_DYN_SMEM(smem_raw);
     const MrDevBand b = bands[blockIdx.x];
     const int F = 1 << b.logF;
@@ -132,11 +129,7 @@ mr_table_kernel(const MrDevBand* __restrict__ bands, i64 n_points, int half_w_ca
     __syncthreads();
     tile_fft<float, FFT_FWD>(tile, tw, b.logF, 1, 2);
     const float inv = 1.0f / (float)F;
-    for (int p = threadIdx.x; p < F; p += blockDim.x) {
-        const cplx<float> k = tile[p * 2] * inv;
-        tables[b.table_off + p] = k;
-        if (tables_dup) tables_dup[b.table_off + p] = make_float4(k.re, k.re, k.im, k.im);   // operands of qi_mr_level2kp.cuh
-    }
+    for (int p = threadIdx.x; p < F; p += blockDim.x) tables[b.table_off + p] = tile[p * 2] * inv;
 }
 
 // ---------------------------------------------------------------- A: overlap-save level convolution (generic)
@@ -300,8 +293,7 @@ struct MrPlan {
     std::vector<MrLevelGeom> levels;
     int n_edge;                         // edge rows = the first n_edge bands; their source bands are B .. B + n_edge - 1
     i64 n_prefix;
-    size_t off_bands, off_list, off_deep, off_tw, off_twp, off_pyr, off_tables, off_tables_dup, off_w, off_mid, off_prefix,
-        off_group, total;
+    size_t off_bands, off_list, off_deep, off_tw, off_pyr, off_tables, off_w, off_mid, off_prefix, off_group, total;
     i64 pyr_per_chan, w_total, mid_total;
 };
 
@@ -442,10 +434,8 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl, bool all
     pl.off_prefix = o; o = align_up(o + sizeof(double) * 2 * (size_t)pl.n_prefix * (size_t)C * (E > 0 ? 1 : 0), 256);
     pl.off_group = o; o = align_up(o + sizeof(float2) * (size_t)(N / 8) * (size_t)C * (E > 0 ? 1 : 0), 256);
     pl.off_tw = o; o = align_up(o + sizeof(float4) * (size_t)L2K_TW_TOTAL, 256);
-    pl.off_twp = o; o = align_up(o + sizeof(float4) * (size_t)L2KP_TW_TOTAL, 256);
     pl.off_pyr = o; o = align_up(o + sizeof(float) * (size_t)pl.pyr_per_chan * C, 256);
     pl.off_tables = o; o = align_up(o + sizeof(cplx<float>) * (size_t)toff, 256);
-    pl.off_tables_dup = o; o = align_up(o + sizeof(float4) * (size_t)toff, 256);
     pl.off_w = o; o = align_up(o + sizeof(cplx<float>) * (size_t)woff, 256);
     pl.off_mid = o; o = align_up(o + sizeof(cplx<float>) * (size_t)moff, 256);
     pl.total = o;
@@ -542,8 +532,6 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     float4* tw2k = reinterpret_cast<float4*>(base + pl.off_tw);
     float* pyr = reinterpret_cast<float*>(base + pl.off_pyr);
     cplx<float>* tables = reinterpret_cast<cplx<float>*>(base + pl.off_tables);
-    float4* tables_dup = reinterpret_cast<float4*>(base + pl.off_tables_dup);
-    float4* twp2k = reinterpret_cast<float4*>(base + pl.off_twp);
     cplx<float>* wbuf = reinterpret_cast<cplx<float>*>(base + pl.off_w);
     const HbTaps taps = make_taps();
 
@@ -565,10 +553,8 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
 #ifndef QI_EMUL
         cudaFuncSetAttribute(mr_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-        QI_LAUNCH(mr_table_kernel, dim3((unsigned)(B + E)), dim3(256), smem, st, (const MrDevBand*)d_bands, N, 2047, tables,
-                  tables_dup);
+        QI_LAUNCH(mr_table_kernel, dim3((unsigned)(B + E)), dim3(256), smem, st, (const MrDevBand*)d_bands, N, 2047, tables);
         QI_LAUNCH(mr_twiddle2k_kernel, dim3((L2K_TW_TOTAL + 255) / 256), dim3(256), 0, st, tw2k);
-        QI_LAUNCH(mr_twiddle2kp_kernel, dim3((L2KP_TW_TOTAL + 255) / 256), dim3(256), 0, st, twp2k);
         if (E > 0) {   // running sums of the record for the edge rows
             QI_LAUNCH(mr_prefix_sums_kernel, dim3((unsigned)(pl.n_prefix - 1), (unsigned)C), dim3(256), 0, st, sig, stride, N,
                       d_prefix, pl.n_prefix, d_group);
@@ -629,14 +615,7 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
             cudaFuncSetAttribute(mr_level2k_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2K_SMEM);
             cudaFuncSetAttribute(mr_level2k_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2K_SMEM);
 #endif
-            static const bool scalar_l2k = getenv("QI_L2K_SCALAR") != nullptr;      // A/B switch of the packed kernel
-            if (!g.env && !scalar_l2k) {
-#ifndef QI_EMUL
-                cudaFuncSetAttribute(mr_level2kp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2KP_SMEM);
-#endif
-                QI_LAUNCH(mr_level2kp_kernel, grid2, dim3(L2K_THREADS), L2KP_SMEM, st, x, g, (const MrDevBand*)d_bands,
-                          (const float4*)tables_dup, (const float4*)twp2k, wbuf, out_power, out_complex, sum_dst, (int)ppc);
-            } else if (g.env)
+            if (g.env)
                 QI_LAUNCH((mr_level2k_kernel<true>), grid2, dim3(L2K_THREADS), L2K_SMEM, st, x, g, (const MrDevBand*)d_bands,
                           (const cplx<float>*)tables, (const float4*)tw2k, wbuf, out_power, out_complex, sum_dst, (int)ppc);
             else
