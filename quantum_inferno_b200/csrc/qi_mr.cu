@@ -20,8 +20,10 @@
 //   E  expand       qi_mr_expand.cuh: per (channel, band, 16384-cell span) the band's decimated samples are read
 //                   once, brought to level k = min(l, 3) by half-band stages in shared memory and to the full rate
 //                   by one merged polyphase interpolator x2^k from registers, fused with |.|^2, -log2(P/S + eps),
-//                   both plane stores (256-bit) and the band / entropy sums.  Bands deeper than level 5 first get a
-//                   level-5 copy (MID mode, 1/32 of the cells).
+//                   both plane stores (256-bit) and the band / entropy sums.  Every band is read at its own level (a
+//                   deep band: a few samples per tile), so that almost no DRAM read disturbs the kernel's write stream.
+//                   Bands deeper than level 5 are also brought to level 5 once (MID mode, 1/32 of the cells) for the
+//                   raw sums and end samples that the band-power estimate is made from.
 //   I  info rows    the level-0 rows' information plane (their power was written before S was known).
 //   R  edge rows    the reference cuts its atoms off at the record; for the record-long atoms of the lowest bands that
 //                   jump answers to every frequency of the record.  It is split off as a straight line over the atom's
@@ -94,6 +96,179 @@ mr_decimate_kernel(const float* __restrict__ src, i64 src_stride, i64 src_len, i
         o[r] = acc;
     }
     *reinterpret_cast<float4*>(dst + c * dst_stride + i_base + j0) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// ---------------------------------------------------------------- running sums of the record (edge rows, see MrDevBand)
+// blk[c][0][j + 1] = sum of x over block j, blk[c][1][j + 1] = sum of (k - (N-1)/2) x[k] over block j  (fp64), and
+// grp[c][j * 256 + t] = (L0, L1) = (sum_{m < 8t} a[m], sum_{m < 8t} (m + 1) a[m]) with a[m] = x[2048 j + m]: the block-local
+// exclusive scans the edge expansion starts its 8 outputs from (see edge_add in qi_mr_expand.cuh).
+// One 2048-sample block per call, 256 threads, z = the thread's samples a[8 tid .. 8 tid + 7].
+struct PrefixScratch { double red[32]; float wtot[2][8]; };
+QI_DEV void prefix_block(const float* z, i64 c, i64 j, i64 n_points, double* __restrict__ blk, i64 n_prefix,
+                         float2* __restrict__ grp, PrefixScratch& sh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float s0 = 0.0f, s1 = 0.0f;
+    const float fi0 = (float)(8 * tid);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { s0 += z[r]; s1 = fmaf(fi0 + (float)(r + 1), z[r], s1); }
+    float i0 = s0, i1 = s1;                              // inclusive scan of the thread totals over the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float u0 = __shfl_up_sync(0xffffffffu, i0, o), u1 = __shfl_up_sync(0xffffffffu, i1, o);
+        if (lane >= o) { i0 += u0; i1 += u1; }
+    }
+    __syncthreads();                                     // the previous block of this CTA has left the scratch
+    if (lane == 31) { sh.wtot[0][warp] = i0; sh.wtot[1][warp] = i1; }
+    __syncthreads();
+    float off0 = i0 - s0, off1 = i1 - s1;
+    for (int w = 0; w < warp; ++w) { off0 += sh.wtot[0][w]; off1 += sh.wtot[1][w]; }
+    grp[c * (n_points >> 3) + j * (MR_EDGE_BLOCK / 8) + tid] = make_float2(off0, off1);
+    // block totals in fp64: sum a[m], sum (2048 j + m - cc) a[m] with sum (m + 1) a[m] = s1
+    const double k0 = (double)(j * MR_EDGE_BLOCK) - 1.0 - 0.5 * (double)(n_points - 1);
+    double d0 = (double)s0, d1 = k0 * (double)s0 + (double)s1;
+    d0 = block_sum(d0, sh.red);
+    d1 = block_sum(d1, sh.red);
+    if (tid == 0) {
+        double* row = blk + c * 2 * n_prefix;
+        row[j + 1] = d0;
+        row[n_prefix + j + 1] = d1;
+    }
+}
+__global__ void __launch_bounds__(256)
+mr_prefix_sums_kernel(const float* __restrict__ x, i64 stride, i64 n_points, double* __restrict__ blk, i64 n_prefix,
+                      float2* __restrict__ grp) {
+    __shared__ PrefixScratch sh;
+    const i64 c = blockIdx.y, j = blockIdx.x;
+    const float4* p = reinterpret_cast<const float4*>(x + c * stride + j * MR_EDGE_BLOCK) + 2 * threadIdx.x;
+    const float4 v0 = p[0], v1 = p[1];
+    const float z[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    prefix_block(z, c, j, n_points, blk, n_prefix, grp, sh);
+}
+
+// ---------------------------------------------------------------- P: levels 1, 2 and 3 in one pass over the record
+// The three finest levels are 7/8 of the pyramid's traffic when each level re-reads the one above it.  Here a CTA reads
+// 8 * P3_T + 224 record samples once and leaves P3_T level-3 samples plus the level-1 / level-2 samples it owns
+// (stored indices [4 P3_T j, 4 P3_T (j+1)) and [2 P3_T j, 2 P3_T (j+1))); the intermediate tiles live in shared memory,
+// split into even and odd samples like the tile of mr_decimate_kernel.  Same arithmetic, same order, same zero
+// extension as three runs of mr_decimate_kernel (a sample outside a level's stored range [-HALO, n + HALO) is zero), so
+// the results are bit-identical to the level-by-level chain.  With edge rows (blk != nullptr) the CTA also makes the
+// running sums of the two 2048-sample blocks [4096 j, 4096 (j+1)) it holds (prefix_block): no second pass over the record.
+// Tile geometry (q = index at the level's own rate, first sample of a tile a multiple of 8):
+//   level 3: q in [P3_T j - 16, + P3_T)            level 2: [2 P3_T j - 48, + 2 P3_T + 32)
+//   level 1: [4 P3_T j - 112, + 4 P3_T + 96)       record : [8 P3_T j - 240, + 8 P3_T + 240)   (the last 16 samples:
+//                                                            prefix sums only)
+// so that output m of a tile sits at p = 8 + m of the tile above it: a thread makes 4 outputs from O[4g .. 4g + 19] and
+// E[4g + 8 .. 4g + 11] (six 128-bit loads), g its group index.
+constexpr int P3_T = 512;
+constexpr int P3_N0 = 8 * P3_T + 240, P3_N1 = 4 * P3_T + 96, P3_N2 = 2 * P3_T + 32;
+static_assert(QI_HB_MAX_TAPS == 7 && MR_HALO == 16, "tile geometry of mr_pyramid3_kernel");
+static_assert(8 * P3_T == 2 * MR_EDGE_BLOCK, "two prefix blocks per CTA");
+
+// 4 consecutive outputs of one half-band decimation from the even / odd arrays of the level above
+QI_DEV void p3_group(const float* __restrict__ E, const float* __restrict__ O, int g, const HbTaps& taps, float* o) {
+    float od[20];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(O + 4 * g + 4 * m);
+        od[4 * m] = v.x; od[4 * m + 1] = v.y; od[4 * m + 2] = v.z; od[4 * m + 3] = v.w;
+    }
+    const float4 ev = *reinterpret_cast<const float4*>(E + 4 * g + 8);
+    const float e[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float acc = 0.5f * e[r];
+#pragma unroll
+        for (int t = 0; t < QI_HB_MAX_TAPS; ++t)
+            acc += taps.c[0][t] * (od[8 + r + t] + od[8 + r - t - 1]);
+        o[r] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mr_pyramid3_kernel(const float* __restrict__ sig, i64 sig_stride, i64 n_points, float* __restrict__ l1,
+                   float* __restrict__ l2, float* __restrict__ l3, i64 pyr_stride, HbTaps taps, double* __restrict__ blk,
+                   i64 n_prefix, float2* __restrict__ grp) {
+    __shared__ PrefixScratch sh;
+    __shared__ __align__(16) float E0[P3_N0 / 2], O0[P3_N0 / 2];
+    __shared__ __align__(16) float E1[P3_N1 / 2], O1[P3_N1 / 2];
+    __shared__ __align__(16) float E2[P3_N2 / 2], O2[P3_N2 / 2];
+    const i64 c = blockIdx.y, j = blockIdx.x;
+    const float* x = sig + c * sig_stride;
+    // record tile: all loads of a thread in flight before the first store
+    {
+        const i64 k0 = 8 * (i64)P3_T * j - 240;
+        constexpr int LU = (P3_N0 / 2 + 255) / 256;
+        float2 v[LU];
+#pragma unroll
+        for (int u = 0; u < LU; ++u) {
+            const int s = threadIdx.x + 256 * u;
+            const i64 k = k0 + 2 * s;
+            v[u] = make_float2(0.0f, 0.0f);
+            if (s < P3_N0 / 2) {
+                if (k >= 0 && k + 1 < n_points) v[u] = *reinterpret_cast<const float2*>(x + k);
+                else {
+                    if (k >= 0 && k < n_points) v[u].x = x[k];
+                    if (k + 1 >= 0 && k + 1 < n_points) v[u].y = x[k + 1];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < LU; ++u) {
+            const int s = threadIdx.x + 256 * u;
+            if (s < P3_N0 / 2) { E0[s] = v[u].x; O0[s] = v[u].y; }
+        }
+    }
+    __syncthreads();
+    if (blk) {
+        // record sample 4096 j + 2048 b + 8 t + r sits at tile offset 240 + 2048 b + 8 t + r: four even, four odd slots
+        for (int b = 0; b < 2; ++b) {
+            const i64 jb = 2 * j + b;
+            if (jb >= n_prefix - 1) break;                           // uniform over the CTA
+            const int s0 = 120 + 1024 * b + 4 * threadIdx.x;
+            const float4 ev = *reinterpret_cast<const float4*>(E0 + s0), ov = *reinterpret_cast<const float4*>(O0 + s0);
+            const float z[8] = {ev.x, ov.x, ev.y, ov.y, ev.z, ov.z, ev.w, ov.w};
+            prefix_block(z, c, jb, n_points, blk, n_prefix, grp, sh);
+        }
+    }
+    // level 1: stored index i = q + HALO, q = 4 P3_T j - 112 + 4 g + r; owned from i = 4 P3_T j on
+    {
+        const i64 len = (n_points >> 1) + 2 * MR_HALO;
+        float* dst = l1 + c * pyr_stride;
+        for (int g = threadIdx.x; g < P3_N1 / 4; g += 256) {
+            float o[4];
+            p3_group(E0, O0, g, taps, o);
+            const i64 i = 4 * (i64)P3_T * j - 112 + MR_HALO + 4 * g;
+            if (i < 0 || i >= len) { o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f; o[3] = 0.0f; }   // len and i are multiples of 4
+            *reinterpret_cast<float2*>(E1 + 2 * g) = make_float2(o[0], o[2]);
+            *reinterpret_cast<float2*>(O1 + 2 * g) = make_float2(o[1], o[3]);
+            if (4 * g >= 96 && i >= 0 && i < len) *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    __syncthreads();
+    {
+        const i64 len = (n_points >> 2) + 2 * MR_HALO;
+        float* dst = l2 + c * pyr_stride;
+        for (int g = threadIdx.x; g < P3_N2 / 4; g += 256) {
+            float o[4];
+            p3_group(E1, O1, g, taps, o);
+            const i64 i = 2 * (i64)P3_T * j - 48 + MR_HALO + 4 * g;
+            if (i < 0 || i >= len) { o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f; o[3] = 0.0f; }
+            *reinterpret_cast<float2*>(E2 + 2 * g) = make_float2(o[0], o[2]);
+            *reinterpret_cast<float2*>(O2 + 2 * g) = make_float2(o[1], o[3]);
+            if (4 * g >= 32 && i >= 0 && i < len) *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    __syncthreads();
+    {
+        const i64 len = (n_points >> 3) + 2 * MR_HALO;
+        float* dst = l3 + c * pyr_stride;
+        for (int g = threadIdx.x; g < P3_T / 4; g += 256) {
+            float o[4];
+            p3_group(E2, O2, g, taps, o);
+            const i64 i = (i64)P3_T * j + 4 * g;
+            if (i < len) *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
 }
 
 // ---------------------------------------------------------------- T: kernel tables
@@ -221,47 +396,7 @@ mr_level_kernel(const float* __restrict__ x, MrLevelGeom g, const MrDevBand* __r
     }
 }
 
-// ---------------------------------------------------------------- running sums of the record (edge rows, see MrDevBand)
-// blk[c][0][j + 1] = sum of x over block j, blk[c][1][j + 1] = sum of (k - (N-1)/2) x[k] over block j  (fp64), and
-// grp[c][j * 256 + t] = (L0, L1) = (sum_{m < 8t} a[m], sum_{m < 8t} (m + 1) a[m]) with a[m] = x[2048 j + m]: the block-local
-// exclusive scans the edge expansion starts its 8 outputs from (see edge_add in qi_mr_expand.cuh)
-__global__ void __launch_bounds__(256)
-mr_prefix_sums_kernel(const float* __restrict__ x, i64 stride, i64 n_points, double* __restrict__ blk, i64 n_prefix,
-                      float2* __restrict__ grp) {
-    __shared__ double scratch[32];
-    __shared__ float wtot[2][8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const i64 c = blockIdx.y, j = blockIdx.x;
-    const float4* p = reinterpret_cast<const float4*>(x + c * stride + j * MR_EDGE_BLOCK) + 2 * tid;
-    const float4 v0 = p[0], v1 = p[1];
-    const float z[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    float s0 = 0.0f, s1 = 0.0f;
-    const float fi0 = (float)(8 * tid);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) { s0 += z[r]; s1 = fmaf(fi0 + (float)(r + 1), z[r], s1); }
-    float i0 = s0, i1 = s1;                              // inclusive scan of the thread totals over the warp
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const float u0 = __shfl_up_sync(0xffffffffu, i0, o), u1 = __shfl_up_sync(0xffffffffu, i1, o);
-        if (lane >= o) { i0 += u0; i1 += u1; }
-    }
-    if (lane == 31) { wtot[0][warp] = i0; wtot[1][warp] = i1; }
-    __syncthreads();
-    float off0 = i0 - s0, off1 = i1 - s1;
-    for (int w = 0; w < warp; ++w) { off0 += wtot[0][w]; off1 += wtot[1][w]; }
-    grp[c * (n_points >> 3) + j * (MR_EDGE_BLOCK / 8) + tid] = make_float2(off0, off1);
-    // block totals in fp64: sum a[m], sum (2048 j + m - cc) a[m] with sum (m + 1) a[m] = s1
-    const double k0 = (double)(j * MR_EDGE_BLOCK) - 1.0 - 0.5 * (double)(n_points - 1);
-    double d0 = (double)s0, d1 = k0 * (double)s0 + (double)s1;
-    d0 = block_sum(d0, scratch);
-    d1 = block_sum(d1, scratch);
-    if (tid == 0) {
-        double* row = blk + c * 2 * n_prefix;
-        row[j + 1] = d0;
-        row[n_prefix + j + 1] = d1;
-    }
-}
-
+// ---------------------------------------------------------------- running sums of the record: block scan
 // in-place inclusive scan of each of the 2 C rows (entry 0 = 0): row[j] = sum over the blocks before block j
 __global__ void __launch_bounds__(1024)
 mr_prefix_scan_kernel(double* __restrict__ blk, i64 n_prefix) {
@@ -412,7 +547,7 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl, bool all
             if (lout > MR_LMID) {
                 d.mid_stride = ((N >> MR_LMID) + 2 * MR_HALO + 63) / 64 * 64;
                 d.mid_off = moff; moff += d.mid_stride * C;
-                pl.deep_list.push_back(idx);
+                if (!(flags & MR_FLAG_EDGE_SRC)) pl.deep_list.push_back(idx);   // sources have no estimate of their own
             }
             pl.bands[idx] = d;
         };
@@ -555,14 +690,22 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
 #endif
         QI_LAUNCH(mr_table_kernel, dim3((unsigned)(B + E)), dim3(256), smem, st, (const MrDevBand*)d_bands, N, 2047, tables);
         QI_LAUNCH(mr_twiddle2k_kernel, dim3((L2K_TW_TOTAL + 255) / 256), dim3(256), 0, st, tw2k);
-        if (E > 0) {   // running sums of the record for the edge rows
+        if (E > 0 && pl.cap < 3) {   // running sums of the record for the edge rows (else: inside mr_pyramid3_kernel)
             QI_LAUNCH(mr_prefix_sums_kernel, dim3((unsigned)(pl.n_prefix - 1), (unsigned)C), dim3(256), 0, st, sig, stride, N,
                       d_prefix, pl.n_prefix, d_group);
             QI_LAUNCH(mr_prefix_scan_kernel, dim3((unsigned)(2 * C)), dim3(1024), 0, st, d_prefix, pl.n_prefix);
         }
     }
     // P: pyramid
-    for (int l = 1; do_front && l <= pl.cap; ++l) {
+    int first_level = 1;
+    if (do_front && pl.cap >= 3) {      // levels 1 - 3 in one pass over the record
+        dim3 grid((unsigned)((pl.lvl_len[3] + P3_T - 1) / P3_T), (unsigned)C);
+        QI_LAUNCH(mr_pyramid3_kernel, grid, dim3(256), 0, st, sig, stride, N, pyr + pl.lvl_off[1], pyr + pl.lvl_off[2],
+                  pyr + pl.lvl_off[3], pl.pyr_per_chan, taps, E > 0 ? d_prefix : nullptr, pl.n_prefix, d_group);
+        if (E > 0) QI_LAUNCH(mr_prefix_scan_kernel, dim3((unsigned)(2 * C)), dim3(1024), 0, st, d_prefix, pl.n_prefix);
+        first_level = 4;
+    }
+    for (int l = first_level; do_front && l <= pl.cap; ++l) {
         const float* src = l == 1 ? sig : pyr + pl.lvl_off[l - 1];
         const i64 src_stride = l == 1 ? stride : pl.pyr_per_chan;
         const i64 src_len = l == 1 ? N : pl.lvl_len[l - 1];
@@ -678,7 +821,9 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
     };
     if (do_front) {
         prof_set_category(QI_CAT_INV_FIRST);
-        if (!pl.deep_list.empty()) launch_groups(pl.deep_list, d_deep, MR_LMID, (N >> MR_LMID) + 2 * MR_HALO, MR_MODE_MID);
+        // level-MR_LMID pass of the deep bands: only the band-power estimates need it (the expansion reads the bands' own samples)
+        if (fused && !pl.deep_list.empty())
+            launch_groups(pl.deep_list, d_deep, MR_LMID, (N >> MR_LMID) + 2 * MR_HALO, MR_MODE_MID);
         if (fused) {
             // raw sums are in band_sum_est (level kernels / the MID pass); finish the estimates and the totals
             QI_LAUNCH(mr_total_kernel, dim3((unsigned)C), dim3(128), 0, st, (const MrDevBand*)d_bands, B, N,
