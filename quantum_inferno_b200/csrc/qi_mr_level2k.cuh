@@ -150,6 +150,13 @@ QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const Mr
     const int pD0 = 4 * t + (t >> 1);                                      // radix 4     : rows 4g + i, g = t
     const int pD1 = 4 * (t + 256) + ((t + 256) >> 1);                      //               g = t + 256
 
+    // twiddles of the stage B=2048 depend on the thread only: kept in registers for the forward stage and every band
+    // (the kernel is bound by the shared-memory / L1 data pipe: 73 % of its wavefront rate, ncu r3c)
+    __syncthreads();
+    float4 wA[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) wA[m] = tw[m * L2K_TWJ + L2K_TW0 + t];
+
     for (int pp = 0; pp < pairs_per_cta; ++pp) {
         const i64 blk0 = 2 * ((i64)bx * pairs_per_cta + pp);
         if (blk0 >= g.n_blocks) break;                                     // uniform over the CTA
@@ -166,14 +173,11 @@ QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const Mr
                 b[i] = mk<float>((has_b && kb >= 0 && kb < g.x_len) ? xs[kb] : 0.0f, 0.0f);
             }
             dif8<float, FFT_FWD>(a); dif8<float, FFT_FWD>(b);
-            float4 w[4];
-#pragma unroll
-            for (int m = 0; m < 4; ++m) w[m] = tw[m * L2K_TWJ + L2K_TW0 + t];
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
                 cplx<float> va = a[s], vb = b[s];
                 if (s) {
-                    const float4 ww = w[s >> 1];
+                    const float4 ww = wA[s >> 1];
                     const cplx<float> tt = (s & 1) ? mk<float>(ww.z, ww.w) : mk<float>(ww.x, ww.y);
                     va = va * tt; vb = vb * tt;
                 }
@@ -373,15 +377,12 @@ QI_DEV void l2k_body(const float* __restrict__ x, const MrLevelGeom& g, const Mr
             // ---- last stage B=2048: outputs n = t + 256 i leave from registers
             cplx<float> a[8], c[8];
             {
-                float4 w[4];
-#pragma unroll
-                for (int m = 0; m < 4; ++m) w[m] = tw[m * L2K_TWJ + L2K_TW0 + t];
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     const float4 v = tile[pA + s * 288];
                     cplx<float> va = mk<float>(v.x, v.y), vb = mk<float>(v.z, v.w);
                     if (s) {
-                        const float4 ww = w[s >> 1];
+                        const float4 ww = wA[s >> 1];
                         const cplx<float> tt = (s & 1) ? mk<float>(ww.z, ww.w) : mk<float>(ww.x, ww.y);
                         va = mul_conj(va, tt); vb = mul_conj(vb, tt);
                     }
