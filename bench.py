@@ -50,7 +50,7 @@ EXTRAS = os.environ.get("QI_BENCH_EXTRAS", "1") != "0"
 CHECKS = os.environ.get("QI_BENCH_CHECKS", "1") != "0"
 ITEM = {"float32": 4, "float64": 8}[DTYPE]
 KERNEL_OF = {
-    "multirate": {"fft_fwd": "mr_table_kernel+mr_decimate_kernel+mr_prefix_sums_kernel",
+    "multirate": {"fft_fwd": "mr_table_kernel+mr_pyramid3_kernel+mr_decimate_kernel",
                   "inv_first": "mr_level2k_kernel[levels>=1]+mr_expand_kernel<MID>",
                   "inv_mid": "mr_level2k_kernel[level 0]", "inv_last": "mr_expand_kernel<POWER_INFO>",
                   "info": "mr_info_rows_kernel"},

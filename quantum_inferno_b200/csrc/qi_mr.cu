@@ -27,7 +27,7 @@
 //   I  info rows    the level-0 rows' information plane (their power was written before S was known).
 //   R  edge rows    the reference cuts its atoms off at the record; for the record-long atoms of the lowest bands that
 //                   jump answers to every frequency of the record.  It is split off as a straight line over the atom's
-//                   support, whose contribution is a running sum + first moment of the record (mr_prefix_*_kernel and
+//                   support, whose contribution is a running sum + first moment of the record (prefix_block in mr_pyramid3_kernel, mr_prefix_scan_kernel and
 //                   a block scan inside E); the continuous remainder runs through T / A / E as an extra source band.
 //                   See MrDevBand in qi_mr_expand.cuh.
 //
@@ -134,17 +134,6 @@ QI_DEV void prefix_block(const float* z, i64 c, i64 j, i64 n_points, double* __r
         row[n_prefix + j + 1] = d1;
     }
 }
-__global__ void __launch_bounds__(256)
-mr_prefix_sums_kernel(const float* __restrict__ x, i64 stride, i64 n_points, double* __restrict__ blk, i64 n_prefix,
-                      float2* __restrict__ grp) {
-    __shared__ PrefixScratch sh;
-    const i64 c = blockIdx.y, j = blockIdx.x;
-    const float4* p = reinterpret_cast<const float4*>(x + c * stride + j * MR_EDGE_BLOCK) + 2 * threadIdx.x;
-    const float4 v0 = p[0], v1 = p[1];
-    const float z[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    prefix_block(z, c, j, n_points, blk, n_prefix, grp, sh);
-}
-
 // ---------------------------------------------------------------- P: levels 1, 2 and 3 in one pass over the record
 // The three finest levels are 7/8 of the pyramid's traffic when each level re-reads the one above it.  Here a CTA reads
 // 8 * P3_T + 224 record samples once and leaves P3_T level-3 samples plus the level-1 / level-2 samples it owns
@@ -690,15 +679,10 @@ static int mr_run(const float* sig, i64 C, i64 N, i64 stride, const QiMrBand* hb
 #endif
         QI_LAUNCH(mr_table_kernel, dim3((unsigned)(B + E)), dim3(256), smem, st, (const MrDevBand*)d_bands, N, 2047, tables);
         QI_LAUNCH(mr_twiddle2k_kernel, dim3((L2K_TW_TOTAL + 255) / 256), dim3(256), 0, st, tw2k);
-        if (E > 0 && pl.cap < 3) {   // running sums of the record for the edge rows (else: inside mr_pyramid3_kernel)
-            QI_LAUNCH(mr_prefix_sums_kernel, dim3((unsigned)(pl.n_prefix - 1), (unsigned)C), dim3(256), 0, st, sig, stride, N,
-                      d_prefix, pl.n_prefix, d_group);
-            QI_LAUNCH(mr_prefix_scan_kernel, dim3((unsigned)(2 * C)), dim3(1024), 0, st, d_prefix, pl.n_prefix);
-        }
     }
     // P: pyramid
     int first_level = 1;
-    if (do_front && pl.cap >= 3) {      // levels 1 - 3 in one pass over the record
+    if (do_front) {                     // levels 1 - 3 in one pass over the record (cap >= 3: records of >= 2^13 samples)
         dim3 grid((unsigned)((pl.lvl_len[3] + P3_T - 1) / P3_T), (unsigned)C);
         QI_LAUNCH(mr_pyramid3_kernel, grid, dim3(256), 0, st, sig, stride, N, pyr + pl.lvl_off[1], pyr + pl.lvl_off[2],
                   pyr + pl.lvl_off[3], pl.pyr_per_chan, taps, E > 0 ? d_prefix : nullptr, pl.n_prefix, d_group);

@@ -63,6 +63,27 @@ template <typename T> QI_HD cplx<T> mul_mi(cplx<T> a) { return mk<T>(a.im, -a.re
 template <typename T> QI_HD cplx<T> mul_pi(cplx<T> a) { return mk<T>(-a.im, a.re); }
 template <typename T> QI_HD T norm2(cplx<T> a) { return a.re * a.re + a.im * a.im; }
 
+// ---------------------------------------------------------------- packed pair of floats
+// One 64-bit register pair on the device: the operand of the f32x2 instructions of sm_100 (fma / add / sub / mul on both
+// halves).  The CPU emulation build spells the same operations out.
+#ifdef QI_EMUL
+struct f32x2 { float x, y; };
+QI_DEV f32x2 f2_make(float x, float y) { f32x2 r; r.x = x; r.y = y; return r; }
+QI_DEV float f2_lo(f32x2 v) { return v.x; }
+QI_DEV float f2_hi(f32x2 v) { return v.y; }
+QI_DEV f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { return f2_make(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+QI_DEV f32x2 f2_add(f32x2 a, f32x2 b) { return f2_make(a.x + b.x, a.y + b.y); }
+#else
+typedef unsigned long long f32x2;
+QI_DEV f32x2 f2_make(float x, float y) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+QI_DEV float f2_lo(f32x2 v) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); return x; }
+QI_DEV float f2_hi(f32x2 v) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); return y; }
+QI_DEV f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+QI_DEV f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+#endif
+
 // ---------------------------------------------------------------- exact twiddles
 // exp(sign * 2*pi*i * m / 2^lb), 0 <= m < 2^lb, evaluated with an exact quadrant
 // reduction so the argument handed to sincospi is exactly representable.
