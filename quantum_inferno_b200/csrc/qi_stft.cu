@@ -31,11 +31,16 @@ template <typename T> struct StftLaunch {
 // Hermitian split (which run along the tiles) start in different banks
 QI_HD int stft_tile_pitch(int R) { return pad8(R) | 1; }
 
-template <typename T>
+// LOGF / LOGTC > 0: FFT length and tiles per CTA known at compile time (the common sizes: every index computation of the
+// gather, the stage loops and the Hermitian split folds to shifts and immediates; ncu of the generic kernel had a third of
+// its instructions in integer index arithmetic); 0: taken from the geometry at run time.
+template <typename T, int LOGF, int LOGTC>
 __global__ void __launch_bounds__(StftLaunch<T>::threads, StftLaunch<T>::min_ctas)
-stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g, cplx<T>* __restrict__ out,
+stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g0, cplx<T>* __restrict__ out,
             double* __restrict__ psd_acc) {
     QI_DYN_SMEM(smem_raw);
+    StftGeom g = g0;
+    if (LOGF > 0) { g.logF = LOGF; g.TC = 1 << LOGTC; }
     const int R = 1 << g.logF;
     // TC single-column tiles (two real frames each) in the padded layout of tile_fft<.., true>, PT elements apart
     const int TC = g.TC, PT = stft_tile_pitch(R);
@@ -59,7 +64,58 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
     // of the span, one warp per block, every sample read once more from L1 / L2) and then gather (x - mean) * window
     // straight into the tile: no separate mean and window passes over shared memory.
     const int hops_per_frame = g.nperseg / g.hop;
-    const bool fused = interior && hops_per_frame * g.hop == g.nperseg && hops_per_frame <= 16;
+    // Compile-time sizes with at least one tile row per thread: a thread owns the rows r = tid + NT k of EVERY tile, so its
+    // window values sit in registers, its 2 TC R / NT samples (32 floats / 16 doubles) are requested in one go with
+    // lanes along the samples, the frame sums come from those registers (warp shuffles in the arithmetic type, fp64
+    // across the warps), and (x - mean) * window goes straight into the tiles.  Any hop, any nperseg <= R.
+    constexpr int NT = StftLaunch<T>::threads;
+    constexpr bool REG_GATHER = LOGF > 0 && (1 << (LOGF > 0 ? LOGF : 0)) >= NT;
+    bool gathered = false;
+    if (REG_GATHER && interior) {
+        constexpr int RPT = REG_GATHER ? (1 << LOGF) / NT : 1, TCC = REG_GATHER ? 1 << LOGTC : 1;
+        const T* xb0 = x + first;
+        const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+        T va[TCC][RPT], vb[TCC][RPT], wv[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int r = t + NT * k;
+            const bool in = r < g.nperseg;
+            wv[k] = in ? window[r] : (T)0;
+#pragma unroll
+            for (int c = 0; c < TCC; ++c) {
+                const T* pa = xb0 + (i64)(2 * c) * g.hop + r;
+                va[c][k] = in ? pa[0] : (T)0;
+                vb[c][k] = in ? pa[g.hop] : (T)0;
+            }
+        }
+        double* wsums = reinterpret_cast<double*>(tile);          // [warps][2 TCC]; the tiles are written after the means
+        if (g.detrend) {
+#pragma unroll
+            for (int c = 0; c < TCC; ++c) {
+                T sa = (T)0, sb = (T)0;
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) { sa += va[c][k]; sb += vb[c][k]; }
+                sa = warp_sum(sa); sb = warp_sum(sb);
+                if (lane == 0) { wsums[warp * 2 * TCC + 2 * c] = (double)sa; wsums[warp * 2 * TCC + 2 * c + 1] = (double)sb; }
+            }
+        }
+        __syncthreads();
+        if (t < 2 * TCC) {
+            double sm = 0.0;
+            if (g.detrend) for (int w = 0; w < NT / 32; ++w) sm += wsums[w * 2 * TCC + t];
+            means[t] = (T)(sm / (double)g.nperseg);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < TCC; ++c) {
+            const T m0 = means[2 * c], m1 = means[2 * c + 1];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k)
+                tile[c * PT + pad8(t + NT * k)] = mk<T>((va[c][k] - m0) * wv[k], (vb[c][k] - m1) * wv[k]);
+        }
+        gathered = true;
+    }
+    const bool fused = !gathered && interior && hops_per_frame * g.hop == g.nperseg && hops_per_frame <= 16;
     if (fused) {
         const T* xb0 = x + first;
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -83,7 +139,9 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
         }
         __syncthreads();
     }
-    if (interior) {
+    if (gathered) {
+        // tiles are complete (registers path above)
+    } else if (interior) {
         // eight (frame a, frame b) sample pairs per thread are requested before the first is stored: the gather is the
         // only HBM-latency-bound phase of the kernel and needs the loads in flight, not one dependent pair per trip
         const T* xb0 = x + first;
@@ -134,7 +192,7 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g,
     }
     __syncthreads();
     // per-frame mean over the nperseg samples (scipy detrend='constant', after the zero extension)
-    if (!fused) {
+    if (!fused && !gathered) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
         for (int col = warp; col < 2 * TC; col += nw) {
             double s = 0.0;
@@ -222,13 +280,28 @@ static int stft_impl(const void* sig, i64 C, i64 n_points, i64 stride, const voi
     if (C > 65535) return QI_ERR_UNSUPPORTED;
     dim3 grid((unsigned)((n_frames + 2 * TC - 1) / (2 * TC)), (unsigned)C);
     const size_t smem = need(TC);
-#ifndef QI_EMUL
-    cudaFuncSetAttribute(stft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-#endif
     if (psd_acc) cudaMemsetAsync(psd_acc, 0, sizeof(double) * (size_t)C * (nfft / 2 + 1), st);
     prof_set_category(QI_CAT_STFT);
-    QI_LAUNCH((stft_kernel<T>), grid, dim3(StftLaunch<T>::threads), smem, st, static_cast<const T*>(sig), static_cast<const T*>(window),
-              g, static_cast<cplx<T>*>(out), psd_acc);
+    int logTC = 0;
+    while ((1 << logTC) < TC) ++logTC;
+#ifndef QI_EMUL
+#define QI_STFT_LAUNCH(LF, LT)                                                                                          \
+    do {                                                                                                                \
+        cudaFuncSetAttribute(stft_kernel<T, LF, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        QI_LAUNCH((stft_kernel<T, LF, LT>), grid, dim3(StftLaunch<T>::threads), smem, st, static_cast<const T*>(sig),   \
+                  static_cast<const T*>(window), g, static_cast<cplx<T>*>(out), psd_acc);                               \
+    } while (0)
+#else
+#define QI_STFT_LAUNCH(LF, LT)                                                                                          \
+    QI_LAUNCH((stft_kernel<T, LF, LT>), grid, dim3(StftLaunch<T>::threads), smem, st, static_cast<const T*>(sig),       \
+              static_cast<const T*>(window), g, static_cast<cplx<T>*>(out), psd_acc)
+#endif
+    // compile-time sizes for the frame lengths 512 / 1024 / 2048 at the tile counts the budget gives them (16 / 8 / 4)
+    if (logF == 9 && logTC == 4) QI_STFT_LAUNCH(9, 4);
+    else if (logF == 10 && logTC == 3) QI_STFT_LAUNCH(10, 3);
+    else if (logF == 11 && logTC == 2) QI_STFT_LAUNCH(11, 2);
+    else QI_STFT_LAUNCH(0, 0);
+#undef QI_STFT_LAUNCH
     return check_cuda("qi_stft");
 }
 
