@@ -70,14 +70,14 @@ cwtf_os_kernel(const T* __restrict__ sig, i64 stride, CwtGeom geo, const int* __
     fill_stage_twiddles<T>(tw, logF);
     for (int p = threadIdx.x; p < F; p += blockDim.x) {
         const i64 k = n0 - half + p;
-        tile_x[pad8(p)] = mk<T>((k >= 0 && k < N) ? xs[k] : (T)0, (T)0);
+        tile_x[padt<T>(p)] = mk<T>((k >= 0 && k < N) ? xs[k] : (T)0, (T)0);
     }
     __syncthreads();
     tile_fft<T, FFT_FWD, true>(tile_x, tw, logF, 1, 1);
     for (int i = 0; i < n_os; ++i) {
         const int band = ids[i];
         const cplx<T>* H = tabF + ((size_t)i << logF);
-        for (int r = threadIdx.x; r < F; r += blockDim.x) tile_y[pad8(r)] = tile_x[pad8(r)] * H[r];
+        for (int r = threadIdx.x; r < F; r += blockDim.x) tile_y[padt<T>(r)] = tile_x[padt<T>(r)] * H[r];
         __syncthreads();
         tile_fft<T, FFT_INV, true>(tile_y, tw, logF, 1, 1);
         const i64 row = (chan * geo.n_bands + band) * N;
@@ -85,7 +85,7 @@ cwtf_os_kernel(const T* __restrict__ sig, i64 stride, CwtGeom geo, const int* __
         for (int v = threadIdx.x; v < V; v += blockDim.x) {
             const i64 n = n0 + v;
             if (n < N) {
-                const cplx<T> y = tile_y[pad8(half + v)];
+                const cplx<T> y = tile_y[padt<T>(half + v)];
                 const T pw = norm2(y);
                 if (out_c) out_c[row + n] = y;
                 if (out_p) out_p[row + n] = pw;

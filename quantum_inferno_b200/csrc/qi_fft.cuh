@@ -114,6 +114,12 @@ QI_HD int stage_tw_off(int logR, int logB) {     // radix-8 stages sit at logB =
 // plain layout puts the 32 / h blocks a warp touches in stages with h < 32 a multiple of 512 B apart -- an 8-way conflict
 // on 16-byte elements; with one padding slot per 8 rows every stage of a 2^m-point transform is conflict free.
 QI_HD int pad8(int r) { return r + (r >> 3); }
+// The slot of row r for elements of cplx<T>.  16-byte elements (double): one padding slot per 8 rows -- a quarter warp is
+// the unit of a 128-bit access.  8-byte elements (float): the unit is the half warp, and one slot per 8 rows makes 16
+// consecutive rows wrap onto their own first bank pair (ncu: 2x the wavefronts in every stage with h >= 16 and in every
+// row-contiguous pass); TWO slots per 16 rows keep 16 consecutive rows, the 8 x 2 rows of the h = 2 stage, the 4 x 4 of
+// h = 4 and the 2 x 8 of h = 8 on distinct bank pairs.  Same footprint: pad8(R) slots for R a multiple of 16.
+template <typename T> QI_HD int padt(int r) { return sizeof(T) == 4 ? r + 2 * (r >> 4) : r + (r >> 3); }
 template <typename T, int DIR, int STEP, bool STW = false>
 QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int TC, int TP) {
     constexpr int Q = 1 << STEP;
@@ -139,24 +145,24 @@ QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int
             cplx<T> a[Q];
             if (DIR == FFT_FWD) {
 #pragma unroll
-                for (int i = 0; i < Q; ++i) a[i] = tl[pad8(r0 + i * h)];
+                for (int i = 0; i < Q; ++i) a[i] = tl[padt<T>(r0 + i * h)];
                 if (STEP == 3) dif8<T, DIR>(a); else if (STEP == 2) dif4<T, DIR>(a); else dif2<T, DIR>(a);
 #pragma unroll
                 for (int s = 0; s < Q; ++s) {
                     cplx<T> v = a[s];
                     if (s != 0 && STEP == 3 && logH > 0) v = v * tws[s * h + jj];
-                    tl[pad8(r0 + s * h)] = v;
+                    tl[padt<T>(r0 + s * h)] = v;
                 }
             } else {
 #pragma unroll
                 for (int s = 0; s < Q; ++s) {
-                    cplx<T> v = tl[pad8(r0 + s * h)];
+                    cplx<T> v = tl[padt<T>(r0 + s * h)];
                     if (s != 0 && STEP == 3 && logH > 0) v = mul_conj(v, tws[s * h + jj]);
                     a[s] = v;
                 }
                 if (STEP == 3) dit8<T, DIR>(a); else if (STEP == 2) dit4<T, DIR>(a); else dit2<T, DIR>(a);
 #pragma unroll
-                for (int i = 0; i < Q; ++i) tl[pad8(r0 + i * h)] = a[i];
+                for (int i = 0; i < Q; ++i) tl[padt<T>(r0 + i * h)] = a[i];
             }
             continue;
         }

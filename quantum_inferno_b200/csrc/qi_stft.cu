@@ -111,7 +111,7 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g0
             const T m0 = means[2 * c], m1 = means[2 * c + 1];
 #pragma unroll
             for (int k = 0; k < RPT; ++k)
-                tile[c * PT + pad8(t + NT * k)] = mk<T>((va[c][k] - m0) * wv[k], (vb[c][k] - m1) * wv[k]);
+                tile[c * PT + padt<T>(t + NT * k)] = mk<T>((va[c][k] - m0) * wv[k], (vb[c][k] - m1) * wv[k]);
         }
         gathered = true;
     }
@@ -172,7 +172,7 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g0
                         v.re = (v.re - means[2 * c]) * w;
                         v.im = (v.im - means[2 * c + 1]) * w;
                     }
-                    tile[c * PT + pad8(r)] = v;
+                    tile[c * PT + padt<T>(r)] = v;
                 }
             }
         }
@@ -187,7 +187,7 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g0
                 if (fa < g.n_frames && pa >= 0 && pa < g.n_points) va = x[pa];
                 if (fb < g.n_frames && pb >= 0 && pb < g.n_points) vb = x[pb];
             }
-            tile[c * PT + pad8(r)] = mk<T>(va, vb);
+            tile[c * PT + padt<T>(r)] = mk<T>(va, vb);
         }
     }
     __syncthreads();
@@ -199,7 +199,7 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g0
             if (g.detrend) {
                 const int c = col >> 1;
                 for (int r = lane; r < g.nperseg; r += 32) {
-                    const cplx<T> v = tile[c * PT + pad8(r)];
+                    const cplx<T> v = tile[c * PT + padt<T>(r)];
                     s += (double)((col & 1) ? v.im : v.re);
                 }
             }
@@ -211,10 +211,10 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g0
             const T m0 = means[2 * c], m1 = means[2 * c + 1];
             for (int r = threadIdx.x; r < g.nperseg; r += blockDim.x) {
                 const T w = window[r];
-                cplx<T> v = tile[c * PT + pad8(r)];
+                cplx<T> v = tile[c * PT + padt<T>(r)];
                 v.re = (v.re - m0) * w;
                 v.im = (v.im - m1) * w;
-                tile[c * PT + pad8(r)] = v;
+                tile[c * PT + padt<T>(r)] = v;
             }
         }
         __syncthreads();
@@ -229,8 +229,8 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g0
         const bool active = idx < total;
         const int c = idx & (TC - 1);
         const int k = active ? idx >> logTC : 0;
-        const cplx<T> z1 = tile[c * PT + pad8((int)brev_bits((unsigned)k, g.logF))];
-        const cplx<T> z2 = tile[c * PT + pad8((int)brev_bits((unsigned)((R - k) & (R - 1)), g.logF))];
+        const cplx<T> z1 = tile[c * PT + padt<T>((int)brev_bits((unsigned)k, g.logF))];
+        const cplx<T> z2 = tile[c * PT + padt<T>((int)brev_bits((unsigned)((R - k) & (R - 1)), g.logF))];
         cplx<T> xa = mk<T>((T)0.5 * (z1.re + z2.re), (T)0.5 * (z1.im - z2.im));
         cplx<T> xb = mk<T>((T)0.5 * (z1.im + z2.im), (T)-0.5 * (z1.re - z2.re));
         if (g.roll) {               // segment rotated left by roll samples: bin k times exp(+2 pi i k roll / nfft)
