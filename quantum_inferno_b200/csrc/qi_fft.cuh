@@ -142,6 +142,17 @@ QI_DEV void tile_stage(cplx<T>* tile, const cplx<T>* tw, int logR, int logB, int
             cplx<T>* tl = tile + (size_t)(task >> logPer) * TP;
             const int jj = uu & (h - 1);
             const int r0 = ((uu >> logH) << logB) + jj;
+            if (STEP == 1 && (sizeof(T) == 8 || (TP & 1) == 0)) {
+                // the radix-2 remainder stage (h = 1): rows 2 uu and 2 uu + 1 are neighbours in the padded layout, one
+                // vector access each way instead of two (which a half warp could only serve in twice the wavefronts)
+                struct __align__(16) Pair { cplx<T> x, y; };        // float: needs an even tile pitch
+                Pair* pp = reinterpret_cast<Pair*>(tl + padt<T>(r0));
+                Pair v = *pp;
+                const cplx<T> d = v.x - v.y;
+                v.x = v.x + v.y; v.y = d;
+                *pp = v;
+                continue;
+            }
             cplx<T> a[Q];
             if (DIR == FFT_FWD) {
 #pragma unroll

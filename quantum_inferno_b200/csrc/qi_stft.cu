@@ -27,9 +27,10 @@ template <typename T> struct StftLaunch {
     static constexpr int min_ctas = sizeof(T) == 8 ? 1 : 2;
     static constexpr size_t budget = sizeof(T) == 8 ? 200 * 1024 : 100 * 1024;
 };
-// pitch (elements) between the single-column tiles of the STFT kernels: the padded tile, made odd so that the lanes of the
-// Hermitian split (which run along the tiles) start in different banks
-QI_HD int stft_tile_pitch(int R) { return pad8(R) | 1; }
+// pitch (elements) between the single-column tiles of the STFT kernels: the padded tile plus an offset that puts the lanes
+// of the Hermitian split (which run along the tiles) on different banks -- one 16-byte element for double; two 8-byte
+// elements for float, which also keeps every tile 16-byte aligned for the vector accesses of the radix-2 stage
+template <typename T> QI_HD int stft_tile_pitch(int R) { return sizeof(T) == 8 ? (pad8(R) | 1) : pad8(R) + 2; }
 
 // LOGF / LOGTC > 0: FFT length and tiles per CTA known at compile time (the common sizes: every index computation of the
 // gather, the stage loops and the Hermitian split folds to shifts and immediates; ncu of the generic kernel had a third of
@@ -43,7 +44,7 @@ stft_kernel(const T* __restrict__ sig, const T* __restrict__ window, StftGeom g0
     if (LOGF > 0) { g.logF = LOGF; g.TC = 1 << LOGTC; }
     const int R = 1 << g.logF;
     // TC single-column tiles (two real frames each) in the padded layout of tile_fft<.., true>, PT elements apart
-    const int TC = g.TC, PT = stft_tile_pitch(R);
+    const int TC = g.TC, PT = stft_tile_pitch<T>(R);
     const int logTC = 31 - __clz(TC);
     cplx<T>* tile = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* tw = tile + (size_t)TC * PT;
@@ -267,7 +268,7 @@ static int stft_impl(const void* sig, i64 C, i64 n_points, i64 stride, const voi
     // <= ~100 KB per CTA so that two CTAs (2 x 512 threads) share an SM; fall back to one big CTA for long FFTs
     size_t budget = StftLaunch<T>::budget;
     int TC = 16;
-    auto need = [&](int tc) { return ((size_t)stft_tile_pitch(nfft) * tc + nfft) * sizeof(cplx<T>) + 2 * tc * sizeof(T) + (2 * tc + 16) * sizeof(double) + 64; };
+    auto need = [&](int tc) { return ((size_t)stft_tile_pitch<T>(nfft) * tc + nfft) * sizeof(cplx<T>) + 2 * tc * sizeof(T) + (2 * tc + 16) * sizeof(double) + 64; };
     while (TC > 2 && need(TC) > budget) TC >>= 1;
     if (need(TC) > budget) { budget = 200 * 1024; while (TC > 1 && need(TC) > budget) TC >>= 1; }
     if (need(TC) > budget) return QI_ERR_UNSUPPORTED;
