@@ -70,7 +70,9 @@ def test_stft_interior_fused_path():
     from oracle import qi_oracle as orc
     k = np.arange(40000)
     x = np.random.default_rng(0).standard_normal((2, 40000)) + 3.0 + np.cos(2 * np.pi * 60 / 800 * k)
-    for seg, ov, nfft in ((256, None, None), (256, 192, 512), (128, 96, None), (300, 100, 512), (200, 150, 256), (250, 100, 256)):
+    # 512 / 1024 / 2048-point frames take the compile-time instantiations (register gather), the others the generic kernel
+    for seg, ov, nfft in ((256, None, None), (256, 192, 512), (128, 96, None), (300, 100, 512), (200, 150, 256), (250, 100, 256),
+                          (1024, None, None), (700, 300, 1024), (2048, None, None), (1500, 1100, 2048), (512, 128, None)):
         f0, t0, z0 = orc.stft_complex_pow2(x, FS, seg, ov, nfft, alpha=0.25)
         for dtype, tol in (("float64", 1e-12), ("float32", 3e-6)):
             f, t, z = styx_fft.stft_complex_pow2(x, FS, seg, ov, nfft, alpha=0.25, dtype=dtype)
