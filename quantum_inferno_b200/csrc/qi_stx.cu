@@ -64,6 +64,76 @@ __global__ void stx_windows_kernel(const DevStxBand* bands, i64 n, cplx<T>* out)
     out[(i64)blockIdx.y * n + k] = mk<T>(exp((T)-0.5 * u * u), (T)0);
 }
 
+// ---------------------------------------------------------------- overlap-save route of the widest voices
+// A voice whose window is WIDE in frequency is SHORT in time: voice(t) = exp(-2 pi i shift t / n) * (x (*) h)(t) with
+// h(t) = g_sigma(t) exp(+2 pi i shift t / n), g_sigma the (periodised) Gaussian of std sigma samples, (*) the circular
+// convolution of the reference's spectral product (styx_stx.py:233-236).  For sigma <= ~60 samples that is an
+// overlap-save convolution in 2048-sample blocks read circularly from the record: one forward transform per block, per
+// band a real response exp(-0.5 (q u)^2) / F at u = j n / F - shift (an integer: the block grid is a subset of the
+// record's) + one inverse transform in shared memory, the carrier taken out on the way to HBM.  Replaces two full-length
+// HBM passes per voice (a third of a Stockwell call at 16 x 2^18).  Truncating h at U_CUT sigma costs exp(-U_CUT^2 / 2)
+// (1.5e-7 float32, 1.3e-13 float64) of the peak, like the band-limited route.
+template <typename T>
+__global__ void __launch_bounds__(512)
+stx_os_kernel(const T* __restrict__ sig, i64 stride, CwtGeom geo, const DevStxBand* __restrict__ bands,
+              const int* __restrict__ ids, int n_os, int half, cplx<T>* __restrict__ out_c, T* __restrict__ out_p,
+              double* __restrict__ band_sum) {
+    QI_DYN_SMEM(smem_raw);
+    constexpr int logF = CWTF_OS_LOGF, F = 1 << logF;
+    const int V = F - 2 * half;
+    const int FP = pad8(F);
+    cplx<T>* tile_x = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* tile_y = tile_x + FP;
+    cplx<T>* tw = tile_y + FP;
+    double* scratch = reinterpret_cast<double*>(tw + F);
+    const i64 chan = blockIdx.y, N = geo.n_points;                  // N = 2^logL
+    const i64 n0 = (i64)blockIdx.x * V;
+    const T* xs = sig + chan * stride;
+    fill_stage_twiddles<T>(tw, logF);
+    for (int p = threadIdx.x; p < F; p += blockDim.x)
+        tile_x[padt<T>(p)] = mk<T>(xs[(n0 - half + p) & (N - 1)], (T)0);       // circular, like the reference's product
+    __syncthreads();
+    tile_fft<T, FFT_FWD, true>(tile_x, tw, logF, 1, 1);
+    const int up = geo.logL - logF;                                   // block bin j <-> record bin j << up
+    for (int i = 0; i < n_os; ++i) {
+        const int band = ids[i];
+        const DevStxBand b = bands[band];
+        for (int r = threadIdx.x; r < F; r += blockDim.x) {
+            const i64 j = (i64)brev_bits((unsigned)r, logF);
+            i64 u = ((j << up) - b.shift) & (N - 1);
+            if (u >= (N >> 1)) u -= N;                                // signed distance from the voice's centre bin
+            T w = (T)0;
+            if (u <= b.kmax && -u <= b.kmax) {
+                const T a = (T)b.q * (T)u;
+                w = exp((T)-0.5 * a * a) * (T)(1.0 / (double)F);
+            }
+            tile_y[padt<T>(r)] = tile_x[padt<T>(r)] * w;
+        }
+        __syncthreads();
+        tile_fft<T, FFT_INV, true>(tile_y, tw, logF, 1, 1);
+        const i64 row = (chan * geo.n_bands + band) * N;
+        double acc = 0.0;
+        for (int v = threadIdx.x; v < V; v += blockDim.x) {
+            const i64 n = n0 + v;
+            if (n < N) {
+                const cplx<T> y = tile_y[padt<T>(half + v)];
+                const T pw = norm2(y);
+                if (out_c) {
+                    const unsigned long long m = ((unsigned long long)b.shift * (unsigned long long)n) & (unsigned long long)(N - 1);
+                    out_c[row + n] = mul_conj(y, unit_root<T>(m, geo.logL));       // * exp(-2 pi i shift n / N), exact phase
+                }
+                if (out_p) out_p[row + n] = pw;
+                acc += (double)pw;
+            }
+        }
+        if (band_sum) {
+            acc = block_sum(acc, scratch);
+            if (threadIdx.x == 0) atomicAdd(&band_sum[chan * geo.n_bands + band], acc);
+        }
+        __syncthreads();
+    }
+}
+
 struct StxLayout { int logL; i64 L; size_t off_bands, off_spec, off_work, off_ids, off_coef, total; int group; };
 
 template <typename T> static StxLayout stx_layout(i64 C, i64 N, int B, int group) {
@@ -189,6 +259,34 @@ static int stx_fft_impl(const void* sig, i64 C, i64 N, i64 stride, const QiStxBa
                 sub += (size_t)gs;
             }
             pos = end;
+        }
+    }
+    // ---- overlap-save route: voices that are too wide to decimate and short in time
+    if (fast && lo.logL >= 13) {
+        std::vector<int> os_ids;
+        int os_half = 0;
+        for (int b = 0; b < B; ++b) {
+            if (logK[b] != lo.logL) continue;
+            const double sg = fabs(hb[b].sigma);
+            const int half = (int)ceil(Cfg::U_CUT * sg) + 2;
+            // sigma >= 2.5: the window has decayed (exp(-30)) where the signed bin index wraps, so the response on the block
+            // grid is the reference's window
+            if (sg >= 2.5 && half <= CWTF_OS_MAX_HALF) { os_ids.push_back(b); if (half > os_half) os_half = half; }
+        }
+        if (!os_ids.empty()) {
+            os_half = (os_half + 15) & ~15;
+            int* d_os = reinterpret_cast<int*>(base + lo.off_ids) + dec_ids.size();
+            stage_to_device(d_os, os_ids.data(), sizeof(int) * os_ids.size(), st);
+            for (int b : os_ids) logK[b] = -1;                          // taken: the full-length loop below skips them
+            const int F = 1 << CWTF_OS_LOGF, V = F - 2 * os_half;
+            const size_t smem = sizeof(cplx<T>) * (2 * (size_t)pad8(F) + (size_t)F) + 256;
+#ifndef QI_EMUL
+            cudaFuncSetAttribute(stx_os_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+            prof_set_category(QI_CAT_INV_LAST);
+            QI_LAUNCH((stx_os_kernel<T>), dim3((unsigned)((N + V - 1) / V), (unsigned)C), dim3(512), smem, st,
+                      static_cast<const T*>(sig), stride, geo, (const DevStxBand*)d_bands, (const int*)d_os, (int)os_ids.size(),
+                      os_half, static_cast<cplx<T>*>(out_c), static_cast<T*>(out_p), band_sum);
         }
     }
     // ---- full-length passes: maximal runs of consecutive bands that took no other route
