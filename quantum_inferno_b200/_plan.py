@@ -140,7 +140,14 @@ def stft_time_axis(ext_length, nperseg, noverlap, fs, boundary_zeros=True):
 
 
 # ----------------------------------------------------------------------------- multirate fp32 CWT
-MR_KAPPA = 4.8           # half-width (in 1/s) of the band response that must sit inside a level's alias-free band
+# Half-width (in 1/s) of the band response that must sit inside a level's alias-free band [0, pi/2] when the band's level is
+# chosen.  What has to hold is that the LAST decimation stage of the band's level neither droops nor aliases where the band
+# still answers: max over theta of |H(theta) - 1| * exp(-((theta - omega) s)^2 / 2) for the 7-tap minimax half-band filter.
+# That figure is the filter's own pass-band ripple (9.4e-7) for every half-width from 4.8 down to 2.0 (orders 1.5 ... 24;
+# the filter is still within 4e-5 of 1 at 1.06 pi/4) and rises below 2.0; the envelope decimation has its own check in
+# mr_plan (csrc/qi_mr.cu), unaffected down to 2.0.  2.4 instead of the 4.8 of round 1 moves one band per order from the
+# full-rate level 0 -- the expensive one: convolution at the full rate + a separate information pass -- to level 1.
+MR_KAPPA = 2.4
 MR_PASS = np.pi / 2      # alias-free band of every pyramid level, in radians at that level's rate
 MR_MIN_LOG2_POINTS = 13
 
