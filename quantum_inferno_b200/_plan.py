@@ -2,6 +2,8 @@
 Host-side planning (pure numpy, float64): turns the reference's call arguments into the small
 per-band parameter tables the kernels consume.  No GPU, no torch -- so it is testable anywhere.
 """
+import os
+
 import numpy as np
 
 from . import scales_dyadic as scales
@@ -147,7 +149,7 @@ def stft_time_axis(ext_length, nperseg, noverlap, fs, boundary_zeros=True):
 # the filter is still within 4e-5 of 1 at 1.06 pi/4) and rises below 2.0; the envelope decimation has its own check in
 # mr_plan (csrc/qi_mr.cu), unaffected down to 2.0.  2.4 instead of the 4.8 of round 1 moves one band per order from the
 # full-rate level 0 -- the expensive one: convolution at the full rate + a separate information pass -- to level 1.
-MR_KAPPA = 2.4
+MR_KAPPA = float(os.environ.get("QI_MR_KAPPA", "2.4"))     # the environment override is for measurements only
 MR_PASS = np.pi / 2      # alias-free band of every pyramid level, in radians at that level's rate
 MR_MIN_LOG2_POINTS = 13
 
