@@ -4,8 +4,9 @@
 //
 //   P  pyramid      x_(l+1)[q] = halfband(x_l)[2q]  (zero-phase minimax half-band FIR, |error| <= 1e-6, exact
 //                   zero extension of the record carried in a 16-sample halo).  Total work ~ N per channel.
-//   T  tables       every band lives at the deepest level l whose alias-free band [0, pi/2] still holds its whole
-//                   Gaussian response (|theta - omega| <= 4.8/s).  Its kernel at that rate,
+//   T  tables       every band lives at the deepest level l whose alias-free band [0, pi/2] still holds its response out
+//                   to |theta - omega| <= 2.4/s (the host's choice, _plan.MR_KAPPA: beyond that the last decimation
+//                   stage is still within 4e-5 of unity where the band answers with less than 6 %).  Its kernel at that rate,
 //                   2^l * psi(2^l d - 1/2) truncated like the reference's N-sample atom, is sampled in fp64,
 //                   transformed once in shared memory and kept (bit-reversed order, L2 resident) for all channels.
 //   A  level conv   overlap-save convolution of x_l with all bands of level l in 2048-point blocks

@@ -221,3 +221,30 @@ def test_band_shard_cost_balance():
     with pytest.raises(ValueError):
         distributed.band_shard(3, 0, 4)
     assert [distributed.channel_shard(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+
+
+def test_multirate_level_assignment_keeps_the_decimator_error_at_its_ripple():
+    """_plan.MR_KAPPA: a band may sit at level l if the LAST half-band decimation stage (7-tap minimax filter of
+    csrc/qi_halfband_coeffs.h) neither droops nor aliases where the band still answers -- the weighted error
+    max |H(theta) - 1| exp(-((theta - omega) s)^2 / 2) must stay at the filter's own pass-band ripple."""
+    import os
+    import re
+    from quantum_inferno_b200 import _plan, scales_dyadic as scales
+    hdr = open(os.path.join(os.path.dirname(_plan.__file__), "csrc", "qi_halfband_coeffs.h")).read()
+    taps = np.array([float(v) for v in re.search(r"qi_hb_taps\[QI_HB_CLASSES\]\[QI_HB_MAX_TAPS\] = \{\s*\{([^}]*)\}", hdr).group(1).split(",")])
+    th = np.linspace(0.0, np.pi, 4097)
+    h_err = np.abs(0.5 + 2.0 * sum(c * np.cos((2 * t + 1) * th) for t, c in enumerate(taps)) - 1.0)
+    ripple = h_err[th <= np.pi / 4].max()
+    assert ripple < 1.1e-6
+    for order, log2n in ((1.5, 20), (3, 24), (6, 22), (12, 24), (24, 20)):
+        n = 1 << log2n
+        f = scales.log_frequency_hz_from_fft_points(800.0, n, order)
+        bands, scale, omega, _ = _plan.multirate_bands(order, n, f, 800.0)
+        worst = 0.0
+        for lv, s, w in zip(bands["level"], scale, omega):
+            if lv == 0:
+                continue
+            up = 2.0 ** (int(lv) - 1)                      # the band in the units of the level the last stage reads
+            worst = max(worst, float((h_err * np.exp(-0.5 * ((th - w * up) * (s / up)) ** 2)).max()))
+            assert (w + 5.2 / s) * 2.0 ** int(lv) < np.pi  # and its kernel is representable at its own level's rate
+        assert worst < 1.5 * ripple, (order, worst, ripple)
