@@ -44,6 +44,7 @@
 
 #include <vector>
 #include <math.h>
+#include <stdlib.h>
 
 namespace qi {
 
@@ -505,7 +506,9 @@ static int mr_plan(i64 C, i64 N, const QiMrBand* hb, int B, MrPlan& pl, bool all
                 const double wc = hb[b].omega * (double)(1ll << (l + 1));             // centre at level l + 1
                 const int kd = (int)llround(wc * 64.0 / (2.0 * M_PI));
                 const double dev = fabs(wc - 2.0 * M_PI * kd / 64.0);
-                const double halfbw = 4.8 / (hb[b].scale / (double)(1ll << (l + 1)));
+                // QI_MR_ENV_KAPPA: measurement override of the envelope half-width ("what is next")
+                static const double env_kappa = getenv("QI_MR_ENV_KAPPA") ? atof(getenv("QI_MR_ENV_KAPPA")) : 4.8;
+                const double halfbw = env_kappa / (hb[b].scale / (double)(1ll << (l + 1)));
                 if (halfbw + dev > 0.98 * M_PI / 2.0 || wc + halfbw >= 2.0 * M_PI) g.env = 0;
                 demod[b - first] = kd & 63;
             }

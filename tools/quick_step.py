@@ -55,7 +55,7 @@ out = {"label": label, "ms_per_step": e0.elapsed_time(e1) / steps,
        "entropy_bits_ch0": float(r.entropy_bits()[0].item())}
 if os.environ.get("QI_QUICK_CHECK", "1") != "0":
     # one channel, exact float32 method on three rows
-    rows = [nb - 1, nb - 5, nb - 8, nb - 11, 20]
+    rows = [nb - 1, nb - 5, nb - 7, nb - 8, nb - 10, nb - 11, 20]
     ex = cwt_entropy.cwt_power_entropy(ORDER, x[:1], FS, dtype="float32", method="exact", want_info=False)
     l2 = {}
     for b in rows:
